@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's Go API for the hot path, over the C ABI.
+
+Same names, argument meaning and guard behaviour as the Go functions (file:line cited per
+function), so the parity tests read like fennec_test.go.  Images are numpy uint8 arrays of shape
+(h, w, 4) — NRGBA, `arr.strides[0]` plays image.NRGBA.Stride.  Where the reference returns its
+input pointer unchanged, the SAME array object is returned.
+
+Every function goes through libfennec_b200.so; there is no NumPy/CPU compute path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import FB_IDENTITY, FbWeights, check, dp, ip, u8p
+
+
+def _img(a: np.ndarray):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 4):
+        raise TypeError("expected a uint8 array of shape (h, w, 4) (NRGBA)")
+    if a.size and (a.strides[2] != 1 or a.strides[1] != 4):
+        raise ValueError("pixels must be interleaved NRGBA bytes")
+    h, w = a.shape[:2]
+    stride = int(a.strides[0]) if h > 1 else w * 4
+    return a.ctypes.data_as(u8p), stride, w, h
+
+
+def _new(h: int, w: int) -> np.ndarray:
+    return np.zeros((h, w, 4), dtype=np.uint8)  # image.NewNRGBA zero-fills
+
+
+def _empty() -> np.ndarray:
+    return np.zeros((0, 0, 4), dtype=np.uint8)  # image.NewNRGBA(image.Rect(0,0,0,0))
+
+
+def device_count() -> int:
+    return _lib.load().fb_device_count()
+
+
+def version() -> str:
+    return _lib.load().fb_version().decode()
+
+
+def set_device(device: int) -> None:
+    check(_lib.load().fb_set_device(device))
+
+
+# ---- resize.go ---------------------------------------------------------------------------------
+
+def lanczos_weights(dst_size: int, src_size: int):
+    """precomputeWeights (resize.go:164-197) as CSR arrays (start, index, weight)."""
+    L = _lib.load()
+    cap = L.fb_lanczos_weights_cap(dst_size, src_size)
+    start = np.zeros(dst_size + 1, dtype=np.int32)
+    index = np.zeros(cap + 1, dtype=np.int32)
+    weight = np.zeros(cap + 1, dtype=np.float64)
+    n = check(L.fb_build_lanczos_weights(dst_size, src_size, start.ctypes.data_as(ip), index.ctypes.data_as(ip),
+                                         weight.ctypes.data_as(dp)))
+    return start, index[:n].copy(), weight[:n].copy()
+
+
+def _weights_struct(tab) -> Tuple[FbWeights, tuple]:
+    start, index, weight = (np.ascontiguousarray(tab[0], dtype=np.int32), np.ascontiguousarray(tab[1], dtype=np.int32),
+                            np.ascontiguousarray(tab[2], dtype=np.float64))
+    w = FbWeights(len(start) - 1, start.ctypes.data_as(ip), index.ctypes.data_as(ip), weight.ctypes.data_as(dp))
+    return w, (start, index, weight)
+
+
+def lanczos_resize(img: np.ndarray, dst_w: int, dst_h: int, weights_x=None, weights_y=None) -> np.ndarray:
+    """lanczosResize (resize.go:37-53). weights_* optionally carry caller-built CSR tables."""
+    ps, ss, sw, sh = _img(img)
+    if sw <= 0 or sh <= 0 or dst_w <= 0 or dst_h <= 0:
+        return _empty()  # resize.go:41-43
+    dst = _new(dst_h, dst_w)
+    pd, sd, _, _ = _img(dst)
+    wx = wy = None
+    keep = []
+    if weights_x is not None:
+        wx, k = _weights_struct(weights_x)
+        keep.append(k)
+    if weights_y is not None:
+        wy, k = _weights_struct(weights_y)
+        keep.append(k)
+    check(_lib.load().fb_lanczos_resize(ps, ss, sw, sh, pd, sd, dst_w, dst_h,
+                                        C.byref(wx) if wx is not None else None,
+                                        C.byref(wy) if wy is not None else None))
+    return dst
+
+
+def smart_resize(img: np.ndarray, max_w: int, max_h: int) -> np.ndarray:
+    """smartResize (resize.go:12-32): returns `img` itself when it already fits."""
+    _, _, sw, sh = _img(img)
+    dw, dh = C.c_int(), C.c_int()
+    if _lib.load().fb_smart_resize_dims(sw, sh, max_w, max_h, C.byref(dw), C.byref(dh)) == 1:
+        return img
+    return lanczos_resize(img, dw.value, dh.value)
+
+
+# ---- ssim.go ------------------------------------------------------------------------------------
+
+def _score(fn, a: np.ndarray, b: np.ndarray) -> float:
+    pa, sa, w, h = _img(a)
+    pb, sb, wb, hb = _img(b)
+    if (w, h) != (wb, hb):
+        raise ValueError("images must have equal dimensions")
+    out = C.c_double()
+    check(fn(pa, sa, pb, sb, w, h, C.byref(out)))
+    return out.value
+
+
+def SSIM(img1: np.ndarray, img2: np.ndarray) -> float:
+    """fennec.SSIM (ssim.go:24-43): resizes img2 to img1's dims if they differ (ssim.go:31-33)."""
+    h, w = img1.shape[:2]
+    if img2.shape[:2] != (h, w):
+        img2 = lanczos_resize(img2, w, h)
+    return _score(_lib.load().fb_ssim, img1, img2)
+
+
+def SSIMFast(img1: np.ndarray, img2: np.ndarray) -> float:
+    """fennec.SSIMFast (ssim.go:48-70). Like the reference, equal dims are the caller's business."""
+    return _score(_lib.load().fb_ssim_fast, img1, img2)
+
+
+def MSSSIM(img1: np.ndarray, img2: np.ndarray) -> float:
+    """fennec.MSSSIM (ssim.go:313-365)."""
+    h, w = img1.shape[:2]
+    if img2.shape[:2] != (h, w):
+        img2 = lanczos_resize(img2, w, h)
+    return _score(_lib.load().fb_msssim, img1, img2)
+
+
+def pixel_ssim(a: np.ndarray, b: np.ndarray) -> float:
+    """pixelSSIM (ssim.go:169-204)."""
+    return _score(_lib.load().fb_pixel_ssim, a, b)
+
+
+def box_downsample(img: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
+    """boxDownsample (ssim.go:244-309)."""
+    ps, ss, sw, sh = _img(img)
+    if sw <= 0 or sh <= 0 or dst_w <= 0 or dst_h <= 0:
+        return _empty()
+    dst = _new(dst_h, dst_w)
+    pd, sd, _, _ = _img(dst)
+    check(_lib.load().fb_box_downsample(ps, ss, sw, sh, pd, sd, dst_w, dst_h))
+    return dst
+
+
+def ssim_fast_dims(w: int, h: int):
+    nw, nh = C.c_int(), C.c_int()
+    did = _lib.load().fb_ssim_fast_dims(w, h, C.byref(nw), C.byref(nh))
+    return bool(did), nw.value, nh.value
+
+
+# ---- effects.go ---------------------------------------------------------------------------------
+
+def blur_kernel(sigma: float):
+    """The 1-D kernel of effects.go:153-165 → (weights, radius)."""
+    if not sigma > 0:
+        raise ValueError("sigma must be > 0")
+    L = _lib.load()
+    need = -L.fb_blur_kernel(float(sigma), None, 0)
+    k = np.zeros(need, dtype=np.float64)
+    radius = check(L.fb_blur_kernel(float(sigma), k.ctypes.data_as(dp), need))
+    return k, radius
+
+
+def GaussianBlur(img: np.ndarray, sigma: float, kernel: Optional[np.ndarray] = None) -> np.ndarray:
+    """fennec.GaussianBlur (effects.go:146-220). sigma <= 0 → the same array (effects.go:147-149).
+    `kernel` lets the caller supply the weight table it built with its own libm."""
+    if sigma <= 0:
+        return img
+    ps, ss, w, h = _img(img)
+    dst = _new(h, w)
+    pd, sd, _, _ = _img(dst)
+    if kernel is None:
+        check(_lib.load().fb_gaussian_blur_sigma(ps, ss, w, h, float(sigma), pd, sd))
+    else:
+        k = np.ascontiguousarray(kernel, dtype=np.float64)
+        check(_lib.load().fb_gaussian_blur(ps, ss, w, h, k.ctypes.data_as(dp), (len(k) - 1) // 2, pd, sd))
+    return dst
+
+
+def blur3x3(img: np.ndarray) -> np.ndarray:
+    """gaussianBlur3x3 (effects.go:116-141)."""
+    ps, ss, w, h = _img(img)
+    dst = _new(h, w)
+    pd, sd, _, _ = _img(dst)
+    check(_lib.load().fb_blur3x3(ps, ss, w, h, pd, sd))
+    return dst
+
+
+def _fx(fn, img: np.ndarray, strength: float) -> np.ndarray:
+    ps, ss, w, h = _img(img)
+    dst = _new(h, w)
+    pd, sd, _, _ = _img(dst)
+    if check(fn(ps, ss, w, h, float(strength), pd, sd)) == FB_IDENTITY:
+        return img  # same pointer (effects.go:11-22 / 50-61)
+    return dst
+
+
+def Sharpen(img: np.ndarray, strength: float) -> np.ndarray:
+    """fennec.Sharpen (effects.go:10-45)."""
+    return _fx(_lib.load().fb_sharpen, img, strength)
+
+
+def AdaptiveSharpen(img: np.ndarray, strength: float) -> np.ndarray:
+    """fennec.AdaptiveSharpen (effects.go:49-90)."""
+    return _fx(_lib.load().fb_adaptive_sharpen, img, strength)

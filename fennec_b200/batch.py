@@ -1,0 +1,180 @@
+"""Device-resident batch entry points and the batch sharder (batch.go:58-128), over the C ABI.
+
+torch is plumbing only: device memory (uint8 tensors), the current CUDA stream handed to the
+library, and torch.distributed for the result gather.  Batches are tensors of shape (n, h, w, 4),
+uint8, on a CUDA device; image i is the NRGBA buffer at data_ptr() + i*stride(0).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FB_IDENTITY, check, dp
+
+
+def _batch(t: torch.Tensor):
+    if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 4):
+        raise TypeError("expected a CUDA uint8 tensor of shape (n, h, w, 4)")
+    if t.stride(3) != 1 or t.stride(2) != 4:
+        raise ValueError("pixels must be interleaved NRGBA bytes")
+    n, h, w, _ = t.shape
+    return t.data_ptr(), int(t.stride(0)), int(t.stride(1)), w, h, n
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dev(t: torch.Tensor) -> int:
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _scores(fn, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor]) -> torch.Tensor:
+    pa, ia, ra, w, h, n = _batch(a)
+    pb, ib, rb, wb, hb, nb = _batch(b)
+    if (ia, ra, w, h, n) != (ib, rb, wb, hb, nb):
+        raise ValueError("a and b must have identical shapes and strides")
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=a.device)
+    check(fn(_dev(a), _stream(a), pa, pb, ia, ra, w, h, n, out.data_ptr()))
+    return out
+
+
+def ssim_batch(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fennec.SSIM for n device-resident pairs (ssim.go:24-43) → float64 scores on the device."""
+    return _scores(_lib.load().fb_ssim_batch_dev, a, b, out)
+
+
+def ssim_fast_batch(a, b, out=None) -> torch.Tensor:
+    """fennec.SSIMFast per pair (ssim.go:48-70)."""
+    return _scores(_lib.load().fb_ssim_fast_batch_dev, a, b, out)
+
+
+def msssim_batch(a, b, out=None) -> torch.Tensor:
+    """fennec.MSSSIM per pair (ssim.go:313-365)."""
+    return _scores(_lib.load().fb_msssim_batch_dev, a, b, out)
+
+
+def box_downsample_batch(src: torch.Tensor, dst_w: int, dst_h: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    ps, i_s, rs, w, h, n = _batch(src)
+    if out is None:
+        out = torch.zeros((n, dst_h, dst_w, 4), dtype=torch.uint8, device=src.device)
+    pd, i_d, rd, _, _, _ = _batch(out)
+    check(_lib.load().fb_box_downsample_batch_dev(_dev(src), _stream(src), ps, i_s, rs, w, h, pd, i_d, rd, dst_w, dst_h, n))
+    return out
+
+
+def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Tensor] = None,
+                        kernel: Optional[np.ndarray] = None) -> torch.Tensor:
+    """fennec.GaussianBlur per image (effects.go:146-220); sigma <= 0 returns `src` itself."""
+    if sigma <= 0:
+        return src
+    from .api import blur_kernel
+    if kernel is None:
+        kernel, radius = blur_kernel(sigma)
+    else:
+        kernel = np.ascontiguousarray(kernel, dtype=np.float64)
+        radius = (len(kernel) - 1) // 2
+    ps, i_s, rs, w, h, n = _batch(src)
+    if out is None:
+        out = torch.empty_like(src)
+    check(_lib.load().fb_gaussian_blur_batch_dev(_dev(src), _stream(src), ps, out.data_ptr(), i_s, rs, w, h, n,
+                                                 kernel.ctypes.data_as(dp), radius))
+    return out
+
+
+def _fx(fn, src, strength, out):
+    ps, i_s, rs, w, h, n = _batch(src)
+    if out is None:
+        out = torch.empty_like(src)
+    if check(fn(_dev(src), _stream(src), ps, out.data_ptr(), i_s, rs, w, h, n, float(strength))) == FB_IDENTITY:
+        return src
+    return out
+
+
+def sharpen_batch(src: torch.Tensor, strength: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fennec.Sharpen per image (effects.go:10-45)."""
+    return _fx(_lib.load().fb_sharpen_batch_dev, src, strength, out)
+
+
+def adaptive_sharpen_batch(src, strength, out=None) -> torch.Tensor:
+    """fennec.AdaptiveSharpen per image (effects.go:49-90)."""
+    return _fx(_lib.load().fb_adaptive_sharpen_batch_dev, src, strength, out)
+
+
+def lanczos_resize_batch(src: torch.Tensor, dst_w: int, dst_h: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """lanczosResize per image (resize.go:37-53)."""
+    ps, i_s, rs, w, h, n = _batch(src)
+    if out is None:
+        out = torch.zeros((n, dst_h, dst_w, 4), dtype=torch.uint8, device=src.device)
+    pd, i_d, rd, _, _, _ = _batch(out)
+    check(_lib.load().fb_lanczos_resize_batch_dev(_dev(src), _stream(src), ps, i_s, rs, w, h, pd, i_d, rd, dst_w, dst_h, n))
+    return out
+
+
+def take_launch_count() -> int:
+    return int(_lib.load().fb_take_launch_count())
+
+
+# ---- sharder: the part of CompressBatch (batch.go:58-128) that moves to the GPUs ----------------------
+
+def shard_range(n_items: int, n_shards: int, shard: int):
+    """Static contiguous partition: shard s owns [begin, end)."""
+    b, e = C.c_int(), C.c_int()
+    check(_lib.load().fb_batch_shard(n_items, n_shards, shard, C.byref(b), C.byref(e)))
+    return b.value, e.value
+
+
+@dataclass
+class BatchResult:
+    """batch.go:21-30"""
+    item: object
+    result: object = None
+    err: Optional[BaseException] = None
+    index: int = 0
+
+
+def run_sharded(items: Sequence, work: Callable[[object], object], *, rank: int = 0, world: int = 1,
+                cancelled: Callable[[], bool] = lambda: False,
+                on_item: Optional[Callable[[int, int], None]] = None) -> List[Optional[BatchResult]]:
+    """The worker loop of CompressBatch (batch.go:84-124) for ONE shard: results keep the input index,
+    a cancelled context marks unstarted items with an error instead of running them (batch.go:90-98),
+    one failing item does not stop the rest (batch.go:107-113), on_item(completed, total) fires after
+    each item (batch.go:115-121).  Items owned by other shards are left as None for the gather."""
+    total = len(items)
+    out: List[Optional[BatchResult]] = [None] * total
+    if total == 0:
+        return out
+    begin, end = shard_range(total, world, rank)
+    completed = 0
+    for idx in range(begin, end):
+        if cancelled():
+            out[idx] = BatchResult(items[idx], None, RuntimeError("context canceled"), idx)
+            continue
+        try:
+            out[idx] = BatchResult(items[idx], work(items[idx]), None, idx)
+        except Exception as e:  # per-item isolation
+            out[idx] = BatchResult(items[idx], None, e, idx)
+        if on_item is not None:
+            completed += 1
+            on_item(completed, total)
+    return out
+
+
+def gather_scores(local: torch.Tensor, n_items: int, world: int, rank: int) -> torch.Tensor:
+    """All-gather the per-shard float64 scores into input order. The only collective of the path:
+    per-image work is embarrassingly parallel. Works on nccl (CUDA) and gloo (CPU)."""
+    import torch.distributed as dist
+    if world == 1:
+        return local
+    per = (n_items + world - 1) // world
+    padded = torch.zeros(per, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat(parts)[:n_items]

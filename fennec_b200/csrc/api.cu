@@ -1,0 +1,968 @@
+// api.cu — the C ABI of libfennec_b200.so (include/fennec_b200.h): lifecycle, per-thread contexts,
+// host-buffer entry points (H2D → kernels → D2H, synchronous like the Go functions they replace),
+// device-resident batch entry points, and the host-side table builders / dimension rules that sit on
+// the host side of the boundary.  No CPU compute fallback lives here: without a GPU every compute
+// entry point fails with FB_E_NOGPU.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+namespace fb {
+
+// ---- errors ---------------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+thread_local long long t_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    if (e == cudaErrorMemoryAllocation) return FB_E_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return FB_E_NOGPU;
+    return FB_E_CUDA;
+}
+
+// ---- global init ------------------------------------------------------------------------------
+static std::mutex g_mu;
+static bool g_inited = false;
+static std::vector<int> g_devices;
+static thread_local int t_device = 0;
+
+static int init_locked(const int *devices, int n) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no usable CUDA device (cudaGetDeviceCount: %s); libfennec_b200 has no CPU fallback",
+                  e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return FB_E_NOGPU;
+    }
+    std::vector<int> devs;
+    if (n <= 0 || devices == nullptr) {
+        for (int i = 0; i < count; i++) devs.push_back(i);
+    } else {
+        for (int i = 0; i < n; i++) {
+            if (devices[i] < 0 || devices[i] >= count) {
+                set_error("fb_init: device %d out of range (0..%d)", devices[i], count - 1);
+                return FB_E_INVALID;
+            }
+            devs.push_back(devices[i]);
+        }
+    }
+    g_devices = devs;
+    g_inited = true;
+    return (int)g_devices.size();
+}
+
+int ensure_init() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited) return (int)g_devices.size();
+    return init_locked(nullptr, 0);
+}
+
+int device_count() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_inited ? (int)g_devices.size() : 0;
+}
+
+int current_device() { return t_device; }
+
+// ---- per-thread contexts ------------------------------------------------------------------------
+struct TableKey {
+    int kind, a, b;
+    bool operator<(const TableKey &o) const {
+        if (kind != o.kind) return kind < o.kind;
+        if (a != o.a) return a < o.a;
+        return b < o.b;
+    }
+};
+struct LanczosTable {
+    int *start = nullptr;
+    int *index = nullptr;
+    double *weight = nullptr;
+    int entries = 0, maxTaps = 0;
+};
+struct ThreadState {
+    std::vector<DevCtx> ctxs;
+    std::vector<bool> pinBusy;
+    std::map<std::pair<int, TableKey>, LanczosTable> lanczos;  // (device, key) → device tables
+    ~ThreadState() {
+        // Streams and arenas are reclaimed by fb_shutdown / process exit; destroying CUDA objects from
+        // a thread destructor can race with runtime teardown, so we deliberately leave them.
+    }
+};
+static thread_local ThreadState t_state;
+
+DevCtx *ctx(int dev) {
+    int nd = ensure_init();
+    if (nd < 0) return nullptr;
+    if (dev < 0 || dev >= nd) {
+        set_error("device index %d out of range (fb_init selected %d device(s))", dev, nd);
+        return nullptr;
+    }
+    if ((int)t_state.ctxs.size() < nd) {
+        t_state.ctxs.resize(nd);
+        t_state.pinBusy.resize(nd, false);
+    }
+    DevCtx *c = &t_state.ctxs[dev];
+    int phys;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        phys = g_devices[dev];
+    }
+    if (cudaSetDevice(phys) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+        return nullptr;
+    }
+    if (c->dev < 0) {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess) {
+            cuda_fail(cudaGetLastError(), "stream/event creation", __FILE__, __LINE__);
+            return nullptr;
+        }
+        c->dev = dev;
+    }
+    return c;
+}
+
+int reserve(DevCtx *c, size_t dev_bytes, size_t pinned_bytes) {
+    // The pinned arena may still feed an async H2D enqueued by a previous _dev call.
+    if (t_state.pinBusy[c->dev]) {
+        FB_CUDA(cudaEventSynchronize(c->ev));
+        t_state.pinBusy[c->dev] = false;
+    }
+    dev_bytes += 4096;
+    pinned_bytes += 4096;
+    if (c->ws.cap < dev_bytes) {
+        FB_CUDA(cudaDeviceSynchronize());  // enqueued work may still use the old buffer
+        if (c->ws.base) FB_CUDA(cudaFree(c->ws.base));
+        c->ws.base = nullptr;
+        c->ws.cap = 0;
+        size_t want = dev_bytes + dev_bytes / 4;
+        void *ptr = nullptr;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = dev_bytes;
+            e = cudaMalloc(&ptr, want);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)", __FILE__, __LINE__);
+        c->ws.base = (char *)ptr;
+        c->ws.cap = want;
+    }
+    if (c->pin.cap < pinned_bytes) {
+        FB_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->pin.base) FB_CUDA(cudaFreeHost(c->pin.base));
+        c->pin.base = nullptr;
+        c->pin.cap = 0;
+        void *ptr = nullptr;
+        FB_CUDA(cudaMallocHost(&ptr, pinned_bytes * 2));
+        c->pin.base = (char *)ptr;
+        c->pin.cap = pinned_bytes * 2;
+    }
+    c->ws.reset();
+    c->pin.reset();
+    return FB_OK;
+}
+
+static void mark_pin_busy(DevCtx *c, cudaStream_t s) {
+    cudaEventRecord(c->ev, s);
+    t_state.pinBusy[c->dev] = true;
+}
+
+// ---- host-side rules and table builders (host side of the boundary) -----------------------------
+
+// ssim.go:52-56
+static int ssim_fast_dims(int w, int h, int *nw, int *nh) {
+    const int maxDim = 512;
+    if (w > maxDim || h > maxDim) {
+        double scale = (double)maxDim / fmax((double)w, (double)h);
+        *nw = (int)fmax(8.0, round((double)w * scale));
+        *nh = (int)fmax(8.0, round((double)h * scale));
+        return 1;
+    }
+    *nw = w;
+    *nh = h;
+    return 0;
+}
+
+// resize.go:55-69
+static double lanczos_kernel(double x) {
+    if (x == 0) return 1.0;
+    if (x < 0) x = -x;
+    if (x >= 3.0) return 0.0;
+    double xpi = x * M_PI;
+    return (3.0 * sin(xpi) * sin(xpi / 3.0)) / (xpi * xpi);
+}
+
+static void lanczos_geom(int dstSize, int srcSize, double *ratio, double *support, double *fscale) {
+    *ratio = (double)srcSize / (double)dstSize;  // resize.go:81-85
+    *support = 3.0;
+    if (*ratio > 1) *support = 3.0 * *ratio;
+    *fscale = fmax(*ratio, 1.0);  // resize.go:166
+}
+
+static void lanczos_span(int d, int srcSize, double ratio, double support, double *center, int *left, int *right) {
+    *center = ((double)d + 0.5) * ratio - 0.5;  // resize.go:169-178
+    *left = (int)ceil(*center - support);
+    *right = (int)floor(*center + support);
+    if (*left < 0) *left = 0;
+    if (*right >= srcSize) *right = srcSize - 1;
+}
+
+static int lanczos_cap(int dstSize, int srcSize) {
+    if (dstSize <= 0 || srcSize <= 0) return 0;
+    double ratio, support, fscale, center;
+    lanczos_geom(dstSize, srcSize, &ratio, &support, &fscale);
+    long long cap = 0;
+    for (int d = 0; d < dstSize; d++) {
+        int l, r;
+        lanczos_span(d, srcSize, ratio, support, &center, &l, &r);
+        if (r >= l) cap += r - l + 1;
+    }
+    return cap > 0x7fffffff ? 0x7fffffff : (int)cap;
+}
+
+// resize.go:164-197
+static int lanczos_build(int dstSize, int srcSize, int *start, int *index, double *weight) {
+    double ratio, support, fscale, center;
+    lanczos_geom(dstSize, srcSize, &ratio, &support, &fscale);
+    int n = 0;
+    for (int d = 0; d < dstSize; d++) {
+        int l, r;
+        lanczos_span(d, srcSize, ratio, support, &center, &l, &r);
+        start[d] = n;
+        double wsum = 0.0;
+        int first = n;
+        for (int s = l; s <= r; s++) {
+            double w = lanczos_kernel(((double)s - center) / fscale);
+            if (w != 0) {
+                wsum += w;
+                index[n] = s;
+                weight[n] = w;
+                n++;
+            }
+        }
+        if (wsum != 0)
+            for (int i = first; i < n; i++) weight[i] /= wsum;
+    }
+    start[dstSize] = n;
+    return n;
+}
+
+// Upload a CSR table into persistent device memory of this thread's context (cached per dims when
+// the library built it; caller-supplied tables are uploaded per call into the arena instead).
+static int lanczos_table_cached(DevCtx *c, int dstSize, int srcSize, LanczosTable *out) {
+    std::pair<int, TableKey> key{c->dev, TableKey{1, dstSize, srcSize}};
+    auto it = t_state.lanczos.find(key);
+    if (it != t_state.lanczos.end()) {
+        *out = it->second;
+        return FB_OK;
+    }
+    int cap = lanczos_cap(dstSize, srcSize);
+    std::vector<int> start(dstSize + 1), index(cap + 1);
+    std::vector<double> weight(cap + 1);
+    int n = lanczos_build(dstSize, srcSize, start.data(), index.data(), weight.data());
+    LanczosTable t;
+    t.entries = n;
+    for (int d = 0; d < dstSize; d++) t.maxTaps = std::max(t.maxTaps, start[d + 1] - start[d]);
+    FB_CUDA(cudaMalloc((void **)&t.start, sizeof(int) * (dstSize + 1)));
+    FB_CUDA(cudaMalloc((void **)&t.index, sizeof(int) * (n + 1)));
+    FB_CUDA(cudaMalloc((void **)&t.weight, sizeof(double) * (n + 1)));
+    FB_CUDA(cudaMemcpy(t.start, start.data(), sizeof(int) * (dstSize + 1), cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(t.index, index.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(t.weight, weight.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    t_state.lanczos[key] = t;
+    *out = t;
+    return FB_OK;
+}
+
+// effects.go:153-165
+static int blur_kernel_host(double sigma, std::vector<double> &k) {
+    int radius = (int)ceil(sigma * 3);
+    int size = radius * 2 + 1;
+    k.resize(size);
+    double sum = 0.0;
+    for (int i = 0; i < size; i++) {
+        double x = (double)(i - radius);
+        k[i] = exp(-(x * x) / (2 * sigma * sigma));
+        sum += k[i];
+    }
+    for (int i = 0; i < size; i++) k[i] /= sum;
+    return radius;
+}
+
+// MSSSIM level plan (ssim.go:324-362): which levels are scored, their dims and weights.
+struct MsLevel { int w, h; double weight; };
+static std::vector<MsLevel> msssim_plan(int w0, int h0) {
+    double weights[5] = {0.0448, 0.2856, 0.3001, 0.2363, 0.1333};
+    int nweights = 5, w = w0, h = h0;
+    for (int i = 0; i < 4; i++) {
+        int minDim = (int)fmin((double)w, (double)h);
+        if (minDim < 8) {
+            nweights = i + 1;
+            double sum = 0.0;
+            for (int j = 0; j < nweights; j++) sum += weights[j];
+            for (int j = 0; j < nweights; j++) weights[j] /= sum;
+            break;
+        }
+        w /= 2;
+        h /= 2;
+    }
+    std::vector<MsLevel> plan;
+    int cw = w0, ch = h0;
+    for (int i = 0; i < nweights; i++) {
+        plan.push_back({cw, ch, weights[i]});
+        if (i < nweights - 1) {
+            int nw = cw / 2, nh = ch / 2;
+            if (nw < 8 || nh < 8) break;  // ssim.go:356-358 — later weights are simply never used
+            cw = nw;
+            ch = nh;
+        }
+    }
+    return plan;
+}
+
+// ---- device pipelines (shared by host and _dev entry points) --------------------------------------
+
+struct ImgBatch {  // n images of identical dims in device memory
+    const uint8_t *p;
+    long long imgStride;
+    int rowStride;
+};
+
+static size_t ssim_fast_scratch(int w, int h, int n) {
+    int nw, nh;
+    size_t bytes = 0;
+    if (ssim_fast_dims(w, h, &nw, &nh)) bytes += 2 * align_up((size_t)dev_pitch(nw) * nh * n, 256);
+    bytes += ssim_scratch_bytes(nw, nh, n);
+    return bytes + 1024;
+}
+
+// SSIMFast on device images: scores[i*scoreStride] (ssim.go:48-70).
+static int pipeline_ssim_fast(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, int w, int h, int n,
+                              double *scores, long long scoreStride) {
+    int nw, nh;
+    if (ssim_fast_dims(w, h, &nw, &nh)) {
+        int pitch = dev_pitch(nw);
+        long long imgBytes = (long long)pitch * nh;
+        uint8_t *da = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+        uint8_t *db = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+        if (!da || !db) { set_error("internal: workspace under-reserved (ssim_fast)"); return FB_E_INVALID; }
+        FB_TRY(launch_box(s, a.p, a.imgStride, a.rowStride, w, h, da, imgBytes, pitch, nw, nh, n, nullptr));
+        FB_TRY(launch_box(s, b.p, b.imgStride, b.rowStride, w, h, db, imgBytes, pitch, nw, nh, n, nullptr));
+        a = ImgBatch{da, imgBytes, pitch};
+        b = ImgBatch{db, imgBytes, pitch};
+        w = nw;
+        h = nh;
+    }
+    void *scratch = c->ws.take(ssim_scratch_bytes(w, h, n));
+    if (!scratch) { set_error("internal: workspace under-reserved (ssim)"); return FB_E_INVALID; }
+    return launch_ssim(c, s, a.p, b.p, a.imgStride, b.imgStride, a.rowStride, b.rowStride, w, h, n, scores,
+                       scoreStride, scratch);
+}
+
+static size_t msssim_scratch(int w, int h, int n) {
+    std::vector<MsLevel> plan = msssim_plan(w, h);
+    size_t bytes = 0, fast = 0;
+    for (size_t l = 0; l < plan.size(); l++) {
+        if (l > 0) bytes += 2 * align_up((size_t)dev_pitch(plan[l].w) * plan[l].h * n, 256);
+        fast = std::max(fast, ssim_fast_scratch(plan[l].w, plan[l].h, n));
+    }
+    bytes += fast * plan.size();  // arena is bump-only within a call
+    bytes += align_up(sizeof(double) * (size_t)n * 5, 256) * 2 + 1024;
+    return bytes;
+}
+
+// MSSSIM on device images (ssim.go:313-365); weights table uploaded through the pinned arena.
+static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, int w, int h, int n, double *out) {
+    std::vector<MsLevel> plan = msssim_plan(w, h);
+    const int L = (int)plan.size();
+    double *levelScores = (double *)c->ws.take(sizeof(double) * (size_t)n * L);
+    double *wdev = (double *)c->ws.take(sizeof(double) * 8);
+    double *wpin = (double *)c->pin.take(sizeof(double) * 8);
+    if (!levelScores || !wdev || !wpin) { set_error("internal: workspace under-reserved (msssim)"); return FB_E_INVALID; }
+    for (int l = 0; l < L; l++) wpin[l] = plan[l].weight;
+    FB_CUDA(cudaMemcpyAsync(wdev, wpin, sizeof(double) * L, cudaMemcpyHostToDevice, s));
+    mark_pin_busy(c, s);
+    ImgBatch ca = a, cb = b;
+    for (int l = 0; l < L; l++) {
+        FB_TRY(pipeline_ssim_fast(c, s, ca, cb, plan[l].w, plan[l].h, n, levelScores + l, L));
+        if (l + 1 < L) {  // 2x box cascade (ssim.go:354-360)
+            int nw = plan[l + 1].w, nh = plan[l + 1].h;
+            int pitch = dev_pitch(nw);
+            long long imgBytes = (long long)pitch * nh;
+            uint8_t *na = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+            uint8_t *nb = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+            if (!na || !nb) { set_error("internal: workspace under-reserved (msssim level)"); return FB_E_INVALID; }
+            FB_TRY(launch_box(s, ca.p, ca.imgStride, ca.rowStride, plan[l].w, plan[l].h, na, imgBytes, pitch, nw, nh, n, nullptr));
+            FB_TRY(launch_box(s, cb.p, cb.imgStride, cb.rowStride, plan[l].w, plan[l].h, nb, imgBytes, pitch, nw, nh, n, nullptr));
+            ca = ImgBatch{na, imgBytes, pitch};
+            cb = ImgBatch{nb, imgBytes, pitch};
+        }
+    }
+    return launch_msssim_combine(s, levelScores, L, n, wdev, out);
+}
+
+// ---- host-buffer plumbing ---------------------------------------------------------------------------
+
+static int check_img(const char *fn, const void *p, int stride, int w, int h) {
+    if (w < 0 || h < 0) { set_error("%s: negative dimensions %dx%d", fn, w, h); return FB_E_INVALID; }
+    if (w > 0 && h > 0) {
+        if (!p) { set_error("%s: null pixel pointer", fn); return FB_E_INVALID; }
+        if (stride < w * 4) { set_error("%s: stride %d < 4*w (%d)", fn, stride, w * 4); return FB_E_INVALID; }
+    }
+    return FB_OK;
+}
+
+static int upload(DevCtx *c, const uint8_t *host, int stride, int w, int h, uint8_t **dev, int *pitch) {
+    *pitch = dev_pitch(w);
+    *dev = (uint8_t *)c->ws.take((size_t)*pitch * h + 16);
+    if (!*dev) { set_error("internal: workspace under-reserved (upload)"); return FB_E_INVALID; }
+    FB_CUDA(cudaMemcpy2DAsync(*dev, *pitch, host, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, c->stream));
+    return FB_OK;
+}
+
+static int download(DevCtx *c, const uint8_t *dev, int pitch, uint8_t *host, int stride, int w, int h) {
+    FB_CUDA(cudaMemcpy2DAsync(host, stride, dev, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, c->stream));
+    return FB_OK;
+}
+
+static int finish_score(DevCtx *c, const double *dscore, double *out) {
+    double *pin = (double *)c->pin.take(sizeof(double));
+    if (!pin) { set_error("internal: pinned arena under-reserved"); return FB_E_INVALID; }
+    FB_CUDA(cudaMemcpyAsync(pin, dscore, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = *pin;
+    return FB_OK;
+}
+
+enum ScoreOp { OP_SSIM, OP_SSIM_FAST, OP_MSSSIM, OP_PIXEL };
+
+static int host_score(const char *fn, ScoreOp op, const uint8_t *a, int strideA, const uint8_t *b, int strideB,
+                      int w, int h, double *out) {
+    if (!out) { set_error("%s: null output pointer", fn); return FB_E_INVALID; }
+    FB_TRY(check_img(fn, a, strideA, w, h));
+    FB_TRY(check_img(fn, b, strideB, w, h));
+    if (w == 0 || h == 0) {  // pixelSSIM with n == 0 (ssim.go:172-175); MSSSIM: exp(1.0 * ln(1)) = 1
+        *out = 1.0;
+        return FB_OK;
+    }
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    size_t img = (size_t)dev_pitch(w) * h + 512;
+    size_t need = 2 * img + 1024;
+    if (op == OP_SSIM || op == OP_PIXEL) need += ssim_scratch_bytes(w, h, 1);
+    if (op == OP_SSIM_FAST) need += ssim_fast_scratch(w, h, 1);
+    if (op == OP_MSSSIM) need += msssim_scratch(w, h, 1);
+    FB_TRY(reserve(c, need, 256));
+    uint8_t *da, *db;
+    int pa, pb;
+    FB_TRY(upload(c, a, strideA, w, h, &da, &pa));
+    FB_TRY(upload(c, b, strideB, w, h, &db, &pb));
+    double *dscore = (double *)c->ws.take(sizeof(double) * 2);
+    ImgBatch A{da, 0, pa}, B{db, 0, pb};
+    switch (op) {
+        case OP_SSIM: {
+            void *scratch = c->ws.take(ssim_scratch_bytes(w, h, 1));
+            FB_TRY(launch_ssim(c, c->stream, da, db, 0, 0, pa, pb, w, h, 1, dscore, 1, scratch));
+            break;
+        }
+        case OP_PIXEL: {
+            // force the global-statistics path regardless of size
+            void *scratch = c->ws.take(256);
+            (void)scratch;
+            FB_TRY(launch_pixel_ssim(c->stream, da, db, 0, 0, pa, pb, w, h, 1, dscore, 1));
+            break;
+        }
+        case OP_SSIM_FAST:
+            FB_TRY(pipeline_ssim_fast(c, c->stream, A, B, w, h, 1, dscore, 1));
+            break;
+        case OP_MSSSIM:
+            FB_TRY(pipeline_msssim(c, c->stream, A, B, w, h, 1, dscore));
+            break;
+    }
+    return finish_score(c, dscore, out);
+}
+
+static int dev_ctx_for(const char *fn, int device, DevCtx **out) {
+    DevCtx *c = ctx(device);
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_INVALID;
+    (void)fn;
+    *out = c;
+    return FB_OK;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int fb_init(const int *devices, int n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited && n <= 0) return (int)g_devices.size();
+    return init_locked(devices, n);
+}
+
+void fb_shutdown(void) {
+    // Per-thread objects of the calling thread are released; other threads' objects go with the process.
+    for (auto &c : t_state.ctxs) {
+        if (c.dev < 0) continue;
+        int phys;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            phys = g_devices[c.dev];
+        }
+        cudaSetDevice(phys);
+        cudaStreamSynchronize(c.stream);
+        if (c.ws.base) cudaFree(c.ws.base);
+        if (c.pin.base) cudaFreeHost(c.pin.base);
+        cudaEventDestroy(c.ev);
+        cudaStreamDestroy(c.stream);
+        c = DevCtx();
+    }
+    for (auto &kv : t_state.lanczos) {
+        cudaFree(kv.second.start);
+        cudaFree(kv.second.index);
+        cudaFree(kv.second.weight);
+    }
+    t_state.lanczos.clear();
+    t_state.ctxs.clear();
+    t_state.pinBusy.clear();
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_inited = false;
+    g_devices.clear();
+}
+
+int fb_device_count(void) {
+    int n = ensure_init();
+    return n < 0 ? 0 : n;
+}
+
+int fb_set_device(int device) {
+    int n = ensure_init();
+    if (n < 0) return n;
+    if (device < 0 || device >= n) { set_error("fb_set_device: %d out of range (0..%d)", device, n - 1); return FB_E_INVALID; }
+    t_device = device;
+    return FB_OK;
+}
+
+const char *fb_last_error(void) { return t_err; }
+const char *fb_version(void) { return "fennec-b200 0.1.0 (sm_100a; parity target shamspias/fennec 1.0.2 @ 98234f2c)"; }
+long long fb_take_launch_count(void) { long long v = t_launches; t_launches = 0; return v; }
+
+// ---- SSIM family --------------------------------------------------------------------------------
+int fb_ssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out) {
+    return host_score("fb_ssim", OP_SSIM, a, strideA, b, strideB, w, h, out);
+}
+int fb_ssim_fast(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out) {
+    return host_score("fb_ssim_fast", OP_SSIM_FAST, a, strideA, b, strideB, w, h, out);
+}
+int fb_msssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out) {
+    return host_score("fb_msssim", OP_MSSSIM, a, strideA, b, strideB, w, h, out);
+}
+int fb_pixel_ssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out) {
+    return host_score("fb_pixel_ssim", OP_PIXEL, a, strideA, b, strideB, w, h, out);
+}
+int fb_ssim_fast_dims(int w, int h, int *newW, int *newH) {
+    int nw, nh;
+    int did = ssim_fast_dims(w, h, &nw, &nh);
+    if (newW) *newW = nw;
+    if (newH) *newH = nh;
+    return did;
+}
+
+int fb_box_downsample(const uint8_t *src, int srcStride, int srcW, int srcH, uint8_t *dst, int dstStride,
+                      int dstW, int dstH) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return FB_IDENTITY;  // ssim.go:246-248
+    FB_TRY(check_img("fb_box_downsample", src, srcStride, srcW, srcH));
+    FB_TRY(check_img("fb_box_downsample", dst, dstStride, dstW, dstH));
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    FB_TRY(reserve(c, (size_t)dev_pitch(srcW) * srcH + (size_t)dev_pitch(dstW) * dstH + 4096, 256));
+    uint8_t *ds;
+    int ps;
+    FB_TRY(upload(c, src, srcStride, srcW, srcH, &ds, &ps));
+    int pd = dev_pitch(dstW);
+    uint8_t *dd = (uint8_t *)c->ws.take((size_t)pd * dstH);
+    FB_TRY(launch_box(c->stream, ds, 0, ps, srcW, srcH, dd, 0, pd, dstW, dstH, 1, nullptr));
+    FB_TRY(download(c, dd, pd, dst, dstStride, dstW, dstH));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+// ---- effects ---------------------------------------------------------------------------------------
+int fb_blur_kernel(double sigma, double *kernel, int cap) {
+    if (!(sigma > 0)) { set_error("fb_blur_kernel: sigma must be > 0"); return FB_E_INVALID; }
+    std::vector<double> k;
+    int radius = blur_kernel_host(sigma, k);
+    if (!kernel || cap < (int)k.size()) return -(int)k.size();
+    memcpy(kernel, k.data(), sizeof(double) * k.size());
+    return radius;
+}
+
+static int blur_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, uint8_t *ddst, long long imgStride,
+                          int rowStride, int w, int h, int n, const double *kernel_host, int radius) {
+    int taps = 2 * radius + 1;
+    double *kpin = (double *)c->pin.take(sizeof(double) * taps);
+    float *fpin = (float *)c->pin.take(sizeof(float) * taps);
+    double *kdev = (double *)c->ws.take(sizeof(double) * taps);
+    float *fdev = (float *)c->ws.take(sizeof(float) * taps);
+    int tpitch = dev_pitch(w);
+    long long timg = (long long)tpitch * h;
+    uint8_t *tmp = (uint8_t *)c->ws.take((size_t)timg * n);
+    if (!kpin || !fpin || !kdev || !fdev || !tmp) { set_error("internal: workspace under-reserved (blur)"); return FB_E_INVALID; }
+    for (int i = 0; i < taps; i++) { kpin[i] = kernel_host[i]; fpin[i] = (float)kernel_host[i]; }
+    FB_CUDA(cudaMemcpyAsync(kdev, kpin, sizeof(double) * taps, cudaMemcpyHostToDevice, s));
+    FB_CUDA(cudaMemcpyAsync(fdev, fpin, sizeof(float) * taps, cudaMemcpyHostToDevice, s));
+    mark_pin_busy(c, s);
+    return launch_gaussian_blur(s, dsrc, ddst, imgStride, rowStride, w, h, n, kdev, fdev, radius, tmp, timg, tpitch);
+}
+
+int fb_gaussian_blur(const uint8_t *src, int srcStride, int w, int h, const double *kernel, int radius,
+                     uint8_t *dst, int dstStride) {
+    FB_TRY(check_img("fb_gaussian_blur", src, srcStride, w, h));
+    FB_TRY(check_img("fb_gaussian_blur", dst, dstStride, w, h));
+    if (!kernel || radius < 0) { set_error("fb_gaussian_blur: kernel table missing or radius < 0"); return FB_E_INVALID; }
+    if (w == 0 || h == 0) return FB_OK;
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    int taps = 2 * radius + 1;
+    size_t img = (size_t)dev_pitch(w) * h + 512;
+    FB_TRY(reserve(c, 3 * img + 16 * (size_t)taps + 4096, 16 * (size_t)taps + 256));
+    uint8_t *ds;
+    int ps;
+    FB_TRY(upload(c, src, srcStride, w, h, &ds, &ps));
+    uint8_t *dd = (uint8_t *)c->ws.take((size_t)ps * h);
+    FB_TRY(blur_on_device(c, c->stream, ds, dd, 0, ps, w, h, 1, kernel, radius));
+    FB_TRY(download(c, dd, ps, dst, dstStride, w, h));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_gaussian_blur_sigma(const uint8_t *src, int srcStride, int w, int h, double sigma, uint8_t *dst,
+                           int dstStride) {
+    if (sigma <= 0) return FB_IDENTITY;  // effects.go:147-149
+    std::vector<double> k;
+    int radius = blur_kernel_host(sigma, k);
+    return fb_gaussian_blur(src, srcStride, w, h, k.data(), radius, dst, dstStride);
+}
+
+static int host_fx(const char *fn, int mode, const uint8_t *src, int srcStride, int w, int h, double strength,
+                   uint8_t *dst, int dstStride) {
+    if (mode != 0) {
+        if (strength <= 0) return FB_IDENTITY;  // effects.go:11-13 / 50-52
+        if (strength > 1) strength = 1;
+        if (w < 3 || h < 3) return FB_IDENTITY;  // effects.go:20-22 / 59-61
+    }
+    FB_TRY(check_img(fn, src, srcStride, w, h));
+    FB_TRY(check_img(fn, dst, dstStride, w, h));
+    if (w == 0 || h == 0) return FB_OK;
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    size_t img = (size_t)dev_pitch(w) * h + 512;
+    FB_TRY(reserve(c, 2 * img + 4096, 256));
+    uint8_t *ds;
+    int ps;
+    FB_TRY(upload(c, src, srcStride, w, h, &ds, &ps));
+    uint8_t *dd = (uint8_t *)c->ws.take((size_t)ps * h);
+    if (mode == 0) FB_TRY(launch_blur3x3(c->stream, ds, dd, 0, ps, w, h, 1, 0, ps));
+    else {
+        double amount = mode == 1 ? 1.0 + strength * 1.5 : 1.0 + strength * 2.0;  // effects.go:26 / 65
+        FB_TRY(launch_sharpen(c->stream, ds, dd, 0, ps, w, h, 1, 0, ps, amount, mode == 2));
+    }
+    FB_TRY(download(c, dd, ps, dst, dstStride, w, h));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_blur3x3(const uint8_t *src, int srcStride, int w, int h, uint8_t *dst, int dstStride) {
+    return host_fx("fb_blur3x3", 0, src, srcStride, w, h, 0.0, dst, dstStride);
+}
+int fb_sharpen(const uint8_t *src, int srcStride, int w, int h, double strength, uint8_t *dst, int dstStride) {
+    return host_fx("fb_sharpen", 1, src, srcStride, w, h, strength, dst, dstStride);
+}
+int fb_adaptive_sharpen(const uint8_t *src, int srcStride, int w, int h, double strength, uint8_t *dst,
+                        int dstStride) {
+    return host_fx("fb_adaptive_sharpen", 2, src, srcStride, w, h, strength, dst, dstStride);
+}
+
+// ---- Lanczos ----------------------------------------------------------------------------------------
+int fb_lanczos_weights_cap(int dstSize, int srcSize) { return lanczos_cap(dstSize, srcSize); }
+
+int fb_build_lanczos_weights(int dstSize, int srcSize, int *start, int *index, double *weight) {
+    if (dstSize <= 0 || srcSize <= 0 || !start || !index || !weight) {
+        set_error("fb_build_lanczos_weights: bad arguments");
+        return FB_E_INVALID;
+    }
+    return lanczos_build(dstSize, srcSize, start, index, weight);
+}
+
+static int upload_weights(DevCtx *c, cudaStream_t s, const fb_weights *w, LanczosTable *t) {
+    int n = w->n, entries = w->start[n];
+    int *pstart = (int *)c->pin.take(sizeof(int) * (n + 1));
+    int *pindex = (int *)c->pin.take(sizeof(int) * (entries + 1));
+    double *pweight = (double *)c->pin.take(sizeof(double) * (entries + 1));
+    t->start = (int *)c->ws.take(sizeof(int) * (n + 1));
+    t->index = (int *)c->ws.take(sizeof(int) * (entries + 1));
+    t->weight = (double *)c->ws.take(sizeof(double) * (entries + 1));
+    if (!pstart || !pindex || !pweight || !t->start || !t->index || !t->weight) {
+        set_error("internal: workspace under-reserved (weights)");
+        return FB_E_INVALID;
+    }
+    memcpy(pstart, w->start, sizeof(int) * (n + 1));
+    memcpy(pindex, w->index, sizeof(int) * entries);
+    memcpy(pweight, w->weight, sizeof(double) * entries);
+    FB_CUDA(cudaMemcpyAsync(t->start, pstart, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
+    FB_CUDA(cudaMemcpyAsync(t->index, pindex, sizeof(int) * entries, cudaMemcpyHostToDevice, s));
+    FB_CUDA(cudaMemcpyAsync(t->weight, pweight, sizeof(double) * entries, cudaMemcpyHostToDevice, s));
+    mark_pin_busy(c, s);
+    t->entries = entries;
+    t->maxTaps = 0;
+    for (int d = 0; d < n; d++) t->maxTaps = std::max(t->maxTaps, w->start[d + 1] - w->start[d]);
+    return FB_OK;
+}
+
+static int check_weights(const char *fn, const fb_weights *w, int dstSize, int srcSize) {
+    if (!w) return FB_OK;
+    if (w->n != dstSize || !w->start || !w->index || !w->weight) {
+        set_error("%s: weight table has n=%d, expected %d", fn, w->n, dstSize);
+        return FB_E_INVALID;
+    }
+    for (int d = 0; d < dstSize; d++)
+        if (w->start[d + 1] < w->start[d]) { set_error("%s: weight table start[] not monotone", fn); return FB_E_INVALID; }
+    int entries = w->start[dstSize];
+    for (int i = 0; i < entries; i++)
+        if (w->index[i] < 0 || w->index[i] >= srcSize) { set_error("%s: tap index %d out of range", fn, w->index[i]); return FB_E_INVALID; }
+    return FB_OK;
+}
+
+static int resize_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, long long srcImgStride, int srcRowStride,
+                            int srcW, int srcH, uint8_t *ddst, long long dstImgStride, int dstRowStride, int dstW,
+                            int dstH, int n, const LanczosTable &tx, const LanczosTable &ty) {
+    int tpitch = dev_pitch(dstW);
+    long long timg = (long long)tpitch * srcH;
+    uint8_t *tmp = (uint8_t *)c->ws.take((size_t)timg * n);
+    if (!tmp) { set_error("internal: workspace under-reserved (resize tmp)"); return FB_E_INVALID; }
+    FB_TRY(launch_resize_h(s, dsrc, srcImgStride, srcRowStride, srcW, srcH, tmp, timg, tpitch, dstW, n, tx.start,
+                           tx.index, tx.weight, tx.maxTaps));
+    return launch_resize_v(s, tmp, timg, tpitch, dstW, srcH, ddst, dstImgStride, dstRowStride, dstH, n, ty.start,
+                           ty.index, ty.weight, ty.maxTaps);
+}
+
+int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH, uint8_t *dst, int dstStride, int dstW,
+                      int dstH, const fb_weights *wx, const fb_weights *wy) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return FB_IDENTITY;  // resize.go:41-43
+    FB_TRY(check_img("fb_lanczos_resize", src, srcStride, srcW, srcH));
+    FB_TRY(check_img("fb_lanczos_resize", dst, dstStride, dstW, dstH));
+    if (srcW == dstW && srcH == dstH) {  // resize.go:45-49 — plain copy, no device work needed
+        for (int y = 0; y < srcH; y++) memcpy(dst + (size_t)y * dstStride, src + (size_t)y * srcStride, (size_t)srcW * 4);
+        return FB_OK;
+    }
+    FB_TRY(check_weights("fb_lanczos_resize", wx, dstW, srcW));
+    FB_TRY(check_weights("fb_lanczos_resize", wy, dstH, srcH));
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    size_t tabBytes = 0;
+    if (wx) tabBytes += 16 * (size_t)(wx->start[dstW] + dstW + 8);
+    if (wy) tabBytes += 16 * (size_t)(wy->start[dstH] + dstH + 8);
+    size_t need = (size_t)dev_pitch(srcW) * srcH + (size_t)dev_pitch(dstW) * srcH + (size_t)dev_pitch(dstW) * dstH +
+                  tabBytes + 8192;
+    FB_TRY(reserve(c, need, tabBytes + 4096));
+    LanczosTable tx, ty;
+    if (wx) FB_TRY(upload_weights(c, c->stream, wx, &tx)); else FB_TRY(lanczos_table_cached(c, dstW, srcW, &tx));
+    if (wy) FB_TRY(upload_weights(c, c->stream, wy, &ty)); else FB_TRY(lanczos_table_cached(c, dstH, srcH, &ty));
+    uint8_t *ds;
+    int ps;
+    FB_TRY(upload(c, src, srcStride, srcW, srcH, &ds, &ps));
+    int pd = dev_pitch(dstW);
+    uint8_t *dd = (uint8_t *)c->ws.take((size_t)pd * dstH);
+    FB_TRY(resize_on_device(c, c->stream, ds, 0, ps, srcW, srcH, dd, 0, pd, dstW, dstH, 1, tx, ty));
+    FB_TRY(download(c, dd, pd, dst, dstStride, dstW, dstH));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int *dstH) {
+    if (maxW <= 0) maxW = srcW;  // resize.go:16-21
+    if (maxH <= 0) maxH = srcH;
+    int dw = srcW, dh = srcH, noop = 1;
+    if (!(srcW <= maxW && srcH <= maxH)) {
+        double ratio = fmin((double)maxW / (double)srcW, (double)maxH / (double)srcH);
+        dw = (int)fmax(1.0, round((double)srcW * ratio));
+        dh = (int)fmax(1.0, round((double)srcH * ratio));
+        noop = 0;
+    }
+    if (dstW) *dstW = dw;
+    if (dstH) *dstH = dh;
+    return noop;
+}
+
+// ---- device-resident batch entry points ---------------------------------------------------------------
+static int check_batch(const char *fn, const void *p, long long imgStride, int rowStride, int w, int h, int n) {
+    if (n < 0 || w <= 0 || h <= 0) { set_error("%s: bad batch dims n=%d %dx%d", fn, n, w, h); return FB_E_INVALID; }
+    if (!p && n > 0) { set_error("%s: null device pointer", fn); return FB_E_INVALID; }
+    if (rowStride < w * 4 || (rowStride & 3) || ((uintptr_t)p & 3) || (imgStride & 3)) {
+        set_error("%s: rowStride %d / imgStride %lld / base must be >= 4*w and 4-byte aligned", fn, rowStride, imgStride);
+        return FB_E_INVALID;
+    }
+    if (n > 1 && imgStride < (long long)rowStride * (h - 1) + (long long)w * 4) {
+        set_error("%s: imgStride %lld smaller than one image", fn, imgStride);
+        return FB_E_INVALID;
+    }
+    return FB_OK;
+}
+
+int fb_ssim_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride,
+                      int rowStride, int w, int h, int n, double *scores) {
+    FB_TRY(check_batch("fb_ssim_batch_dev", a, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch("fb_ssim_batch_dev", b, imgStride, rowStride, w, h, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_ssim_batch_dev", device, &c));
+    FB_TRY(reserve(c, ssim_scratch_bytes(w, h, n) + 1024, 256));
+    void *scratch = c->ws.take(ssim_scratch_bytes(w, h, n));
+    return launch_ssim(c, (cudaStream_t)stream, a, b, imgStride, imgStride, rowStride, rowStride, w, h, n, scores, 1,
+                       scratch);
+}
+
+int fb_ssim_fast_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride,
+                           int rowStride, int w, int h, int n, double *scores) {
+    FB_TRY(check_batch("fb_ssim_fast_batch_dev", a, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch("fb_ssim_fast_batch_dev", b, imgStride, rowStride, w, h, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_ssim_fast_batch_dev", device, &c));
+    FB_TRY(reserve(c, ssim_fast_scratch(w, h, n), 256));
+    return pipeline_ssim_fast(c, (cudaStream_t)stream, ImgBatch{a, imgStride, rowStride}, ImgBatch{b, imgStride, rowStride},
+                              w, h, n, scores, 1);
+}
+
+int fb_msssim_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride,
+                        int rowStride, int w, int h, int n, double *scores) {
+    FB_TRY(check_batch("fb_msssim_batch_dev", a, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch("fb_msssim_batch_dev", b, imgStride, rowStride, w, h, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_msssim_batch_dev", device, &c));
+    FB_TRY(reserve(c, msssim_scratch(w, h, n), 1024));
+    return pipeline_msssim(c, (cudaStream_t)stream, ImgBatch{a, imgStride, rowStride}, ImgBatch{b, imgStride, rowStride},
+                           w, h, n, scores);
+}
+
+int fb_box_downsample_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride, int srcRowStride,
+                                int srcW, int srcH, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int dstW,
+                                int dstH, int n) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return FB_IDENTITY;
+    FB_TRY(check_batch("fb_box_downsample_batch_dev", src, srcImgStride, srcRowStride, srcW, srcH, n));
+    FB_TRY(check_batch("fb_box_downsample_batch_dev", dst, dstImgStride, dstRowStride, dstW, dstH, n));
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_box_downsample_batch_dev", device, &c));
+    return launch_box((cudaStream_t)stream, src, srcImgStride, srcRowStride, srcW, srcH, dst, dstImgStride,
+                      dstRowStride, dstW, dstH, n, nullptr);
+}
+
+int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst, int64_t imgStride,
+                               int rowStride, int w, int h, int n, const double *kernel_host, int radius) {
+    FB_TRY(check_batch("fb_gaussian_blur_batch_dev", src, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch("fb_gaussian_blur_batch_dev", dst, imgStride, rowStride, w, h, n));
+    if (!kernel_host || radius < 0) { set_error("fb_gaussian_blur_batch_dev: kernel table missing"); return FB_E_INVALID; }
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_gaussian_blur_batch_dev", device, &c));
+    int taps = 2 * radius + 1;
+    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h * n + 16 * (size_t)taps + 4096, 16 * (size_t)taps + 256));
+    return blur_on_device(c, (cudaStream_t)stream, src, dst, imgStride, rowStride, w, h, n, kernel_host, radius);
+}
+
+static int fx_batch(const char *fn, int adaptive, int device, void *stream, const uint8_t *src, uint8_t *dst,
+                    int64_t imgStride, int rowStride, int w, int h, int n, double strength) {
+    if (strength <= 0 || w < 3 || h < 3) return FB_IDENTITY;
+    if (strength > 1) strength = 1;
+    FB_TRY(check_batch(fn, src, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch(fn, dst, imgStride, rowStride, w, h, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for(fn, device, &c));
+    double amount = adaptive ? 1.0 + strength * 2.0 : 1.0 + strength * 1.5;
+    return launch_sharpen((cudaStream_t)stream, src, dst, imgStride, rowStride, w, h, n, imgStride, rowStride, amount,
+                          adaptive);
+}
+
+int fb_sharpen_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst, int64_t imgStride, int rowStride,
+                         int w, int h, int n, double strength) {
+    return fx_batch("fb_sharpen_batch_dev", 0, device, stream, src, dst, imgStride, rowStride, w, h, n, strength);
+}
+int fb_adaptive_sharpen_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst, int64_t imgStride,
+                                  int rowStride, int w, int h, int n, double strength) {
+    return fx_batch("fb_adaptive_sharpen_batch_dev", 1, device, stream, src, dst, imgStride, rowStride, w, h, n, strength);
+}
+
+int fb_lanczos_resize_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride, int srcRowStride,
+                                int srcW, int srcH, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int dstW,
+                                int dstH, int n) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return FB_IDENTITY;
+    FB_TRY(check_batch("fb_lanczos_resize_batch_dev", src, srcImgStride, srcRowStride, srcW, srcH, n));
+    FB_TRY(check_batch("fb_lanczos_resize_batch_dev", dst, dstImgStride, dstRowStride, dstW, dstH, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_lanczos_resize_batch_dev", device, &c));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (srcW == dstW && srcH == dstH) {
+        for (int i = 0; i < n; i++)
+            FB_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * dstImgStride, dstRowStride, src + (size_t)i * srcImgStride,
+                                      srcRowStride, (size_t)srcW * 4, srcH, cudaMemcpyDeviceToDevice, s));
+        return FB_OK;
+    }
+    FB_TRY(reserve(c, (size_t)dev_pitch(dstW) * srcH * n + 8192, 256));
+    LanczosTable tx, ty;
+    FB_TRY(lanczos_table_cached(c, dstW, srcW, &tx));
+    FB_TRY(lanczos_table_cached(c, dstH, srcH, &ty));
+    return resize_on_device(c, s, src, srcImgStride, srcRowStride, srcW, srcH, dst, dstImgStride, dstRowStride, dstW,
+                            dstH, n, tx, ty);
+}
+
+size_t fb_workspace_bytes(const char *op, int w, int h, int dstW, int dstH, int n) {
+    if (!op) return 0;
+    if (!strcmp(op, "ssim")) return ssim_scratch_bytes(w, h, n);
+    if (!strcmp(op, "ssim_fast")) return ssim_fast_scratch(w, h, n);
+    if (!strcmp(op, "msssim")) return msssim_scratch(w, h, n);
+    if (!strcmp(op, "gaussian_blur")) return (size_t)dev_pitch(w) * h * n;
+    if (!strcmp(op, "lanczos_resize")) return (size_t)dev_pitch(dstW) * h * n;
+    (void)dstH;
+    return 0;
+}
+
+// ---- batch sharder (batch.go:58-128) ----------------------------------------------------------------------
+int fb_batch_shard(int n_items, int n_shards, int shard, int *begin, int *end) {
+    if (n_items < 0 || n_shards <= 0 || shard < 0 || shard >= n_shards || !begin || !end) {
+        set_error("fb_batch_shard: bad arguments (n_items=%d n_shards=%d shard=%d)", n_items, n_shards, shard);
+        return FB_E_INVALID;
+    }
+    int per = (n_items + n_shards - 1) / n_shards;  // owner(i) = i / ceil(n/G)
+    long long b = (long long)shard * per, e = b + per;
+    if (b > n_items) b = n_items;
+    if (e > n_items) e = n_items;
+    *begin = (int)b;
+    *end = (int)e;
+    return FB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// box.cu — K2: variable-box mean downsample of all four channels, bit-exact with
+// boxDownsample + averageBoxPixel (ssim.go:244-309).
+//
+// The reference sums uint8 values in float64 (exact integers), multiplies once by 1.0/count and
+// rounds half away from zero.  Here the sums are integers, the single multiply is an IEEE binary64
+// __dmul_rn and the rounding is clampf_dev, so every output byte is identical.  Box edges are
+// int(float64(d) * ratio) with the reference's clamps (ssim.go:255-278); they are recomputed on the
+// device with the same IEEE double multiply + truncation, so no tables cross the ABI.
+//
+// Mapping (HBM-bound: every source byte is read exactly once, fully coalesced): one CTA per
+// (output row, chunk of output columns).  Phase 1 — each thread owns 4 adjacent source columns
+// (one 128-bit load per row) and accumulates the vertical sums of the box rows as packed 2x16-bit
+// integers; the column sums go to shared memory.  Phase 2 — one thread per output pixel adds the
+// column sums of its box, multiplies by the reciprocal count in FP64 and writes 4 bytes.
+#include "common.cuh"
+
+namespace fb {
+
+namespace {
+
+constexpr int kSpanMax = 2048;   // source columns whose sums fit in shared memory (16 KB)
+constexpr int kThreads = 256;
+
+struct BoxParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcImgStride, dstImgStride;
+    int srcRowStride, dstRowStride;
+    int srcW, srcH, dstW, dstH;
+    double xRatio, yRatio;
+    int dxChunk;   // output columns per CTA
+    int vecOK;
+};
+
+// ssim.go:255-265 / 268-278
+__device__ __forceinline__ void box_edge(int d, double ratio, int srcSize, int &lo, int &hi) {
+    lo = (int)__dmul_rn((double)d, ratio);
+    hi = (int)__dmul_rn((double)(d + 1), ratio);
+    if (hi > srcSize) hi = srcSize;
+    if (lo >= hi) lo = hi - 1;
+    if (lo < 0) lo = 0;
+}
+
+__device__ __forceinline__ uint32_t box_finish(uint32_t sr, uint32_t sg, uint32_t sb, uint32_t sa, int count) {
+    double inv = __ddiv_rn(1.0, (double)count);  // ssim.go:302
+    uint32_t r = clampf_dev(__dmul_rn((double)sr, inv));
+    uint32_t g = clampf_dev(__dmul_rn((double)sg, inv));
+    uint32_t b = clampf_dev(__dmul_rn((double)sb, inv));
+    uint32_t a = clampf_dev(__dmul_rn((double)sa, inv));
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
+__global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams p) {
+    __shared__ uint2 colsum[kSpanMax + 8];  // per source column: (R | B<<16, G | A<<16) 16-bit sums
+    const int dy = blockIdx.y, img = blockIdx.z;
+    const int dx0 = blockIdx.x * p.dxChunk;
+    const int dx1 = min(dx0 + p.dxChunk, p.dstW);
+    int sy0, sy1, sxa, sxb, tmp;
+    box_edge(dy, p.yRatio, p.srcH, sy0, sy1);
+    box_edge(dx0, p.xRatio, p.srcW, sxa, tmp);
+    box_edge(dx1 - 1, p.xRatio, p.srcW, tmp, sxb);
+    const int base = sxa & ~3;            // 16-byte aligned first column
+    const int span = sxb - base;          // <= kSpanMax + 3 by construction of dxChunk
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+
+    for (int c4 = threadIdx.x * 4; c4 < span; c4 += kThreads * 4) {
+        const int x = base + c4;
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+        const bool full = p.vecOK && (x + 4 <= p.srcW);
+        const uint8_t *q = s + (long long)sy0 * p.srcRowStride + (long long)x * 4;
+        for (int y = sy0; y < sy1; y++, q += p.srcRowStride) {
+            uint32_t v[4];
+            if (full) {
+                uint4 t = ld_nc_u128(q);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = (x + i < p.srcW) ? ld_nc_u32(q + 4 * i) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                lo[i] += v[i] & 0x00FF00FFu;          // R, B
+                hi[i] += (v[i] >> 8) & 0x00FF00FFu;   // G, A
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) colsum[c4 + i] = make_uint2(lo[i], hi[i]);
+    }
+    __syncthreads();
+    const int count_y = sy1 - sy0;
+    uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)dy * p.dstRowStride;
+    for (int dx = dx0 + threadIdx.x; dx < dx1; dx += kThreads) {
+        int sx0, sx1;
+        box_edge(dx, p.xRatio, p.srcW, sx0, sx1);
+        uint32_t sr = 0, sg = 0, sb = 0, sa = 0;
+        for (int x = sx0; x < sx1; x++) {
+            uint2 c = colsum[x - base];
+            sr += c.x & 0xFFFFu; sb += c.x >> 16;
+            sg += c.y & 0xFFFFu; sa += c.y >> 16;
+        }
+        *reinterpret_cast<uint32_t *>(drow + (long long)dx * 4) = box_finish(sr, sg, sb, sa, count_y * (sx1 - sx0));
+    }
+}
+
+// Generic fallback: one thread per output pixel walks its own box (upsampling, boxes taller than
+// 256 rows or wider than the shared-memory span). Same arithmetic.
+__global__ void __launch_bounds__(kThreads) box_naive_kernel(const BoxParams p) {
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dy = blockIdx.y, img = blockIdx.z;
+    if (dx >= p.dstW) return;
+    int sy0, sy1, sx0, sx1;
+    box_edge(dy, p.yRatio, p.srcH, sy0, sy1);
+    box_edge(dx, p.xRatio, p.srcW, sx0, sx1);
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    unsigned long long sr = 0, sg = 0, sb = 0, sa = 0;
+    for (int y = sy0; y < sy1; y++) {
+        const uint8_t *q = s + (long long)y * p.srcRowStride + (long long)sx0 * 4;
+        for (int x = sx0; x < sx1; x++, q += 4) {
+            uint32_t v = ld_nc_u32(q);
+            sr += v & 0xFF; sg += (v >> 8) & 0xFF; sb += (v >> 16) & 0xFF; sa += v >> 24;
+        }
+    }
+    long long count = (long long)(sy1 - sy0) * (sx1 - sx0);
+    uint8_t *d = p.dst + (long long)img * p.dstImgStride + (long long)dy * p.dstRowStride + (long long)dx * 4;
+    if (count > 0) {
+        double inv = __ddiv_rn(1.0, (double)count);
+        uint32_t r = clampf_dev(__dmul_rn((double)sr, inv));
+        uint32_t g = clampf_dev(__dmul_rn((double)sg, inv));
+        uint32_t b = clampf_dev(__dmul_rn((double)sb, inv));
+        uint32_t a = clampf_dev(__dmul_rn((double)sa, inv));
+        *reinterpret_cast<uint32_t *>(d) = r | (g << 8) | (b << 16) | (a << 24);
+    }
+}
+
+}  // namespace
+
+// Host copy of the edge rule (used to size chunks; same IEEE ops as the device).
+void box_edges_host(int src, int dst, int *lo, int *hi) {
+    double ratio = (double)src / (double)dst;
+    for (int d = 0; d < dst; d++) {
+        int a = (int)((double)d * ratio);
+        int b = (int)((double)(d + 1) * ratio);
+        if (b > src) b = src;
+        if (a >= b) a = b - 1;
+        if (a < 0) a = 0;
+        lo[d] = a;
+        hi[d] = b;
+    }
+}
+
+int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
+               int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
+               const int *unused_edges) {
+    (void)unused_edges;
+    if (n <= 0) return FB_OK;
+    BoxParams p;
+    p.src = src; p.dst = dst;
+    p.srcImgStride = srcImgStride; p.dstImgStride = dstImgStride;
+    p.srcRowStride = srcRowStride; p.dstRowStride = dstRowStride;
+    p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH;
+    p.xRatio = (double)srcW / (double)dstW;   // ssim.go:251-252
+    p.yRatio = (double)srcH / (double)dstH;
+    p.vecOK = (((uintptr_t)src | (uintptr_t)srcImgStride | (uintptr_t)srcRowStride) & 15) == 0;
+    // Fast path needs: disjoint ascending boxes (ratio >= 1), <= 256 rows per box (16-bit sums),
+    // and at least one output column per shared-memory span.
+    int maxBoxW = (int)p.xRatio + 2, maxBoxH = (int)p.yRatio + 2;
+    bool fast = p.xRatio >= 1.0 && p.yRatio >= 1.0 && maxBoxH <= 256 && maxBoxW <= kSpanMax / 2;
+    if (fast) {
+        int chunk = (int)((double)(kSpanMax - maxBoxW - 4) / p.xRatio);
+        if (chunk < 1) chunk = 1;
+        if (chunk > dstW) chunk = dstW;
+        p.dxChunk = chunk;
+        dim3 grid((dstW + chunk - 1) / chunk, dstH, n);
+        box_rows_kernel<<<grid, kThreads, 0, s>>>(p);
+    } else {
+        p.dxChunk = 0;
+        dim3 grid((dstW + kThreads - 1) / kThreads, dstH, n);
+        box_naive_kernel<<<grid, kThreads, 0, s>>>(p);
+    }
+    FB_LAUNCHED(1);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+}
+
+}  // namespace fb

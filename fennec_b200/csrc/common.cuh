@@ -1,0 +1,139 @@
+// common.cuh — runtime plumbing shared by every translation unit of libfennec_b200.so:
+// per-thread / per-device streams and scratch arenas, error text, launch counting, and the
+// device-side rounding helpers that make uint8 outputs bit-exact with the reference's
+// clampF (convert.go:149-158).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/fennec_b200.h"
+
+namespace fb {
+
+// ---- error handling ------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FB_CUDA(call)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return fb::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define FB_TRY(call)                   \
+    do {                               \
+        int _s = (call);               \
+        if (_s < 0) return _s;         \
+    } while (0)
+
+// ---- launch accounting (bench.py's gpu_launches) --------------------------------------------
+extern thread_local long long t_launches;
+#define FB_LAUNCHED(n) (fb::t_launches += (n))
+
+// ---- per-thread, per-device context ----------------------------------------------------------
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0;
+    size_t off = 0;
+    void reset() { off = 0; }
+    // 256-byte aligned carve; nullptr when the reservation was too small (programming error).
+    void *take(size_t bytes) {
+        size_t a = (off + 255) & ~size_t(255);
+        if (a + bytes > cap) return nullptr;
+        off = a + bytes;
+        return base + a;
+    }
+};
+
+struct DevCtx {
+    int dev = -1;
+    cudaStream_t stream = nullptr;  // owned stream used by the host entry points
+    Arena ws;                        // device scratch (grow-only)
+    Arena pin;                       // pinned host scratch (scores, small tables)
+    cudaEvent_t ev = nullptr;
+};
+
+int ensure_init();
+int device_count();
+int current_device();  // thread's device for host entry points
+// Context of this thread for `dev`; creates stream/events on first use. nullptr on failure.
+DevCtx *ctx(int dev);
+// Make sure the arenas can hold the given bytes (may synchronise + reallocate).
+int reserve(DevCtx *c, size_t dev_bytes, size_t pinned_bytes);
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// Row pitch the library uses for its own device copies: 16-byte aligned rows enable 128-bit loads.
+static inline int dev_pitch(int w) { return (int)align_up((size_t)w * 4, 16); }
+
+// ---- kernels' host-side launchers (one per .cu) ---------------------------------------------
+// All take device pointers and enqueue on `s`; scratch comes from c->ws (already reserved).
+
+// ssim.cu
+size_t ssim_scratch_bytes(int w, int h, int n);
+int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, long long imgStrideA,
+                long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h, int n,
+                double *scores, long long scoreStride, void *scratch);
+int launch_pixel_ssim(cudaStream_t s, const uint8_t *a, const uint8_t *b, long long imgStrideA,
+                      long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h, int n,
+                      double *scores, long long scoreStride);
+// MSSSIM tail: per-level scores are combined on the device:
+int launch_msssim_combine(cudaStream_t s, const double *levelScores, int nLevels, int n,
+                          const double *weights_dev, double *out);
+
+// box.cu
+int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
+               int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
+               const int *reserved);
+void box_edges_host(int src, int dst, int *lo, int *hi);
+
+// effects.cu
+int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
+                         int rowStride, int w, int h, int n, const double *kernel_dev,
+                         const float *kernel32_dev, int radius, uint8_t *tmp, long long tmpImgStride,
+                         int tmpRowStride);
+int launch_blur3x3(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride, int rowStride,
+                   int w, int h, int n, long long dstImgStride, int dstRowStride);
+int launch_sharpen(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride, int rowStride,
+                   int w, int h, int n, long long dstImgStride, int dstRowStride, double amount, int adaptive);
+
+// resize.cu
+int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
+                    int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,
+                    const int *start_dev, const int *index_dev, const double *weight_dev, int maxTaps);
+int launch_resize_v(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
+                    int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstH, int n,
+                    const int *start_dev, const int *index_dev, const double *weight_dev, int maxTaps);
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+
+// clampF (convert.go:149-158): uint8(clamp(int64(math.Round(x)), 0, 255)), Round = half away from 0.
+// Exact: t = trunc(x) and x - t are both exact in binary64 for |x| < 2^52.
+__device__ __forceinline__ uint32_t clampf_dev(double x) {
+    if (!(x > -0.5)) return 0u;      // rounds to <= 0 (also NaN → 0, unreachable on this path)
+    if (x >= 254.5) return 255u;
+    double t = trunc(x);
+    int v = (int)t;
+    if (x - t >= 0.5) v += 1;
+    return (uint32_t)v;
+}
+
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint8_t *p) {
+    return __ldg(reinterpret_cast<const uint32_t *>(p));
+}
+__device__ __forceinline__ uint4 ld_nc_u128(const uint8_t *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_nc_u64(const uint8_t *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+#endif
+
+}  // namespace fb

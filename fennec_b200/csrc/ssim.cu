@@ -1,0 +1,399 @@
+// ssim.cu — K1: BT.601 luma + 8x8 Gaussian-windowed SSIM + reduction, one pass over HBM.
+//
+// Replaces toLuminance + windowedSSIM (ssim.go:73-166, 207-220) and pixelSSIM (ssim.go:169-204).
+//
+// Formulation (DESIGN.md "K1"): the reference's two-pass 64-tap window is restated as a separable
+// one-pass filter of four planes per pixel — a', b', q = a'^2 + b'^2, p = a'b' — where a' = luma(a) - c
+// is centred on a per-strip constant c (the luma of the strip's centre pixel) so that
+// E[x^2] - mu^2 does not cancel catastrophically in FP32 (measured <= 2e-6 absolute on adversarial
+// inputs, tests/test_ssim_parity.py; the contract is 1e-5).  The window is
+// exp(-(x^2+y^2)/4.5) for x,y in [-4,3] (ssim.go:74-77,116-117,223-241): an outer product g(y)g(x).
+//
+// Mapping: one warp owns a strip of 32*CPL input columns and walks down RS(+7) rows.  Each lane owns
+// CPL adjacent columns, keeps the last 8 rows of its 4 planes in registers (the vertical 8-tap pass
+// costs no memory traffic), publishes the vertical sums to shared memory once per row (conflict-free
+// float4 layout) and reads its 7 right-hand neighbours back for the horizontal 8-tap pass.  Pixels
+// are loaded with 128-bit non-allocating loads, one row ahead.  Bytes -> float goes through
+// dp2a (integer dot product with the BT.601 weights x1000) accumulating straight into the bit pattern
+// of 2^23 + L, because I2F runs at 1/8 of the FMA rate on sm_100 (tools/microbench.cu).
+// This kernel is FMA-pipe-bound, not HBM-bound: ~87 FP32 lane-ops per pixel (profiles/).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace fb {
+
+namespace {
+
+constexpr float kC1f = 6.5025f;   // ssim.go:15
+constexpr float kC2f = 58.5225f;  // ssim.go:16
+constexpr float kLumaScale = 0.001f;
+
+struct SsimParams {
+    const uint8_t *a;
+    const uint8_t *b;
+    long long imgStrideA, imgStrideB;
+    int rowStrideA, rowStrideB;
+    int w, h, n;
+    int nsx, nsy, rs;
+    int vecOK;          // base pointers and strides are 16-byte aligned
+    double *partials;   // [n][nsy*nsx]
+    float g[8];         // 1-D Gaussian, k = -4..3, normalised
+};
+
+// 299*R + 587*G + 114*B accumulated onto the bits of 2^23 → float(2^23 + L), L <= 255000 < 2^23.
+__device__ __forceinline__ float luma_magic(uint32_t px) {
+    const uint32_t wRG = 299u | (587u << 16);
+    const uint32_t wB0 = 114u;
+    uint32_t t = __dp2a_hi(wB0, px, 0x4B000000u);
+    t = __dp2a_lo(wRG, px, t);
+    return __uint_as_float(t);
+}
+
+template <int CPL>
+__device__ __forceinline__ void load_px(const uint8_t *p, bool vec, int nvalid, uint32_t (&o)[CPL]) {
+    if (vec) {
+        if (CPL == 4) {
+            uint4 v = ld_nc_u128(p);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[CPL - 1] = v.w;
+        } else {
+            uint2 v = ld_nc_u64(p);
+            o[0] = v.x; o[CPL - 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CPL; i++) o[i] = (i < nvalid) ? ld_nc_u32(p + 4 * i) : 0u;
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(128, (CPL == 4 ? 2 : 4)) ssim_strip_kernel(const SsimParams p) {
+    constexpr int WARPS = 4;
+    constexpr int INC = 32 * CPL;    // input columns per strip
+    constexpr int OUTC = INC - 8;    // outputs per strip (multiple of 4 → 16-byte aligned strips)
+    __shared__ float4 vbuf[WARPS][2][INC];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long segsPerImg = (long long)p.nsx * p.nsy;
+    const long long seg = (long long)blockIdx.x * WARPS + warp;
+    if (seg >= segsPerImg * p.n) return;  // no block-wide barriers below
+    const int img = (int)(seg / segsPerImg);
+    const int rseg = (int)(seg - (long long)img * segsPerImg);
+    const int sy = rseg / p.nsx, sx = rseg - sy * p.nsx;
+
+    const int X0 = sx * OUTC, Y0 = sy * p.rs;
+    const int nOut = min(p.rs, (p.h - 8) - Y0);  // output rows of this segment (>= 1)
+    const int nIn = nOut + 7;
+    const int xl = X0 + CPL * lane;
+    const int nvalid = max(0, min(CPL, p.w - xl));
+    const bool vec = p.vecOK && nvalid == CPL;
+
+    const uint8_t *pa = p.a + (long long)img * p.imgStrideA + (long long)Y0 * p.rowStrideA + (long long)xl * 4;
+    const uint8_t *pb = p.b + (long long)img * p.imgStrideB + (long long)Y0 * p.rowStrideB + (long long)xl * 4;
+
+    // Centring constant: luma of image a at the strip's centre pixel (same for every lane).
+    float K, c;
+    {
+        int cx = min(X0 + OUTC / 2, p.w - 1), cy = min(Y0 + nIn / 2, p.h - 1);
+        uint32_t cp = ld_nc_u32(p.a + (long long)img * p.imgStrideA + (long long)cy * p.rowStrideA + (long long)cx * 4);
+        float f = luma_magic(cp);                       // 2^23 + L
+        K = -(f * kLumaScale);                          // a' = F*s + K  ~  luma - luma_c
+        c = -fmaf(8388608.0f, kLumaScale, K);           // the centring this K really applies
+    }
+    const float2 s2 = make_float2(kLumaScale, kLumaScale);
+    const float2 K2 = make_float2(K, K);
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(p.g[j], p.g[j]);
+
+    // formula constants: th = c*(mua'+mub') + (c^2 + C1/2)
+    const float kTh = fmaf(c, c, 0.5f * kC1f);
+    const float2 qpInit = make_float2(kC2f, 0.5f * kC2f);  // Q' = Q + C2, P' = P + C2/2
+
+    bool valid[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) valid[i] = (CPL * lane + i < OUTC) && (xl + i < p.w - 8);
+
+    float2 rab[8][CPL], rqp[8][CPL];
+    uint32_t na[CPL], nb[CPL];
+    load_px<CPL>(pa, vec, nvalid, na);
+    load_px<CPL>(pb, vec, nvalid, nb);
+
+    auto planes = [&](int slot, const uint32_t(&ca)[CPL], const uint32_t(&cb)[CPL]) {
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            float2 f = make_float2(luma_magic(ca[i]), luma_magic(cb[i]));
+            float2 t = __ffma2_rn(f, s2, K2);           // (a', b')
+            float2 sq = __fmul2_rn(t, t);
+            rab[slot][i] = t;
+            rqp[slot][i] = make_float2(sq.x + sq.y, t.x * t.y);
+        }
+    };
+
+    // prologue: rows 0..6 → slots 0..6
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        uint32_t ca[CPL], cb[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; i++) { ca[i] = na[i]; cb[i] = nb[i]; }
+        pa += p.rowStrideA;
+        pb += p.rowStrideB;
+        load_px<CPL>(pa, vec, nvalid, na);  // row j+1 <= 7 <= nIn-1 always exists
+        load_px<CPL>(pb, vec, nvalid, nb);
+        planes(j, ca, cb);
+    }
+
+    double dsum = 0.0;
+    float4 *vb0 = &vbuf[warp][0][0];
+    float4 *vb1 = &vbuf[warp][1][0];
+
+    for (int yo = 0; yo < nOut; yo += 8) {
+        float fsum = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            if (yo + s < nOut) {  // warp-uniform
+                uint32_t ca[CPL], cb[CPL];
+#pragma unroll
+                for (int i = 0; i < CPL; i++) { ca[i] = na[i]; cb[i] = nb[i]; }
+                if (yo + s + 8 < nIn) {  // prefetch the next input row
+                    pa += p.rowStrideA;
+                    pb += p.rowStrideB;
+                    load_px<CPL>(pa, vec, nvalid, na);
+                    load_px<CPL>(pb, vec, nvalid, nb);
+                }
+                planes((s + 7) & 7, ca, cb);
+
+                // vertical 8-tap: output row yo+s uses input rows yo+s+j, j = 0..7 → slots (s+j)&7
+                float4 it[CPL + 7];
+#pragma unroll
+                for (int i = 0; i < CPL; i++) {
+                    float2 vab = __fmul2_rn(rab[s & 7][i], g2[0]);
+                    float2 vqp = __fmul2_rn(rqp[s & 7][i], g2[0]);
+#pragma unroll
+                    for (int j = 1; j < 8; j++) {
+                        vab = __ffma2_rn(rab[(s + j) & 7][i], g2[j], vab);
+                        vqp = __ffma2_rn(rqp[(s + j) & 7][i], g2[j], vqp);
+                    }
+                    it[i] = make_float4(vab.x, vab.y, vqp.x, vqp.y);
+                }
+                float4 *vb = (s & 1) ? vb1 : vb0;
+#pragma unroll
+                for (int i = 0; i < CPL; i++) vb[i * 32 + lane] = it[i];
+                __syncwarp();
+#pragma unroll
+                for (int k = CPL; k < CPL + 7; k++) {
+                    int l2 = min(lane + k / CPL, 31);  // clamped lanes feed masked outputs only
+                    it[k] = vb[(k % CPL) * 32 + l2];
+                }
+                // horizontal 8-tap + SSIM
+#pragma unroll
+                for (int i = 0; i < CPL; i++) {
+                    float2 mab = __fmul2_rn(make_float2(it[i].x, it[i].y), g2[0]);
+                    float2 mqp = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], qpInit);
+#pragma unroll
+                    for (int t = 1; t < 8; t++) {
+                        mab = __ffma2_rn(make_float2(it[i + t].x, it[i + t].y), g2[t], mab);
+                        mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
+                    }
+                    // mab = (mua', mub'); mqp = (E[a'^2+b'^2] + C2, E[a'b'] + C2/2)
+                    float m = mab.x * mab.y;
+                    float nn = fmaf(mab.x, mab.x, mab.y * mab.y);
+                    float th = fmaf(c, mab.x + mab.y, kTh);
+                    float A1h = m + th;                  // (2 mua mub + C1) / 2
+                    float B1 = fmaf(2.f, th, nn);        // mua^2 + mub^2 + C1
+                    float A2h = mqp.y - m;               // (2 sab + C2) / 2
+                    float B2 = mqp.x - nn;               // saa + sbb + C2
+                    float ssim4 = __fdividef(A1h * A2h, B1 * B2);  // ssim / 4
+                    fsum += valid[i] ? ssim4 : 0.f;
+                }
+            }
+        }
+        dsum += (double)fsum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) p.partials[seg] = dsum * 4.0;
+}
+
+// Deterministic per-image reduction of the strip partials → mean SSIM (ssim.go:155-165).
+__global__ void ssim_finalize_kernel(const double *partials, int segsPerImg, long long count,
+                                     double *scores, long long scoreStride) {
+    const int img = blockIdx.x;
+    const double *pp = partials + (long long)img * segsPerImg;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < segsPerImg; i += 32) s += pp[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) scores[(long long)img * scoreStride] = (count == 0) ? 1.0 : s / (double)count;
+}
+
+// pixelSSIM (ssim.go:169-204): global statistics in FP64; images here are < 8 px on a side, or the
+// caller asked for it explicitly.  One block per pair; two passes like the reference.
+__global__ void pixel_ssim_kernel(const uint8_t *a, const uint8_t *b, long long imgStrideA,
+                                  long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h,
+                                  double *scores, long long scoreStride) {
+    __shared__ double red[5][32];
+    __shared__ double mu[2];
+    const int img = blockIdx.x;
+    const uint8_t *ia = a + (long long)img * imgStrideA;
+    const uint8_t *ib = b + (long long)img * imgStrideB;
+    const long long npx = (long long)w * h;
+    const double n = (double)npx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    auto lum = [](const uint8_t *q) {
+        return __dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)q[0]), __dmul_rn(0.587, (double)q[1])),
+                         __dmul_rn(0.114, (double)q[2]));
+    };
+    auto block_sum = [&](double v, int slot) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[slot][warp] = v;
+    };
+    double sa = 0, sb = 0;
+    for (long long i = threadIdx.x; i < npx; i += blockDim.x) {
+        int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        sa += lum(ia + (long long)y * rowStrideA + x * 4);
+        sb += lum(ib + (long long)y * rowStrideB + x * 4);
+    }
+    block_sum(sa, 0);
+    block_sum(sb, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0;
+        for (int k = 0; k < nw; k++) { ta += red[0][k]; tb += red[1][k]; }
+        mu[0] = ta / n;
+        mu[1] = tb / n;
+    }
+    __syncthreads();
+    const double muA = mu[0], muB = mu[1];
+    double saa = 0, sbb = 0, sab = 0;
+    for (long long i = threadIdx.x; i < npx; i += blockDim.x) {
+        int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        double da = lum(ia + (long long)y * rowStrideA + x * 4) - muA;
+        double db = lum(ib + (long long)y * rowStrideB + x * 4) - muB;
+        saa += da * da;
+        sbb += db * db;
+        sab += da * db;
+    }
+    block_sum(saa, 2);
+    block_sum(sbb, 3);
+    block_sum(sab, 4);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 1.0;
+        if (npx > 0) {
+            double taa = 0, tbb = 0, tab = 0;
+            for (int k = 0; k < nw; k++) { taa += red[2][k]; tbb += red[3][k]; tab += red[4][k]; }
+            taa /= n; tbb /= n; tab /= n;
+            double num = (2 * muA * muB + 6.5025) * (2 * tab + 58.5225);
+            double den = (muA * muA + muB * muB + 6.5025) * (taa + tbb + 58.5225);
+            r = num / den;
+        }
+        scores[(long long)img * scoreStride] = r;
+    }
+}
+
+// MSSSIM tail (ssim.go:349-364): out = exp(sum_i w_i * ln(max(score_i, 1e-10))).
+__global__ void msssim_combine_kernel(const double *levelScores, int nLevels, int n,
+                                      const double *weights, double *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = 0.0;
+    for (int l = 0; l < nLevels; l++) r += weights[l] * log(fmax(levelScores[(long long)i * nLevels + l], 1e-10));
+    out[i] = exp(r);
+}
+
+void gaussian1d(float g[8]) {
+    // 1-D factor of ssim.go:223-241: exp(-(x^2+y^2)/(2*1.5^2)) / sum == g(x)*g(y)
+    double v[8], s = 0.0;
+    for (int k = -4; k < 4; k++) { v[k + 4] = exp(-(double)(k * k) / 4.5); s += v[k + 4]; }
+    for (int k = 0; k < 8; k++) g[k] = (float)(v[k] / s);
+}
+
+// Segment geometry: strips of OUTC outputs; rs rows per segment chosen so the grid fills the GPU.
+struct Geo { int cpl, outc, nsx, nsy, rs; };
+Geo geometry(int w, int h, int n) {
+    Geo g;
+    g.cpl = 4;
+    g.outc = 32 * g.cpl - 8;
+    int ow = w - 8, oh = h - 8;
+    g.nsx = (ow + g.outc - 1) / g.outc;
+    // Aim for >= ~8 warps per SM over 148 SMs while keeping the 7-row warm-up overhead small.
+    long long want = 148LL * 16;
+    int rs = 128;
+    while (rs > 16 && (long long)n * g.nsx * ((oh + rs - 1) / rs) < want) rs >>= 1;
+    g.rs = rs;
+    g.nsy = (oh + rs - 1) / rs;
+    return g;
+}
+
+}  // namespace
+
+size_t ssim_scratch_bytes(int w, int h, int n) {
+    if (w < 9 || h < 9) return 256;
+    Geo g = geometry(w, h, n);
+    return align_up(sizeof(double) * (size_t)n * g.nsx * g.nsy, 256);
+}
+
+// Scores for n equal-sized pairs.  Dispatch of ssim.go:35-42: w<8||h<8 → pixelSSIM, else windowed.
+int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, long long imgStrideA,
+                long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h, int n,
+                double *scores, long long scoreStride, void *scratch) {
+    (void)c;
+    if (n <= 0) return FB_OK;
+    if (w < 8 || h < 8) {
+        pixel_ssim_kernel<<<n, 256, 0, s>>>(a, b, imgStrideA, imgStrideB, rowStrideA, rowStrideB, w, h,
+                                            scores, scoreStride);
+        FB_LAUNCHED(1);
+        FB_CUDA(cudaGetLastError());
+        return FB_OK;
+    }
+    if (w == 8 || h == 8) {  // zero windows → 1.0 (ssim.go:162-164)
+        ssim_finalize_kernel<<<n, 32, 0, s>>>((const double *)scratch, 0, 0, scores, scoreStride);
+        FB_LAUNCHED(1);
+        FB_CUDA(cudaGetLastError());
+        return FB_OK;
+    }
+    Geo g = geometry(w, h, n);
+    SsimParams p;
+    p.a = a; p.b = b;
+    p.imgStrideA = imgStrideA; p.imgStrideB = imgStrideB;
+    p.rowStrideA = rowStrideA; p.rowStrideB = rowStrideB;
+    p.w = w; p.h = h; p.n = n;
+    p.nsx = g.nsx; p.nsy = g.nsy; p.rs = g.rs;
+    p.vecOK = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)imgStrideA | (uintptr_t)imgStrideB |
+                (uintptr_t)rowStrideA | (uintptr_t)rowStrideB) & 15) == 0;
+    p.partials = (double *)scratch;
+    gaussian1d(p.g);
+    long long segs = (long long)n * g.nsx * g.nsy;
+    long long blocks = (segs + 3) / 4;
+    ssim_strip_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(p);
+    FB_CUDA(cudaGetLastError());
+    ssim_finalize_kernel<<<n, 32, 0, s>>>(p.partials, g.nsx * g.nsy, (long long)(w - 8) * (h - 8), scores,
+                                          scoreStride);
+    FB_CUDA(cudaGetLastError());
+    FB_LAUNCHED(2);
+    return FB_OK;
+}
+
+int launch_pixel_ssim(cudaStream_t s, const uint8_t *a, const uint8_t *b, long long imgStrideA,
+                      long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h, int n,
+                      double *scores, long long scoreStride) {
+    if (n <= 0) return FB_OK;
+    pixel_ssim_kernel<<<n, 256, 0, s>>>(a, b, imgStrideA, imgStrideB, rowStrideA, rowStrideB, w, h, scores,
+                                        scoreStride);
+    FB_LAUNCHED(1);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+}
+
+int launch_msssim_combine(cudaStream_t s, const double *levelScores, int nLevels, int n,
+                          const double *weights_dev, double *out) {
+    msssim_combine_kernel<<<(n + 127) / 128, 128, 0, s>>>(levelScores, nLevels, n, weights_dev, out);
+    FB_LAUNCHED(1);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+}
+
+}  // namespace fb

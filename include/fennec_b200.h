@@ -1,0 +1,162 @@
+/*
+ * fennec_b200.h — C ABI of libfennec_b200.so: the B200-native replacement for fennec's dense
+ * per-pixel hot path (SSIM family, box downsample, blur / sharpen, Lanczos-3 resize, batch sharder).
+ *
+ * The reference (shamspias/fennec, pure Go) has no FFI; the drop-in boundary is therefore the set
+ * of Go function bodies named beside each entry point below (file:line under the reference tree).
+ * A Go maintainer keeps every exported signature and guard and replaces the loop bodies with cgo
+ * calls to these functions — see INTEGRATION.md for the exact stub.
+ *
+ * Conventions
+ *  - Images are NRGBA: 8-bit interleaved R,G,B,A, non-premultiplied, `stride` bytes per row,
+ *    pixel (x,y) at pix[y*stride + x*4] — Go's image.NRGBA{Pix,Stride} (image.NRGBA.PixOffset).
+ *  - "Host" entry points take host pointers; the library copies in, runs the CUDA kernels and copies
+ *    out before returning (synchronous, like the Go functions they replace).  The caller owns every
+ *    buffer; no host pointer is retained after return (cgo pointer-passing rule).
+ *  - "_dev" entry points take device pointers valid on `device` and a cudaStream_t passed as void*;
+ *    they only enqueue work (no synchronisation) so callers can time them with events on that stream.
+ *  - Return value: FB_OK (0); FB_IDENTITY (1) when the reference would return its INPUT pointer
+ *    unchanged or an empty image (dst is not written); negative = error, fb_last_error() has the text
+ *    for the calling thread.  There is NO CPU fallback inside the library: without a usable GPU every
+ *    compute entry point returns FB_E_NOGPU.  (The Go shim falls back to the pure-Go body.)
+ *  - Thread safety: every entry point may be called concurrently (CompressBatch workers,
+ *    batch.go:84-124); each calling thread gets its own stream and workspace per device.
+ *  - Floating point: scores are binary64; SSIM/MS-SSIM agree with the reference to <= 1e-5 absolute
+ *    (measured <= 2e-6); every uint8 output is bit-exact with the reference's FP64 arithmetic.
+ */
+#ifndef FENNEC_B200_H
+#define FENNEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FB_API __attribute__((visibility("default")))
+#else
+#define FB_API
+#endif
+
+#define FB_OK 0
+#define FB_IDENTITY 1
+#define FB_E_INVALID (-1)
+#define FB_E_NOGPU (-2)
+#define FB_E_CUDA (-3)
+#define FB_E_OOM (-4)
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+
+/* Select the devices this process uses (n == 0: all visible). Idempotent. Returns the device count
+ * or a negative error. Compute entry points call it lazily with n == 0. */
+FB_API int fb_init(const int *devices, int n);
+FB_API void fb_shutdown(void);
+FB_API int fb_device_count(void);
+/* Device used by host entry points called from THIS thread (default 0). */
+FB_API int fb_set_device(int device);
+FB_API const char *fb_last_error(void);
+FB_API const char *fb_version(void);
+
+/* ---- SSIM family (ssim.go) --------------------------------------------------------------- */
+
+/* fennec.SSIM for equal-sized NRGBA inputs — ssim.go:24-43 (the Lanczos pre-resize of `b` at
+ * ssim.go:31-33 is fb_lanczos_resize, called by the host side first). w<8||h<8 → pixelSSIM. */
+FB_API int fb_ssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out);
+/* fennec.SSIMFast — ssim.go:48-70: box-downsample to <=512, then the windowed kernel. */
+FB_API int fb_ssim_fast(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out);
+/* fennec.MSSSIM for equal-sized inputs — ssim.go:313-365. */
+FB_API int fb_msssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out);
+/* pixelSSIM — ssim.go:169-204 (global statistics; any size). */
+FB_API int fb_pixel_ssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h, double *out);
+/* boxDownsample — ssim.go:244-309. FB_IDENTITY when any dim <= 0 (reference returns an empty image). */
+FB_API int fb_box_downsample(const uint8_t *src, int srcStride, int srcW, int srcH,
+                      uint8_t *dst, int dstStride, int dstW, int dstH);
+/* The dims SSIMFast downsamples to — ssim.go:52-56. Returns 1 if a downsample happens, else 0. */
+FB_API int fb_ssim_fast_dims(int w, int h, int *newW, int *newH);
+
+/* ---- effects (effects.go) ---------------------------------------------------------------- */
+
+/* GaussianBlur — effects.go:146-220 with the 1-D kernel supplied by the caller (2*radius+1 weights,
+ * built by the host with ITS libm: Go's math.Exp on the Go side — SURVEY.md H5). src != dst. */
+FB_API int fb_gaussian_blur(const uint8_t *src, int srcStride, int w, int h,
+                     const double *kernel, int radius, uint8_t *dst, int dstStride);
+/* Convenience builder for that kernel — effects.go:153-165 (glibc exp). Returns the radius, writes
+ * 2*radius+1 weights if cap is large enough (else returns -(needed entries)). */
+FB_API int fb_blur_kernel(double sigma, double *kernel, int cap);
+/* GaussianBlur with the kernel built inside (sigma <= 0 → FB_IDENTITY, effects.go:147-149). */
+FB_API int fb_gaussian_blur_sigma(const uint8_t *src, int srcStride, int w, int h, double sigma,
+                           uint8_t *dst, int dstStride);
+/* gaussianBlur3x3 — effects.go:116-141. */
+FB_API int fb_blur3x3(const uint8_t *src, int srcStride, int w, int h, uint8_t *dst, int dstStride);
+/* Sharpen — effects.go:10-45; AdaptiveSharpen — effects.go:49-112. FB_IDENTITY for the guards
+ * (strength <= 0, w < 3, h < 3: the reference returns the same pointer). */
+FB_API int fb_sharpen(const uint8_t *src, int srcStride, int w, int h, double strength,
+               uint8_t *dst, int dstStride);
+FB_API int fb_adaptive_sharpen(const uint8_t *src, int srcStride, int w, int h, double strength,
+                        uint8_t *dst, int dstStride);
+
+/* ---- Lanczos-3 resize (resize.go) -------------------------------------------------------- */
+
+/* Per-destination-index filter taps in CSR form — the [][]weightEntry of resize.go:71-74,164-197.
+ * Taps of destination d are index[start[d] .. start[d+1]) with weight[...]; start has n+1 entries. */
+typedef struct fb_weights {
+    int n;
+    const int *start;
+    const int *index;
+    const double *weight;
+} fb_weights;
+
+/* precomputeWeights — resize.go:164-197 (glibc sin). cap() bounds the entry count. */
+FB_API int fb_lanczos_weights_cap(int dstSize, int srcSize);
+FB_API int fb_build_lanczos_weights(int dstSize, int srcSize, int *start, int *index, double *weight);
+/* lanczosResize — resize.go:37-53 (resizeH :77-118 then resizeV :121-161, uint8 intermediate).
+ * wx / wy may be NULL: the library then builds the tables itself. FB_IDENTITY for any dim <= 0
+ * (reference returns an empty image). Same dims → plain copy (resize.go:45-49). */
+FB_API int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH,
+                      uint8_t *dst, int dstStride, int dstW, int dstH,
+                      const fb_weights *wx, const fb_weights *wy);
+/* smartResize's dimension logic — resize.go:12-32. Returns 1 when it is a no-op (same pointer). */
+FB_API int fb_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int *dstH);
+
+/* ---- device-resident batch entry points (configs 3-5 and the headline metric) ------------- */
+/* n images (or pairs) of identical dims; image i starts at base + i*imgStride bytes. All pointers
+ * are device pointers on `device`; `stream` is a cudaStream_t. Scores land in device memory. */
+
+FB_API int fb_ssim_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b,
+                      int64_t imgStride, int rowStride, int w, int h, int n, double *scores);
+FB_API int fb_ssim_fast_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b,
+                           int64_t imgStride, int rowStride, int w, int h, int n, double *scores);
+FB_API int fb_msssim_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b,
+                        int64_t imgStride, int rowStride, int w, int h, int n, double *scores);
+FB_API int fb_box_downsample_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride,
+                                int srcRowStride, int srcW, int srcH, uint8_t *dst, int64_t dstImgStride,
+                                int dstRowStride, int dstW, int dstH, int n);
+FB_API int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst,
+                               int64_t imgStride, int rowStride, int w, int h, int n,
+                               const double *kernel_host, int radius);
+FB_API int fb_sharpen_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst,
+                         int64_t imgStride, int rowStride, int w, int h, int n, double strength);
+FB_API int fb_adaptive_sharpen_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst,
+                                  int64_t imgStride, int rowStride, int w, int h, int n, double strength);
+FB_API int fb_lanczos_resize_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride,
+                                int srcRowStride, int srcW, int srcH, uint8_t *dst, int64_t dstImgStride,
+                                int dstRowStride, int dstW, int dstH, int n);
+/* Bytes of scratch the _dev call above needs for these dims (the library keeps it per thread). */
+FB_API size_t fb_workspace_bytes(const char *op, int w, int h, int dstW, int dstH, int n);
+
+/* ---- batch sharder (batch.go:58-128) ------------------------------------------------------ */
+
+/* Static contiguous partition of n_items over n_shards (GPUs / ranks): shard s owns
+ * [begin, end). Keeps input order, so results[idx] semantics (batch.go:71,108) hold after a
+ * concatenating gather. */
+FB_API int fb_batch_shard(int n_items, int n_shards, int shard, int *begin, int *end);
+
+/* Kernel launches issued by this thread since the last call (bench.py's gpu_launches). */
+FB_API long long fb_take_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

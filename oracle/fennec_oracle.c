@@ -1,0 +1,815 @@
+/*
+ * fennec_oracle.c — CPU restatement of the fennec hot path in plain C (TEST INFRASTRUCTURE ONLY).
+ * See fennec_oracle.h for the rules and the "parity unpinned" statement.
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fPIC -shared -pthread (oracle/Makefile).
+ * Every function cites the reference file:line (under /root/reference) it restates.
+ */
+#include "fennec_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------
+ * parallelDo — resize.go:200-239: contiguous index blocks over GOMAXPROCS workers.
+ * Every index writes disjoint output, so the partition does not change any result.
+ * ---------------------------------------------------------------------------------------- */
+static int g_procs = 8;
+
+void fo_set_procs(int procs) { g_procs = procs < 1 ? 1 : procs; }
+int fo_get_procs(void) { return g_procs; }
+
+typedef void (*fo_index_fn)(int i, void *ctx);
+
+typedef struct {
+    int from, to;
+    fo_index_fn fn;
+    void *ctx;
+} fo_span;
+
+static void *fo_span_run(void *arg) {
+    fo_span *s = (fo_span *)arg;
+    for (int i = s->from; i < s->to; i++) s->fn(i, s->ctx);
+    return NULL;
+}
+
+static void parallel_do(int start, int stop, fo_index_fn fn, void *ctx) {
+    int count = stop - start;
+    if (count <= 0) return;
+    int procs = g_procs;
+    if (procs > count) procs = count;
+    if (procs <= 1) {
+        for (int i = start; i < stop; i++) fn(i, ctx);
+        return;
+    }
+    int batch = (count + procs - 1) / procs;
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)procs);
+    fo_span *sp = (fo_span *)malloc(sizeof(fo_span) * (size_t)procs);
+    int launched = 0;
+    for (int p = 0; p < procs; p++) {
+        int b0 = start + p * batch;
+        int b1 = b0 + batch;
+        if (b1 > stop) b1 = stop;
+        if (b0 >= b1) continue;
+        sp[launched].from = b0;
+        sp[launched].to = b1;
+        sp[launched].fn = fn;
+        sp[launched].ctx = ctx;
+        if (pthread_create(&tid[launched], NULL, fo_span_run, &sp[launched]) != 0) {
+            fo_span_run(&sp[launched]); /* degrade to inline execution */
+            sp[launched].from = sp[launched].to;
+            tid[launched] = pthread_self();
+        }
+        launched++;
+    }
+    for (int p = 0; p < launched; p++)
+        if (!pthread_equal(tid[p], pthread_self())) pthread_join(tid[p], NULL);
+    free(tid);
+    free(sp);
+}
+
+/* convert.go:149-158 — int64(math.Round(x)) clamped to [0,255]; Round is half away from zero. */
+uint8_t fo_clampf(double x) {
+    long long v = (long long)round(x);
+    if (v > 255) return 255;
+    if (v < 0) return 0;
+    return (uint8_t)v;
+}
+
+/* ssim.go:10-17 — Go evaluates the untyped constant expressions exactly, then rounds once. */
+static const double kC1 = 6.5025;
+static const double kC2 = 58.5225;
+
+/* ssim.go:223-241 */
+void fo_gaussian_kernel(int size, double sigma, double *out) {
+    int half = size / 2;
+    double sum = 0.0;
+    int idx = 0;
+    for (int y = -half; y < half; y++) {
+        for (int x = -half; x < half; x++) {
+            double val = exp(-(double)(x * x + y * y) / (2 * sigma * sigma));
+            out[idx] = val;
+            sum += val;
+            idx++;
+        }
+    }
+    for (int i = 0; i < size * size; i++) out[i] /= sum;
+}
+
+/* The BT.601 expression used at ssim.go:179-180,216 and effects.go:96: (0.299*R + 0.587*G) + 0.114*B. */
+static inline double luma_of(const uint8_t *p) {
+    return 0.299 * (double)p[0] + 0.587 * (double)p[1] + 0.114 * (double)p[2];
+}
+
+/* ssim.go:207-220 */
+void fo_to_luminance(const uint8_t *pix, int stride, int w, int h, double *lum) {
+    for (int y = 0; y < h; y++) {
+        const uint8_t *row = pix + (size_t)y * (size_t)stride;
+        for (int x = 0; x < w; x++) lum[(size_t)y * w + x] = luma_of(row + x * 4);
+    }
+}
+
+/* ssim.go:73-166 */
+typedef struct {
+    const double *lumA, *lumB, *kernel;
+    int w, h, half, rowsPerProc;
+    double sum;
+    long long count;
+    int proc;
+} fo_ssim_job;
+
+static void *fo_ssim_worker(void *arg) {
+    fo_ssim_job *j = (fo_ssim_job *)arg;
+    const int w = j->w, h = j->h, half = j->half;
+    int startY = half + j->proc * j->rowsPerProc; /* ssim.go:101-105 */
+    int endY = startY + j->rowsPerProc;
+    if (endY > h - half) endY = h - half;
+    double localSum = 0.0;
+    long long localCount = 0;
+    for (int y = startY; y < endY; y++) {
+        for (int x = half; x < w - half; x++) {
+            double muA = 0.0, muB = 0.0;
+            double sigAA = 0.0, sigBB = 0.0, sigAB = 0.0;
+            int ki = 0;
+            for (int wy = -half; wy < half; wy++) { /* ssim.go:115-126 */
+                for (int wx = -half; wx < half; wx++) {
+                    size_t idx = (size_t)(y + wy) * w + (x + wx);
+                    double weight = j->kernel[ki];
+                    muA += j->lumA[idx] * weight;
+                    muB += j->lumB[idx] * weight;
+                    ki++;
+                }
+            }
+            ki = 0;
+            for (int wy = -half; wy < half; wy++) { /* ssim.go:128-140 */
+                for (int wx = -half; wx < half; wx++) {
+                    size_t idx = (size_t)(y + wy) * w + (x + wx);
+                    double weight = j->kernel[ki];
+                    double da = j->lumA[idx] - muA;
+                    double db = j->lumB[idx] - muB;
+                    sigAA += da * da * weight;
+                    sigBB += db * db * weight;
+                    sigAB += da * db * weight;
+                    ki++;
+                }
+            }
+            double num = (2 * muA * muB + kC1) * (2 * sigAB + kC2); /* ssim.go:142-145 */
+            double den = (muA * muA + muB * muB + kC1) * (sigAA + sigBB + kC2);
+            localSum += num / den;
+            localCount++;
+        }
+    }
+    j->sum = localSum;
+    j->count = localCount;
+    return NULL;
+}
+
+double fo_windowed_ssim(const double *lumA, const double *lumB, int w, int h, int procs) {
+    const int windowSize = 8;
+    const int half = windowSize / 2;
+    double kernel[64];
+    fo_gaussian_kernel(windowSize, 1.5, kernel);
+
+    if (procs <= 0) procs = g_procs;
+    int rows = h - windowSize + 1; /* ssim.go:85-91 */
+    if (procs > rows) procs = rows;
+    if (procs < 1) procs = 1;
+    int rowsPerProc = (rows + procs - 1) / procs;
+
+    fo_ssim_job *jobs = (fo_ssim_job *)calloc((size_t)procs, sizeof(fo_ssim_job));
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)procs);
+    for (int p = 0; p < procs; p++) {
+        jobs[p].lumA = lumA;
+        jobs[p].lumB = lumB;
+        jobs[p].kernel = kernel;
+        jobs[p].w = w;
+        jobs[p].h = h;
+        jobs[p].half = half;
+        jobs[p].rowsPerProc = rowsPerProc;
+        jobs[p].proc = p;
+    }
+    if (procs == 1) {
+        fo_ssim_worker(&jobs[0]);
+    } else {
+        for (int p = 0; p < procs; p++)
+            if (pthread_create(&tid[p], NULL, fo_ssim_worker, &jobs[p]) != 0) {
+                fo_ssim_worker(&jobs[p]);
+                tid[p] = pthread_self();
+            }
+        for (int p = 0; p < procs; p++)
+            if (!pthread_equal(tid[p], pthread_self())) pthread_join(tid[p], NULL);
+    }
+    double totalSum = 0.0; /* ssim.go:155-165 */
+    long long totalCount = 0;
+    for (int p = 0; p < procs; p++) {
+        totalSum += jobs[p].sum;
+        totalCount += jobs[p].count;
+    }
+    free(jobs);
+    free(tid);
+    if (totalCount == 0) return 1.0;
+    return totalSum / (double)totalCount;
+}
+
+/* ssim.go:169-204 — the reference walks Pix as a flat array (i += 4), ignoring Stride; for
+ * compact images (Stride == 4*w, the only kind the hot path produces) that is every pixel once.
+ * For padded strides we walk rows, which is what the flat walk means for a compact copy. */
+double fo_pixel_ssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h) {
+    double n = (double)(w * h);
+    if (n == 0) return 1.0;
+    double muA = 0.0, muB = 0.0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            double la = luma_of(a + (size_t)y * strideA + x * 4);
+            double lb = luma_of(b + (size_t)y * strideB + x * 4);
+            muA += la;
+            muB += lb;
+        }
+    muA /= n;
+    muB /= n;
+    double sigAA = 0.0, sigBB = 0.0, sigAB = 0.0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            double la = luma_of(a + (size_t)y * strideA + x * 4);
+            double lb = luma_of(b + (size_t)y * strideB + x * 4);
+            double da = la - muA;
+            double db = lb - muB;
+            sigAA += da * da;
+            sigBB += db * db;
+            sigAB += da * db;
+        }
+    sigAA /= n;
+    sigBB /= n;
+    sigAB /= n;
+    double num = (2 * muA * muB + kC1) * (2 * sigAB + kC2);
+    double den = (muA * muA + muB * muB + kC1) * (sigAA + sigBB + kC2);
+    return num / den;
+}
+
+/* ssim.go:35-42 / 62-69 — shared tail of SSIM and SSIMFast. */
+static double ssim_tail(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h) {
+    if (w < 8 || h < 8) return fo_pixel_ssim(a, strideA, b, strideB, w, h);
+    double *lumA = (double *)malloc(sizeof(double) * (size_t)w * h);
+    double *lumB = (double *)malloc(sizeof(double) * (size_t)w * h);
+    fo_to_luminance(a, strideA, w, h, lumA);
+    fo_to_luminance(b, strideB, w, h, lumB);
+    double r = fo_windowed_ssim(lumA, lumB, w, h, 0);
+    free(lumA);
+    free(lumB);
+    return r;
+}
+
+/* ssim.go:24-43 (equal dims) */
+double fo_ssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h) {
+    return ssim_tail(a, strideA, b, strideB, w, h);
+}
+
+/* ssim.go:52-56 */
+int fo_ssim_fast_dims(int w, int h, int *newW, int *newH) {
+    const int maxDim = 512;
+    if (w > maxDim || h > maxDim) {
+        double scale = (double)maxDim / fmax((double)w, (double)h);
+        *newW = (int)fmax(8, round((double)w * scale));
+        *newH = (int)fmax(8, round((double)h * scale));
+        return 1;
+    }
+    *newW = w;
+    *newH = h;
+    return 0;
+}
+
+/* ssim.go:286-309 */
+static void average_box_pixel(const uint8_t *src, int srcStride, uint8_t *dst, int dstStride,
+                              int dx, int dy, int sx0, int sx1, int sy0, int sy1) {
+    double rSum = 0, gSum = 0, bSum = 0, aSum = 0, count = 0;
+    for (int sy = sy0; sy < sy1; sy++)
+        for (int sx = sx0; sx < sx1; sx++) {
+            const uint8_t *p = src + (size_t)sy * srcStride + sx * 4;
+            rSum += (double)p[0];
+            gSum += (double)p[1];
+            bSum += (double)p[2];
+            aSum += (double)p[3];
+            count++;
+        }
+    if (count > 0) {
+        double inv = 1.0 / count;
+        uint8_t *q = dst + (size_t)dy * dstStride + dx * 4;
+        q[0] = fo_clampf(rSum * inv);
+        q[1] = fo_clampf(gSum * inv);
+        q[2] = fo_clampf(bSum * inv);
+        q[3] = fo_clampf(aSum * inv);
+    }
+}
+
+/* ssim.go:244-284 (serial in the reference) */
+int fo_box_downsample(const uint8_t *src, int srcStride, int srcW, int srcH,
+                      uint8_t *dst, int dstStride, int dstW, int dstH) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return 1;
+    double xRatio = (double)srcW / (double)dstW;
+    double yRatio = (double)srcH / (double)dstH;
+    for (int dy = 0; dy < dstH; dy++) {
+        int sy0 = (int)((double)dy * yRatio);
+        int sy1 = (int)((double)(dy + 1) * yRatio);
+        if (sy1 > srcH) sy1 = srcH;
+        if (sy0 >= sy1) sy0 = sy1 - 1;
+        if (sy0 < 0) sy0 = 0;
+        for (int dx = 0; dx < dstW; dx++) {
+            int sx0 = (int)((double)dx * xRatio);
+            int sx1 = (int)((double)(dx + 1) * xRatio);
+            if (sx1 > srcW) sx1 = srcW;
+            if (sx0 >= sx1) sx0 = sx1 - 1;
+            if (sx0 < 0) sx0 = 0;
+            average_box_pixel(src, srcStride, dst, dstStride, dx, dy, sx0, sx1, sy0, sy1);
+        }
+    }
+    return 0;
+}
+
+/* ssim.go:48-70 */
+double fo_ssim_fast(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w, int h) {
+    int nw, nh;
+    if (fo_ssim_fast_dims(w, h, &nw, &nh)) {
+        uint8_t *da = (uint8_t *)calloc((size_t)nw * nh, 4);
+        uint8_t *db = (uint8_t *)calloc((size_t)nw * nh, 4);
+        fo_box_downsample(a, strideA, w, h, da, nw * 4, nw, nh);
+        fo_box_downsample(b, strideB, w, h, db, nw * 4, nw, nh);
+        double r = ssim_tail(da, nw * 4, db, nw * 4, nw, nh);
+        free(da);
+        free(db);
+        return r;
+    }
+    return ssim_tail(a, strideA, b, strideB, w, h);
+}
+
+/* ssim.go:313-365 (equal dims) */
+double fo_msssim(const uint8_t *a, int strideA, const uint8_t *b, int strideB, int w0, int h0) {
+    double weights[5] = {0.0448, 0.2856, 0.3001, 0.2363, 0.1333};
+    int levels = 5, nweights = 5;
+    int w = w0, h = h0;
+    for (int i = 0; i < levels - 1; i++) { /* ssim.go:327-342 */
+        int minDim = (int)fmin((double)w, (double)h);
+        if (minDim < 8) {
+            nweights = i + 1;
+            double sum = 0.0;
+            for (int j = 0; j < nweights; j++) sum += weights[j];
+            for (int j = 0; j < nweights; j++) weights[j] /= sum;
+            break;
+        }
+        w /= 2;
+        h /= 2;
+    }
+    /* ssim.go:345-346 — mutable compact copies */
+    int cw = w0, ch = h0;
+    uint8_t *ca = (uint8_t *)malloc((size_t)cw * ch * 4 + 4);
+    uint8_t *cb = (uint8_t *)malloc((size_t)cw * ch * 4 + 4);
+    for (int y = 0; y < ch; y++) {
+        memcpy(ca + (size_t)y * cw * 4, a + (size_t)y * strideA, (size_t)cw * 4);
+        memcpy(cb + (size_t)y * cw * 4, b + (size_t)y * strideB, (size_t)cw * 4);
+    }
+    double result = 0.0;
+    for (int i = 0; i < nweights; i++) { /* ssim.go:349-362 */
+        double s = fo_ssim_fast(ca, cw * 4, cb, cw * 4, cw, ch);
+        result += weights[i] * log(fmax(s, 1e-10));
+        if (i < nweights - 1) {
+            int nw = cw / 2, nh = ch / 2;
+            if (nw < 8 || nh < 8) break;
+            uint8_t *na = (uint8_t *)calloc((size_t)nw * nh, 4);
+            uint8_t *nb = (uint8_t *)calloc((size_t)nw * nh, 4);
+            fo_box_downsample(ca, cw * 4, cw, ch, na, nw * 4, nw, nh);
+            fo_box_downsample(cb, cw * 4, cw, ch, nb, nw * 4, nw, nh);
+            free(ca);
+            free(cb);
+            ca = na;
+            cb = nb;
+            cw = nw;
+            ch = nh;
+        }
+    }
+    free(ca);
+    free(cb);
+    return exp(result);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * effects.go
+ * ---------------------------------------------------------------------------------------- */
+
+/* effects.go:153 */
+int fo_blur_radius(double sigma) { return (int)ceil(sigma * 3); }
+
+/* effects.go:155-165 */
+void fo_blur_kernel(double sigma, int radius, double *kernel) {
+    int kernelSize = radius * 2 + 1;
+    double sum = 0.0;
+    for (int i = 0; i < kernelSize; i++) {
+        double x = (double)(i - radius);
+        kernel[i] = exp(-(x * x) / (2 * sigma * sigma));
+        sum += kernel[i];
+    }
+    for (int i = 0; i < kernelSize; i++) kernel[i] /= sum;
+}
+
+typedef struct {
+    const uint8_t *src; /* image the taps read */
+    int srcStride;
+    const uint8_t *alpha; /* image alpha is copied from (always the ORIGINAL source) */
+    int alphaStride;
+    uint8_t *dst;
+    int dstStride;
+    int w, h, radius;
+    const double *kernel;
+} fo_blur_ctx;
+
+/* effects.go:169-191 — one row of the horizontal pass */
+static void blur_h_row(int y, void *vctx) {
+    fo_blur_ctx *c = (fo_blur_ctx *)vctx;
+    int kernelSize = c->radius * 2 + 1;
+    for (int x = 0; x < c->w; x++) {
+        double r = 0, g = 0, b = 0;
+        for (int k = 0; k < kernelSize; k++) {
+            int sx = x + k - c->radius;
+            if (sx < 0) sx = 0;
+            else if (sx >= c->w) sx = c->w - 1;
+            const uint8_t *p = c->src + (size_t)y * c->srcStride + sx * 4;
+            double wt = c->kernel[k];
+            r += (double)p[0] * wt;
+            g += (double)p[1] * wt;
+            b += (double)p[2] * wt;
+        }
+        uint8_t *q = c->dst + (size_t)y * c->dstStride + x * 4;
+        q[0] = fo_clampf(r);
+        q[1] = fo_clampf(g);
+        q[2] = fo_clampf(b);
+        q[3] = c->alpha[(size_t)y * c->alphaStride + x * 4 + 3];
+    }
+}
+
+/* effects.go:195-217 — one column of the vertical pass */
+static void blur_v_col(int x, void *vctx) {
+    fo_blur_ctx *c = (fo_blur_ctx *)vctx;
+    int kernelSize = c->radius * 2 + 1;
+    for (int y = 0; y < c->h; y++) {
+        double r = 0, g = 0, b = 0;
+        for (int k = 0; k < kernelSize; k++) {
+            int sy = y + k - c->radius;
+            if (sy < 0) sy = 0;
+            else if (sy >= c->h) sy = c->h - 1;
+            const uint8_t *p = c->src + (size_t)sy * c->srcStride + x * 4;
+            double wt = c->kernel[k];
+            r += (double)p[0] * wt;
+            g += (double)p[1] * wt;
+            b += (double)p[2] * wt;
+        }
+        uint8_t *q = c->dst + (size_t)y * c->dstStride + x * 4;
+        q[0] = fo_clampf(r);
+        q[1] = fo_clampf(g);
+        q[2] = fo_clampf(b);
+        q[3] = c->alpha[(size_t)y * c->alphaStride + x * 4 + 3];
+    }
+}
+
+void fo_gaussian_blur_k(const uint8_t *src, int srcStride, int w, int h,
+                        const double *kernel, int radius, uint8_t *dst, int dstStride) {
+    if (w <= 0 || h <= 0) return;
+    uint8_t *tmp = (uint8_t *)calloc((size_t)w * h, 4);
+    fo_blur_ctx c;
+    c.src = src; c.srcStride = srcStride; c.alpha = src; c.alphaStride = srcStride;
+    c.dst = tmp; c.dstStride = w * 4; c.w = w; c.h = h; c.radius = radius; c.kernel = kernel;
+    parallel_do(0, h, blur_h_row, &c);
+    c.src = tmp; c.srcStride = w * 4;
+    c.dst = dst; c.dstStride = dstStride;
+    parallel_do(0, w, blur_v_col, &c);
+    free(tmp);
+}
+
+int fo_gaussian_blur(const uint8_t *src, int srcStride, int w, int h, double sigma,
+                     uint8_t *dst, int dstStride) {
+    if (sigma <= 0) return 1; /* effects.go:147-149 — same pointer */
+    int radius = fo_blur_radius(sigma);
+    double *kernel = (double *)malloc(sizeof(double) * (size_t)(2 * radius + 1));
+    fo_blur_kernel(sigma, radius, kernel);
+    fo_gaussian_blur_k(src, srcStride, w, h, kernel, radius, dst, dstStride);
+    free(kernel);
+    return 0;
+}
+
+typedef struct {
+    const uint8_t *src;
+    int srcStride;
+    const uint8_t *blur;
+    int blurStride;
+    uint8_t *dst;
+    int dstStride;
+    int w, h;
+    double amount;
+} fo_fx_ctx;
+
+/* effects.go:122-139 — one interior row */
+static void blur3_row(int y, void *vctx) {
+    fo_fx_ctx *c = (fo_fx_ctx *)vctx;
+    const uint8_t *s = c->src;
+    int st = c->srcStride;
+    for (int x = 1; x < c->w - 1; x++)
+        for (int ch = 0; ch < 3; ch++) {
+            double sum = 0;
+            sum += (double)s[(size_t)(y - 1) * st + (x - 1) * 4 + ch] * 1;
+            sum += (double)s[(size_t)(y - 1) * st + (x)*4 + ch] * 2;
+            sum += (double)s[(size_t)(y - 1) * st + (x + 1) * 4 + ch] * 1;
+            sum += (double)s[(size_t)(y)*st + (x - 1) * 4 + ch] * 2;
+            sum += (double)s[(size_t)(y)*st + (x)*4 + ch] * 4;
+            sum += (double)s[(size_t)(y)*st + (x + 1) * 4 + ch] * 2;
+            sum += (double)s[(size_t)(y + 1) * st + (x - 1) * 4 + ch] * 1;
+            sum += (double)s[(size_t)(y + 1) * st + (x)*4 + ch] * 2;
+            sum += (double)s[(size_t)(y + 1) * st + (x + 1) * 4 + ch] * 1;
+            c->dst[(size_t)y * c->dstStride + x * 4 + ch] = fo_clampf(sum / 16.0);
+        }
+}
+
+/* effects.go:116-141 */
+void fo_blur3x3(const uint8_t *src, int srcStride, int w, int h, uint8_t *dst, int dstStride) {
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * dstStride, src + (size_t)y * srcStride, (size_t)w * 4);
+    fo_fx_ctx c;
+    memset(&c, 0, sizeof c);
+    c.src = src; c.srcStride = srcStride; c.dst = dst; c.dstStride = dstStride; c.w = w; c.h = h;
+    parallel_do(1, h - 1, blur3_row, &c);
+}
+
+/* effects.go:28-42 */
+static void sharpen_row(int y, void *vctx) {
+    fo_fx_ctx *c = (fo_fx_ctx *)vctx;
+    for (int x = 0; x < c->w; x++) {
+        const uint8_t *s = c->src + (size_t)y * c->srcStride + x * 4;
+        const uint8_t *bl = c->blur + (size_t)y * c->blurStride + x * 4;
+        uint8_t *d = c->dst + (size_t)y * c->dstStride + x * 4;
+        for (int ch = 0; ch < 3; ch++) {
+            double orig = (double)s[ch];
+            double blur = (double)bl[ch];
+            double val = orig + c->amount * (orig - blur);
+            d[ch] = fo_clampf(val);
+        }
+        d[3] = s[3];
+    }
+}
+
+/* effects.go:10-45 */
+int fo_sharpen(const uint8_t *src, int srcStride, int w, int h, double strength,
+               uint8_t *dst, int dstStride) {
+    if (strength <= 0) return 1;
+    if (strength > 1) strength = 1;
+    if (w < 3 || h < 3) return 1;
+    uint8_t *blurred = (uint8_t *)malloc((size_t)w * h * 4);
+    fo_blur3x3(src, srcStride, w, h, blurred, w * 4);
+    fo_fx_ctx c;
+    c.src = src; c.srcStride = srcStride; c.blur = blurred; c.blurStride = w * 4;
+    c.dst = dst; c.dstStride = dstStride; c.w = w; c.h = h;
+    c.amount = 1.0 + strength * 1.5;
+    parallel_do(0, h, sharpen_row, &c);
+    free(blurred);
+    return 0;
+}
+
+/* effects.go:93-112 */
+static double local_edge_strength(const uint8_t *pix, int stride, int x, int y) {
+#define FO_LUM(px, py) luma_of(pix + (size_t)(py)*stride + (px)*4)
+    double gx = -FO_LUM(x - 1, y - 1) + FO_LUM(x + 1, y - 1) -
+                2 * FO_LUM(x - 1, y) + 2 * FO_LUM(x + 1, y) -
+                FO_LUM(x - 1, y + 1) + FO_LUM(x + 1, y + 1);
+    double gy = -FO_LUM(x - 1, y - 1) - 2 * FO_LUM(x, y - 1) - FO_LUM(x + 1, y - 1) +
+                FO_LUM(x - 1, y + 1) + 2 * FO_LUM(x, y + 1) + FO_LUM(x + 1, y + 1);
+#undef FO_LUM
+    double mag = sqrt(gx * gx + gy * gy);
+    double normalized = mag / 400.0;
+    if (normalized > 1) normalized = 1;
+    return normalized;
+}
+
+/* effects.go:70-87 */
+static void adaptive_row(int y, void *vctx) {
+    fo_fx_ctx *c = (fo_fx_ctx *)vctx;
+    for (int x = 1; x < c->w - 1; x++) {
+        const uint8_t *s = c->src + (size_t)y * c->srcStride + x * 4;
+        double edgeStr = local_edge_strength(c->src, c->srcStride, x, y);
+        double localAmount = c->amount * edgeStr;
+        const uint8_t *bl = c->blur + (size_t)y * c->blurStride + x * 4;
+        uint8_t *d = c->dst + (size_t)y * c->dstStride + x * 4;
+        for (int ch = 0; ch < 3; ch++) {
+            double orig = (double)s[ch];
+            double blur = (double)bl[ch];
+            double val = orig + localAmount * (orig - blur);
+            d[ch] = fo_clampf(val);
+        }
+        d[3] = s[3];
+    }
+}
+
+/* effects.go:49-90 */
+int fo_adaptive_sharpen(const uint8_t *src, int srcStride, int w, int h, double strength,
+                        uint8_t *dst, int dstStride) {
+    if (strength <= 0) return 1;
+    if (strength > 1) strength = 1;
+    if (w < 3 || h < 3) return 1;
+    uint8_t *blurred = (uint8_t *)malloc((size_t)w * h * 4);
+    fo_blur3x3(src, srcStride, w, h, blurred, w * 4);
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * dstStride, src + (size_t)y * srcStride, (size_t)w * 4);
+    fo_fx_ctx c;
+    c.src = src; c.srcStride = srcStride; c.blur = blurred; c.blurStride = w * 4;
+    c.dst = dst; c.dstStride = dstStride; c.w = w; c.h = h;
+    c.amount = 1.0 + strength * 2.0;
+    parallel_do(1, h - 1, adaptive_row, &c);
+    free(blurred);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * resize.go
+ * ---------------------------------------------------------------------------------------- */
+
+/* resize.go:55-69 */
+double fo_lanczos_kernel(double x) {
+    const double lanczosA = 3.0;
+    if (x == 0) return 1.0;
+    if (x < 0) x = -x;
+    if (x >= lanczosA) return 0.0;
+    double xpi = x * M_PI;
+    return (lanczosA * sin(xpi) * sin(xpi / lanczosA)) / (xpi * xpi);
+}
+
+/* resize.go:81-85 / 125-129 */
+static void lanczos_ratio_support(int srcSize, int dstSize, double *ratio, double *support) {
+    *ratio = (double)srcSize / (double)dstSize;
+    *support = 3.0;
+    if (*ratio > 1) *support = 3.0 * *ratio;
+}
+
+static void lanczos_span(int d, int srcSize, double ratio, double support, double *center, int *left, int *right) {
+    *center = ((double)d + 0.5) * ratio - 0.5; /* resize.go:169-178 */
+    *left = (int)ceil(*center - support);
+    *right = (int)floor(*center + support);
+    if (*left < 0) *left = 0;
+    if (*right >= srcSize) *right = srcSize - 1;
+}
+
+int fo_lanczos_weights_cap(int dstSize, int srcSize) {
+    double ratio, support;
+    lanczos_ratio_support(srcSize, dstSize, &ratio, &support);
+    long long cap = 0;
+    for (int d = 0; d < dstSize; d++) {
+        double center;
+        int left, right;
+        lanczos_span(d, srcSize, ratio, support, &center, &left, &right);
+        if (right >= left) cap += right - left + 1;
+    }
+    return (int)cap;
+}
+
+/* resize.go:164-197 */
+int fo_lanczos_weights(int dstSize, int srcSize, int *start, int *index, double *weight) {
+    double ratio, support;
+    lanczos_ratio_support(srcSize, dstSize, &ratio, &support);
+    double filterScale = fmax(ratio, 1.0);
+    int n = 0;
+    for (int d = 0; d < dstSize; d++) {
+        double center;
+        int left, right;
+        lanczos_span(d, srcSize, ratio, support, &center, &left, &right);
+        start[d] = n;
+        double wsum = 0.0;
+        int first = n;
+        for (int s = left; s <= right; s++) {
+            double w = fo_lanczos_kernel(((double)s - center) / filterScale);
+            if (w != 0) {
+                wsum += w;
+                index[n] = s;
+                weight[n] = w;
+                n++;
+            }
+        }
+        if (wsum != 0)
+            for (int i = first; i < n; i++) weight[i] /= wsum;
+    }
+    start[dstSize] = n;
+    return n;
+}
+
+typedef struct {
+    const uint8_t *src;
+    int srcStride;
+    uint8_t *dst;
+    int dstStride;
+    int outer; /* dstW for H (loop over dx inside a row); dstH for V (loop over dy inside a column) */
+    const int *start, *index;
+    const double *weight;
+} fo_rs_ctx;
+
+/* resize.go:89-115 — one row */
+static void resize_h_row(int y, void *vctx) {
+    fo_rs_ctx *c = (fo_rs_ctx *)vctx;
+    for (int dx = 0; dx < c->outer; dx++) {
+        double r = 0, g = 0, b = 0, a = 0;
+        for (int t = c->start[dx]; t < c->start[dx + 1]; t++) {
+            const uint8_t *p = c->src + (size_t)y * c->srcStride + c->index[t] * 4;
+            double sa = (double)p[3];
+            double w = c->weight[t];
+            double aw = sa * w;
+            r += (double)p[0] * aw;
+            g += (double)p[1] * aw;
+            b += (double)p[2] * aw;
+            a += aw;
+        }
+        if (a > 0.5) {
+            uint8_t *q = c->dst + (size_t)y * c->dstStride + dx * 4;
+            double inv = 1.0 / a;
+            q[0] = fo_clampf(r * inv);
+            q[1] = fo_clampf(g * inv);
+            q[2] = fo_clampf(b * inv);
+            q[3] = fo_clampf(a);
+        }
+    }
+}
+
+/* resize.go:133-158 — one column */
+static void resize_v_col(int x, void *vctx) {
+    fo_rs_ctx *c = (fo_rs_ctx *)vctx;
+    for (int dy = 0; dy < c->outer; dy++) {
+        double r = 0, g = 0, b = 0, a = 0;
+        for (int t = c->start[dy]; t < c->start[dy + 1]; t++) {
+            const uint8_t *p = c->src + (size_t)c->index[t] * c->srcStride + x * 4;
+            double sa = (double)p[3];
+            double w = c->weight[t];
+            double aw = sa * w;
+            r += (double)p[0] * aw;
+            g += (double)p[1] * aw;
+            b += (double)p[2] * aw;
+            a += aw;
+        }
+        if (a > 0.5) {
+            uint8_t *q = c->dst + (size_t)dy * c->dstStride + x * 4;
+            double inv = 1.0 / a;
+            q[0] = fo_clampf(r * inv);
+            q[1] = fo_clampf(g * inv);
+            q[2] = fo_clampf(b * inv);
+            q[3] = fo_clampf(a);
+        }
+    }
+}
+
+/* resize.go:77-118 */
+void fo_resize_h(const uint8_t *src, int srcStride, int srcW, int srcH,
+                 uint8_t *dst, int dstStride, int dstW) {
+    int cap = fo_lanczos_weights_cap(dstW, srcW);
+    int *start = (int *)malloc(sizeof(int) * (size_t)(dstW + 1));
+    int *index = (int *)malloc(sizeof(int) * (size_t)(cap + 1));
+    double *weight = (double *)malloc(sizeof(double) * (size_t)(cap + 1));
+    fo_lanczos_weights(dstW, srcW, start, index, weight);
+    fo_rs_ctx c;
+    c.src = src; c.srcStride = srcStride; c.dst = dst; c.dstStride = dstStride; c.outer = dstW;
+    c.start = start; c.index = index; c.weight = weight;
+    parallel_do(0, srcH, resize_h_row, &c);
+    free(start); free(index); free(weight);
+}
+
+/* resize.go:121-161 */
+void fo_resize_v(const uint8_t *src, int srcStride, int srcW, int srcH,
+                 uint8_t *dst, int dstStride, int dstH) {
+    int cap = fo_lanczos_weights_cap(dstH, srcH);
+    int *start = (int *)malloc(sizeof(int) * (size_t)(dstH + 1));
+    int *index = (int *)malloc(sizeof(int) * (size_t)(cap + 1));
+    double *weight = (double *)malloc(sizeof(double) * (size_t)(cap + 1));
+    fo_lanczos_weights(dstH, srcH, start, index, weight);
+    fo_rs_ctx c;
+    c.src = src; c.srcStride = srcStride; c.dst = dst; c.dstStride = dstStride; c.outer = dstH;
+    c.start = start; c.index = index; c.weight = weight;
+    parallel_do(0, srcW, resize_v_col, &c);
+    free(start); free(index); free(weight);
+}
+
+/* resize.go:37-53 */
+int fo_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH,
+                      uint8_t *dst, int dstStride, int dstW, int dstH) {
+    if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return 1;
+    if (srcW == dstW && srcH == dstH) {
+        for (int y = 0; y < srcH; y++) memcpy(dst + (size_t)y * dstStride, src + (size_t)y * srcStride, (size_t)srcW * 4);
+        return 0;
+    }
+    uint8_t *tmp = (uint8_t *)calloc((size_t)dstW * srcH, 4);
+    fo_resize_h(src, srcStride, srcW, srcH, tmp, dstW * 4, dstW);
+    fo_resize_v(tmp, dstW * 4, dstW, srcH, dst, dstStride, dstH);
+    free(tmp);
+    return 0;
+}
+
+/* resize.go:12-32 */
+int fo_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int *dstH) {
+    if (maxW <= 0) maxW = srcW;
+    if (maxH <= 0) maxH = srcH;
+    if (srcW <= maxW && srcH <= maxH) {
+        *dstW = srcW;
+        *dstH = srcH;
+        return 1;
+    }
+    double ratio = fmin((double)maxW / (double)srcW, (double)maxH / (double)srcH);
+    *dstW = (int)fmax(1, round((double)srcW * ratio));
+    *dstH = (int)fmax(1, round((double)srcH * ratio));
+    return 0;
+}
