@@ -122,14 +122,16 @@ __global__ void __launch_bounds__(kThreads) box_naive_kernel(const BoxParams p) 
     }
     long long count = (long long)(sy1 - sy0) * (sx1 - sx0);
     uint8_t *d = p.dst + (long long)img * p.dstImgStride + (long long)dy * p.dstRowStride + (long long)dx * 4;
+    uint32_t out = 0u;  // an empty box leaves the (zero-filled) destination pixel untouched (ssim.go:301)
     if (count > 0) {
         double inv = __ddiv_rn(1.0, (double)count);
         uint32_t r = clampf_dev(__dmul_rn((double)sr, inv));
         uint32_t g = clampf_dev(__dmul_rn((double)sg, inv));
         uint32_t b = clampf_dev(__dmul_rn((double)sb, inv));
         uint32_t a = clampf_dev(__dmul_rn((double)sa, inv));
-        *reinterpret_cast<uint32_t *>(d) = r | (g << 8) | (b << 16) | (a << 24);
+        out = r | (g << 8) | (b << 16) | (a << 24);
     }
+    *reinterpret_cast<uint32_t *>(d) = out;
 }
 
 }  // namespace

@@ -116,8 +116,10 @@ def test_reference_resize_and_effects_behaviour(oracle):  # fennec_test.go:510-5
     tiny = S.make_test_image(2, 2)
     assert oracle.sharpen(tiny, 0.5) is tiny and oracle.adaptive_sharpen(tiny, 0.5) is tiny
     assert oracle.gaussian_blur(img, 0.0) is img and oracle.gaussian_blur(img, -1.0) is img
-    assert np.any(oracle.sharpen(img, 0.5) != img)
     st = S.make_striped_image(100, 100, 10)
+    assert np.any(oracle.sharpen(st, 0.8) != st)
+    lin = S.make_test_image(100, 100)
+    assert np.array_equal(oracle.sharpen(lin, 0.5), lin)  # a linear ramp is a fixed point of the 3x3 blur
     assert np.any(oracle.adaptive_sharpen(st, 0.5) != st)
     bl = oracle.gaussian_blur(img, 2.0)
     assert bl.shape == img.shape and oracle.ssim(img, bl) >= 0.3

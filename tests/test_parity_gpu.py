@@ -91,11 +91,14 @@ def test_reference_resize_tests(lib):  # fennec_test.go:510-560
 
 def test_reference_effects_tests(lib):  # fennec_test.go:612-736
     img = S.make_test_image(100, 100)
-    assert np.any(api.Sharpen(img, 0.5) != img)
-    assert api.Sharpen(img, 0.0) is img
+    st = S.make_striped_image(100, 100, 10)
+    sharp = api.Sharpen(st, 0.8)                                   # TestSharpen
+    assert sharp.shape == st.shape and np.any(sharp != st)
+    assert api.Sharpen(img, 0.0) is img                            # TestSharpenZeroStrength
+    assert api.Sharpen(st, 5.0).shape == st.shape                  # TestSharpenClampedStrength
+    assert np.array_equal(api.Sharpen(st, 5.0), api.Sharpen(st, 1.0))
     tiny = S.make_test_image(2, 2)
     assert api.Sharpen(tiny, 0.5) is tiny and api.AdaptiveSharpen(tiny, 0.5) is tiny
-    st = S.make_striped_image(100, 100, 10)
     assert np.any(api.AdaptiveSharpen(st, 0.5) != st)
     assert api.AdaptiveSharpen(st, 0.0) is st
     bl = api.GaussianBlur(img, 2.0)
