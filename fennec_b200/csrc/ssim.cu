@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace fb {
 
@@ -50,9 +51,26 @@ __device__ __forceinline__ float luma_magic(uint32_t px) {
     return __uint_as_float(t);
 }
 
-template <int CPL>
-__device__ __forceinline__ void load_px(const uint8_t *p, bool vec, int nvalid, uint32_t (&o)[CPL]) {
-    if (vec) {
+// ---- per-lane async global→shared copies (LDGSTS) with commit/wait groups -------------------------
+// A TMA bulk-copy + mbarrier ring was measured first (profiles/ssim_strip_r1e): it removed the
+// long-scoreboard stall too, but the elected-lane issue path (R2UR/UBLKCP/expect_tx) cost ~60 extra
+// instructions per row per warp — more than it saved for 512-byte rows.  cp.async needs 4.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void *src) {
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// CPL packed pixels of one row for this lane.  FAST: one aligned vector load (the warp-uniform common
+// case); otherwise per-pixel guarded loads (last strip of images whose width is not a multiple of 4,
+// or unaligned buffers).
+template <int CPL, bool FAST>
+__device__ __forceinline__ void load_px(const uint8_t *p, int nvalid, uint32_t (&o)[CPL]) {
+    if (FAST) {
         if (CPL == 4) {
             uint4 v = ld_nc_u128(p);
             o[0] = v.x; o[1] = v.y; o[2] = v.z; o[CPL - 1] = v.w;
@@ -67,11 +85,201 @@ __device__ __forceinline__ void load_px(const uint8_t *p, bool vec, int nvalid, 
 }
 
 template <int CPL>
+struct StripCtx {
+    const uint8_t *pa, *pb;
+    int rowStrideA, rowStrideB;
+    int nIn, nvalid, lane;
+    float K, c;
+    float g[8];
+    bool valid[CPL];
+    float4 *vb0, *vb1;
+    // FAST path only: per-warp ring of kStages row buffers filled by cp.async.
+    uint8_t *ring;        // [kStages][2 images][32*CPL*4 bytes]
+};
+
+constexpr int kStages = 4;  // rows in flight per warp (power of two: the stage is the ring slot & 3)
+
+// The row walk of one strip segment; returns this lane's sum of ssim/4 over its valid outputs.
+template <int CPL, bool FAST>
+__device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
+    const uint8_t *pa = q.pa, *pb = q.pb;
+    const int nIn = q.nIn, lane = q.lane;
+    const float c = q.c;
+    const float2 s2 = make_float2(kLumaScale, kLumaScale);
+    const float2 K2 = make_float2(q.K, q.K);
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
+    // formula constants (DESIGN.md K1): th = c*(mua'+mub') + (c^2 + C1/2)
+    const float kTh = fmaf(c, c, 0.5f * kC1f);
+    const float2 qpInit = make_float2(kC2f, 0.5f * kC2f);  // Q' = Q + C2, P' = P + C2/2
+
+    float2 rab[8][CPL], rqp[8][CPL];
+    constexpr uint32_t kRowBuf = 32 * CPL * 4;  // bytes per image per stage
+    // FAST: each lane copies its own CPL pixels of both images into its slot of a shared-memory ring with
+    // cp.async, kStages rows ahead, and reads them back after cp.async.wait_group — no cross-lane
+    // traffic, so no barrier is needed.  Register prefetch could not give that distance: all LDGs share
+    // scoreboard slots, so waiting for row r also waited for the loads of rows r+1, r+2 issued after it
+    // (profiles/ssim_strip_r1d: 23% of samples in long-scoreboard on the first consumer).
+    // !FAST: two rows in flight in registers, ping-pong by row parity.
+    uint32_t pfa[2][CPL], pfb[2][CPL];
+    const uint32_t myRing = FAST ? smem_u32(q.ring) + lane * (CPL * 4) : 0u;
+    const uint8_t *myRingP = q.ring + lane * (CPL * 4);
+    if (FAST) {
+#pragma unroll
+        for (int row = 0; row < kStages; row++) {  // rows 0..3 exist (nIn >= 8)
+            cp_async<CPL * 4>(myRing + (2 * row) * kRowBuf, pa);
+            cp_async<CPL * 4>(myRing + (2 * row + 1) * kRowBuf, pb);
+            cp_async_commit();
+            pa += q.rowStrideA;
+            pb += q.rowStrideB;
+        }
+    } else {
+        load_px<CPL, false>(pa, q.nvalid, pfa[0]);
+        load_px<CPL, false>(pb, q.nvalid, pfb[0]);
+        pa += q.rowStrideA;
+        pb += q.rowStrideB;
+        load_px<CPL, false>(pa, q.nvalid, pfa[1]);  // row 1 always exists (nIn >= 8)
+        load_px<CPL, false>(pb, q.nvalid, pfb[1]);
+    }
+
+    // FB_FETCH(S, R): make row R's pixels available in pfa/pfb[(S)&1].  Groups complete in row order,
+    // and one group is committed per row (empty at the tail), so "all but the newest kStages-1" == row R.
+#define FB_FETCH(S, R)                                                                          \
+    if (FAST) {                                                                                 \
+        cp_async_wait<kStages - 1>();                                                           \
+        const uint8_t *rb_ = myRingP + (2 * ((S) & (kStages - 1))) * kRowBuf;                   \
+        if (CPL == 4) {                                                                         \
+            uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                                  \
+            uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + kRowBuf);                        \
+            pfa[(S) & 1][0] = va_.x; pfa[(S) & 1][1] = va_.y; pfa[(S) & 1][2] = va_.z; pfa[(S) & 1][CPL - 1] = va_.w; \
+            pfb[(S) & 1][0] = vb_.x; pfb[(S) & 1][1] = vb_.y; pfb[(S) & 1][2] = vb_.z; pfb[(S) & 1][CPL - 1] = vb_.w; \
+        } else {                                                                                \
+            uint2 va_ = *reinterpret_cast<const uint2 *>(rb_);                                  \
+            uint2 vb_ = *reinterpret_cast<const uint2 *>(rb_ + kRowBuf);                        \
+            pfa[(S) & 1][0] = va_.x; pfa[(S) & 1][CPL - 1] = va_.y;                             \
+            pfb[(S) & 1][0] = vb_.x; pfb[(S) & 1][CPL - 1] = vb_.y;                             \
+        }                                                                                       \
+    }
+
+    // FB_REFILL(S, R): after row R has been consumed, start fetching row R+kStages into the same slot.
+#define FB_REFILL(S, R)                                                                         \
+    if (FAST) {                                                                                 \
+        if ((R) + kStages < nIn) {                                                              \
+            cp_async<CPL * 4>(myRing + (2 * ((S) & (kStages - 1))) * kRowBuf, pa);              \
+            cp_async<CPL * 4>(myRing + (2 * ((S) & (kStages - 1)) + 1) * kRowBuf, pb);          \
+            pa += q.rowStrideA;                                                                 \
+            pb += q.rowStrideB;                                                                 \
+        }                                                                                       \
+        cp_async_commit();                                                                      \
+    } else {                                                                                    \
+        if ((R) + 2 < nIn) {                                                                    \
+            pa += q.rowStrideA;                                                                 \
+            pb += q.rowStrideB;                                                                 \
+            load_px<CPL, false>(pa, q.nvalid, pfa[(S) & 1]);                                    \
+            load_px<CPL, false>(pb, q.nvalid, pfb[(S) & 1]);                                    \
+        }                                                                                       \
+    }
+
+#define FB_PLANES(S, R)                                                                         \
+    FB_FETCH(S, R)                                                                              \
+    _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                           \
+        float2 f = make_float2(luma_magic(pfa[(S) & 1][i]), luma_magic(pfb[(S) & 1][i]));       \
+        float2 t = __ffma2_rn(f, s2, K2);                                                       \
+        float2 sq = __fmul2_rn(t, t);                                                           \
+        rab[S][i] = t;                                                                          \
+        rqp[S][i] = make_float2(sq.x + sq.y, t.x * t.y);                                        \
+    }                                                                                           \
+    FB_REFILL(S, R)
+
+    // warm-up: input rows 0..6 fill ring slots 0..6
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        FB_PLANES(r, r)
+    }
+
+    float fs[CPL];  // per-lane sums of ssim/4 (<= 128 rows * 0.25 each: FP32 is ample)
+#pragma unroll
+    for (int i = 0; i < CPL; i++) fs[i] = 0.f;
+    constexpr int kVLanes = 36;               // 32 lanes + pad for the 7-column right halo (ceil(7/CPL) <= 4)
+    constexpr int kVBuf = CPL * kVLanes;      // float4 per buffer
+    float4 *myV = q.vb0 + lane + ((7 & 1) ? kVBuf : 0);  // first main-loop row is r = 7 (odd)
+
+    // One iteration per input row r >= 7: its planes go to ring slot r&7 and output row r-7 is produced.
+    // Only the slot-specific part (planes + vertical taps, whose register indices depend on r&7) is
+    // replicated by the switch; the horizontal pass and the SSIM formula exist once.
+#pragma unroll 1
+    for (int r = 7; r < nIn; r++) {
+        float4 it[CPL + 7];
+
+#define FB_SSIM_STEP(S)                                                                         \
+    case S: {                                                                                   \
+        FB_PLANES(S, r)                                                                         \
+        /* rows r-7..r live in slots (S+1+j)&7, j = 0..7 */                                     \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 vab = __fmul2_rn(rab[(S + 1) & 7][i], g2[0]);                                \
+            float2 vqp = __fmul2_rn(rqp[(S + 1) & 7][i], g2[0]);                                \
+            _Pragma("unroll") for (int j = 1; j < 8; j++) {                                     \
+                vab = __ffma2_rn(rab[(S + 1 + j) & 7][i], g2[j], vab);                          \
+                vqp = __ffma2_rn(rqp[(S + 1 + j) & 7][i], g2[j], vqp);                          \
+            }                                                                                   \
+            it[i] = make_float4(vab.x, vab.y, vqp.x, vqp.y);                                    \
+        }                                                                                       \
+    } break;
+
+        switch (r & 7) {
+            FB_SSIM_STEP(0) FB_SSIM_STEP(1) FB_SSIM_STEP(2) FB_SSIM_STEP(3)
+            FB_SSIM_STEP(4) FB_SSIM_STEP(5) FB_SSIM_STEP(6) FB_SSIM_STEP(7)
+        }
+#undef FB_SSIM_STEP
+
+        // V rows are padded to kVLanes lane slots so neighbour reads need no clamp: item k of this lane is
+        // at a compile-time offset from its own slot (lanes 30/31 read the pad; their outputs are masked).
+        float4 *vb = myV;
+        myV = (r & 1) ? myV - kVBuf : myV + kVBuf;  // double buffer (row parity)
+#pragma unroll
+        for (int i = 0; i < CPL; i++) vb[i * kVLanes] = it[i];
+        __syncwarp();
+#pragma unroll
+        for (int k = CPL; k < CPL + 7; k++) it[k] = vb[(k % CPL) * kVLanes + k / CPL];
+        // horizontal 8-tap + SSIM
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            float2 mab = __fmul2_rn(make_float2(it[i].x, it[i].y), g2[0]);
+            float2 mqp = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], qpInit);
+#pragma unroll
+            for (int t = 1; t < 8; t++) {
+                mab = __ffma2_rn(make_float2(it[i + t].x, it[i + t].y), g2[t], mab);
+                mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
+            }
+            // mab = (mua', mub'); mqp = (E[a'^2+b'^2] + C2, E[a'b'] + C2/2)
+            float m = mab.x * mab.y;
+            float nn = fmaf(mab.x, mab.x, mab.y * mab.y);
+            float th = fmaf(c, mab.x + mab.y, kTh);
+            float A1h = m + th;                  // (2 mua mub + C1) / 2
+            float B1 = fmaf(2.f, th, nn);        // mua^2 + mub^2 + C1
+            float A2h = mqp.y - m;               // (2 sab + C2) / 2
+            float B2 = mqp.x - nn;               // saa + sbb + C2
+            float ssim4 = __fdividef(A1h * A2h, B1 * B2);  // ssim / 4
+            fs[i] += q.valid[i] ? ssim4 : 0.f;
+        }
+    }
+#undef FB_PLANES
+#undef FB_FETCH
+#undef FB_REFILL
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    return dsum;
+}
+
+template <int CPL>
 __global__ void __launch_bounds__(128, (CPL == 4 ? 2 : 4)) ssim_strip_kernel(const SsimParams p) {
     constexpr int WARPS = 4;
     constexpr int INC = 32 * CPL;    // input columns per strip
     constexpr int OUTC = INC - 8;    // outputs per strip (multiple of 4 → 16-byte aligned strips)
-    __shared__ float4 vbuf[WARPS][2][INC];
+    __shared__ float4 vbuf[WARPS][2][CPL * 36];   // padded V rows, see walk_strip
+    __shared__ __align__(128) uint8_t pxring[WARPS][kStages][2][INC * 4];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -84,133 +292,48 @@ __global__ void __launch_bounds__(128, (CPL == 4 ? 2 : 4)) ssim_strip_kernel(con
 
     const int X0 = sx * OUTC, Y0 = sy * p.rs;
     const int nOut = min(p.rs, (p.h - 8) - Y0);  // output rows of this segment (>= 1)
-    const int nIn = nOut + 7;
     const int xl = X0 + CPL * lane;
-    const int nvalid = max(0, min(CPL, p.w - xl));
-    const bool vec = p.vecOK && nvalid == CPL;
 
-    const uint8_t *pa = p.a + (long long)img * p.imgStrideA + (long long)Y0 * p.rowStrideA + (long long)xl * 4;
-    const uint8_t *pb = p.b + (long long)img * p.imgStrideB + (long long)Y0 * p.rowStrideB + (long long)xl * 4;
-
-    // Centring constant: luma of image a at the strip's centre pixel (same for every lane).
-    float K, c;
-    {
-        int cx = min(X0 + OUTC / 2, p.w - 1), cy = min(Y0 + nIn / 2, p.h - 1);
-        uint32_t cp = ld_nc_u32(p.a + (long long)img * p.imgStrideA + (long long)cy * p.rowStrideA + (long long)cx * 4);
-        float f = luma_magic(cp);                       // 2^23 + L
-        K = -(f * kLumaScale);                          // a' = F*s + K  ~  luma - luma_c
-        c = -fmaf(8388608.0f, kLumaScale, K);           // the centring this K really applies
-    }
-    const float2 s2 = make_float2(kLumaScale, kLumaScale);
-    const float2 K2 = make_float2(K, K);
-    float2 g2[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) g2[j] = make_float2(p.g[j], p.g[j]);
-
-    // formula constants (see DESIGN.md): th = c*(mua'+mub') + (c^2 + C1/2)
-    const float kTh = fmaf(c, c, 0.5f * kC1f);
-    const float2 qpInit = make_float2(kC2f, 0.5f * kC2f);  // Q' = Q + C2, P' = P + C2/2
-
-    bool valid[CPL];
-#pragma unroll
-    for (int i = 0; i < CPL; i++) valid[i] = (CPL * lane + i < OUTC) && (xl + i < p.w - 8);
-
-    float2 rab[8][CPL], rqp[8][CPL];
-    uint32_t na[CPL], nb[CPL];
-    load_px<CPL>(pa, vec, nvalid, na);
-    load_px<CPL>(pb, vec, nvalid, nb);
-
-    auto planes = [&](int slot, const uint32_t(&ca)[CPL], const uint32_t(&cb)[CPL]) {
+    StripCtx<CPL> q;
+    q.nIn = nOut + 7;
+    q.lane = lane;
+    q.nvalid = max(0, min(CPL, p.w - xl));
+    q.rowStrideA = p.rowStrideA;
+    q.rowStrideB = p.rowStrideB;
+    q.vb0 = &vbuf[warp][0][0];
+    q.vb1 = &vbuf[warp][1][0];
+    q.ring = &pxring[warp][0][0][0];
+    if (lane < 4) {  // zero the pad slots once (they feed masked outputs only, but must stay finite)
 #pragma unroll
         for (int i = 0; i < CPL; i++) {
-            float2 f = make_float2(luma_magic(ca[i]), luma_magic(cb[i]));
-            float2 t = __ffma2_rn(f, s2, K2);           // (a', b')
-            float2 sq = __fmul2_rn(t, t);
-            rab[slot][i] = t;
-            rqp[slot][i] = make_float2(sq.x + sq.y, t.x * t.y);
+            vbuf[warp][0][i * 36 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vbuf[warp][1][i * 36 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    };
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j++) q.g[j] = p.g[j];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) q.valid[i] = (CPL * lane + i < OUTC) && (xl + i < p.w - 8);
 
-    // prologue: rows 0..6 → slots 0..6
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-        uint32_t ca[CPL], cb[CPL];
-#pragma unroll
-        for (int i = 0; i < CPL; i++) { ca[i] = na[i]; cb[i] = nb[i]; }
-        pa += p.rowStrideA;
-        pb += p.rowStrideB;
-        load_px<CPL>(pa, vec, nvalid, na);  // row j+1 <= 7 <= nIn-1 always exists
-        load_px<CPL>(pb, vec, nvalid, nb);
-        planes(j, ca, cb);
+    const uint8_t *ia = p.a + (long long)img * p.imgStrideA;
+    const uint8_t *ib = p.b + (long long)img * p.imgStrideB;
+    {   // Centring constant: luma of image a at the strip's centre pixel (same for every lane).
+        int cx = min(X0 + OUTC / 2, p.w - 1), cy = min(Y0 + q.nIn / 2, p.h - 1);
+        float f = luma_magic(ld_nc_u32(ia + (long long)cy * p.rowStrideA + (long long)cx * 4));  // 2^23 + L
+        q.K = -(f * kLumaScale);                          // a' = F*s + K  ~  luma - luma_c
+        q.c = -fmaf(8388608.0f, kLumaScale, q.K);         // the centring this K really applies
     }
 
-    double dsum = 0.0;
-    float4 *vb0 = &vbuf[warp][0][0];
-    float4 *vb1 = &vbuf[warp][1][0];
+    // Warp-uniform choice of the load path.  Lanes entirely right of the image (their outputs are all
+    // masked) re-read the strip's first columns so that the whole warp can use aligned vector loads.
+    const bool fast = p.vecOK && __all_sync(0xffffffffu, q.nvalid == CPL || q.nvalid == 0);
+    const int xld = (fast && q.nvalid == 0) ? X0 : xl;
+    q.pa = ia + (long long)Y0 * p.rowStrideA + (long long)xld * 4;
+    q.pb = ib + (long long)Y0 * p.rowStrideB + (long long)xld * 4;
+    if (fast && q.nvalid == 0) q.nvalid = CPL;
 
-    for (int yo = 0; yo < nOut; yo += 8) {
-        float fsum = 0.f;
-#pragma unroll
-        for (int s = 0; s < 8; s++) {
-            if (yo + s < nOut) {  // warp-uniform
-                uint32_t ca[CPL], cb[CPL];
-#pragma unroll
-                for (int i = 0; i < CPL; i++) { ca[i] = na[i]; cb[i] = nb[i]; }
-                if (yo + s + 8 < nIn) {  // prefetch the next input row
-                    pa += p.rowStrideA;
-                    pb += p.rowStrideB;
-                    load_px<CPL>(pa, vec, nvalid, na);
-                    load_px<CPL>(pb, vec, nvalid, nb);
-                }
-                planes((s + 7) & 7, ca, cb);
-
-                // vertical 8-tap: output row yo+s uses input rows yo+s+j, j = 0..7 → slots (s+j)&7
-                float4 it[CPL + 7];
-#pragma unroll
-                for (int i = 0; i < CPL; i++) {
-                    float2 vab = __fmul2_rn(rab[s & 7][i], g2[0]);
-                    float2 vqp = __fmul2_rn(rqp[s & 7][i], g2[0]);
-#pragma unroll
-                    for (int j = 1; j < 8; j++) {
-                        vab = __ffma2_rn(rab[(s + j) & 7][i], g2[j], vab);
-                        vqp = __ffma2_rn(rqp[(s + j) & 7][i], g2[j], vqp);
-                    }
-                    it[i] = make_float4(vab.x, vab.y, vqp.x, vqp.y);
-                }
-                float4 *vb = (s & 1) ? vb1 : vb0;
-#pragma unroll
-                for (int i = 0; i < CPL; i++) vb[i * 32 + lane] = it[i];
-                __syncwarp();
-#pragma unroll
-                for (int k = CPL; k < CPL + 7; k++) {
-                    int l2 = min(lane + k / CPL, 31);  // clamped lanes feed masked outputs only
-                    it[k] = vb[(k % CPL) * 32 + l2];
-                }
-                // horizontal 8-tap + SSIM
-#pragma unroll
-                for (int i = 0; i < CPL; i++) {
-                    float2 mab = __fmul2_rn(make_float2(it[i].x, it[i].y), g2[0]);
-                    float2 mqp = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], qpInit);
-#pragma unroll
-                    for (int t = 1; t < 8; t++) {
-                        mab = __ffma2_rn(make_float2(it[i + t].x, it[i + t].y), g2[t], mab);
-                        mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
-                    }
-                    // mab = (mua', mub'); mqp = (E[a'^2+b'^2] + C2, E[a'b'] + C2/2)
-                    float m = mab.x * mab.y;
-                    float nn = fmaf(mab.x, mab.x, mab.y * mab.y);
-                    float th = fmaf(c, mab.x + mab.y, kTh);
-                    float A1h = m + th;                  // (2 mua mub + C1) / 2
-                    float B1 = fmaf(2.f, th, nn);        // mua^2 + mub^2 + C1
-                    float A2h = mqp.y - m;               // (2 sab + C2) / 2
-                    float B2 = mqp.x - nn;               // saa + sbb + C2
-                    float ssim4 = __fdividef(A1h * A2h, B1 * B2);  // ssim / 4
-                    fsum += valid[i] ? ssim4 : 0.f;
-                }
-            }
-        }
-        dsum += (double)fsum;
-    }
+    double dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if (lane == 0) p.partials[seg] = dsum * 4.0;
@@ -313,9 +436,16 @@ void gaussian1d(float g[8]) {
 
 // Segment geometry: strips of OUTC outputs; rs rows per segment chosen so the grid fills the GPU.
 struct Geo { int cpl, outc, nsx, nsy, rs; };
+int ssim_cpl() {
+    static int cpl = [] {
+        const char *e = getenv("FB_SSIM_CPL");  // tuning knob: columns per lane (2 or 4)
+        return (e && e[0] == '2') ? 2 : 4;
+    }();
+    return cpl;
+}
 Geo geometry(int w, int h, int n) {
     Geo g;
-    g.cpl = 4;
+    g.cpl = ssim_cpl();
     g.outc = 32 * g.cpl - 8;
     int ow = w - 8, oh = h - 8;
     g.nsx = (ow + g.outc - 1) / g.outc;
@@ -368,7 +498,8 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
     gaussian1d(p.g);
     long long segs = (long long)n * g.nsx * g.nsy;
     long long blocks = (segs + 3) / 4;
-    ssim_strip_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(p);
+    if (g.cpl == 4) ssim_strip_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(p);
+    else ssim_strip_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(p);
     FB_CUDA(cudaGetLastError());
     ssim_finalize_kernel<<<n, 32, 0, s>>>(p.partials, g.nsx * g.nsy, (long long)(w - 8) * (h - 8), scores,
                                           scoreStride);

@@ -125,6 +125,14 @@ __global__ void __launch_bounds__(256) bench(float *out, int iters, float seed) 
         } else if (MODE == 15) {  // I2F.F64 from int x4 + DADD
 #pragma unroll
             for (int i = 0; i < 4; i++) { d[i] += (double)(int)(u[i] & 0xff); u[i] += 0x01010101u; }
+        } else if (MODE == 17) {  // dp2a lo+hi x4 each (8 IDP.2A)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                unsigned t;
+                asm volatile("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(114u), "r"(u[i]), "r"(0x4B000000u));
+                asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(u[i + 4]) : "r"(299u | (587u << 16)), "r"(u[i]), "r"(t));
+                u[i] += u[i + 4];
+            }
         } else if (MODE == 16) {  // HFMA2 x8 (fp16x2)
 #pragma unroll
             for (int i = 0; i < 8; i++) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(0x3c003c00), "r"(0x00010001));
@@ -136,6 +144,56 @@ __global__ void __launch_bounds__(256) bench(float *out, int iters, float seed) 
 #pragma unroll
     for (int i = 0; i < 8; i++) s += (float)d[i] + (float)u[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + c;
+}
+
+// The SSIM kernel's vertical-pass pattern: 8 accumulator pairs, 8 taps, distinct x pairs, scalar weights.
+template <int PACKED>
+__global__ void __launch_bounds__(128) filt(float *out, int iters, float seed) {
+    float2 x[8][4];
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        g[j] = seed * (j + 1) * 0.01f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[j][i] = make_float2(seed + j + threadIdx.x, seed - i);
+    }
+    float2 tot = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float2 acc = make_float2(0.f, 0.f), acc2 = make_float2(1.f, 1.f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (PACKED) {
+                    acc = __ffma2_rn(x[j][i], make_float2(g[j], g[j]), acc);
+                    acc2 = __ffma2_rn(x[(j + 3) & 7][i], make_float2(g[j], g[j]), acc2);
+                } else {
+                    acc.x = fmaf(x[j][i].x, g[j], acc.x); acc.y = fmaf(x[j][i].y, g[j], acc.y);
+                    acc2.x = fmaf(x[(j + 3) & 7][i].x, g[j], acc2.x); acc2.y = fmaf(x[(j + 3) & 7][i].y, g[j], acc2.y);
+                }
+            }
+            tot.x += acc.x + acc2.x; tot.y += acc.y + acc2.y;
+            x[i][i].x += tot.x * 1e-9f;  // keep the ring live and changing (static index: stays in registers)
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = tot.x + tot.y;
+}
+
+template <int PACKED>
+static int run_filt(const char *name, float *out, int sms, int clk_khz, int blocksPerSM) {
+    int blocks = sms * blocksPerSM;
+    filt<PACKED><<<blocks, 128>>>(out, 16, 1.0f);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 5; r++) {
+        cudaEventRecord(e0); filt<PACKED><<<blocks, 128>>>(out, ITERS, 1.0f); cudaEventRecord(e1);
+        cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    double total = 128.0 /*lane fma per iter*/ * ITERS * 128.0 * blocks;
+    double per_s = total / (best * 1e-3);
+    printf("%-34s %8.3f ms  %7.2f lane-fma/clk/SM (%d warps/SM)\n", name, best, per_s / sms / (clk_khz * 1e3), blocksPerSM * 4);
+    return 0;
 }
 
 struct Case { const char *name; int mode; double lane_ops_per_iter; };
@@ -191,5 +249,10 @@ int main() {
     run<10>("FFMA2 x8 + I2F x4 [fma-ops]", 16, out, sms, clk);
     run<11>("FFMA2 x8 + DFMA x4 [fma32-ops]", 16, out, sms, clk);
     run<12>("FFMA x16 + LDS.128 x2 [fma]", 16, out, sms, clk);
+    run<17>("DP2A x8 (+4 IADD)", 8, out, sms, clk);
+    run_filt<1>("filter pattern FFMA2", out, sms, clk, 2);
+    run_filt<1>("filter pattern FFMA2", out, sms, clk, 4);
+    run_filt<0>("filter pattern FFMA", out, sms, clk, 2);
+    run_filt<0>("filter pattern FFMA", out, sms, clk, 4);
     return 0;
 }
