@@ -97,6 +97,9 @@ struct StripCtx {
     uint8_t *ring;        // [kStages][2 images][32*CPL*4 bytes]
 };
 
+#ifndef FB_SSIM_MINB4
+#define FB_SSIM_MINB4 2
+#endif
 constexpr int kStages = 4;  // rows in flight per warp (power of two: the stage is the ring slot & 3)
 
 // The row walk of one strip segment; returns this lane's sum of ssim/4 over its valid outputs.
@@ -274,7 +277,7 @@ __device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
 }
 
 template <int CPL>
-__global__ void __launch_bounds__(128, (CPL == 4 ? 2 : 4)) ssim_strip_kernel(const SsimParams p) {
+__global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_strip_kernel(const SsimParams p) {
     constexpr int WARPS = 4;
     constexpr int INC = 32 * CPL;    // input columns per strip
     constexpr int OUTC = INC - 8;    // outputs per strip (multiple of 4 → 16-byte aligned strips)

@@ -1,0 +1,117 @@
+//go:build cgo && fennec_b200
+
+// Package fennec — cgo shim binding the B200 hot path (libfennec_b200.so) behind fennec's own
+// function bodies.  AUTHORED, NOT COMPILED: no Go toolchain exists in the build image (see
+// INTEGRATION.md).  It is deliberately mechanical: pointer/len/stride marshalling and
+// status → pure-Go fallback, nothing else.
+//
+// cgo rules honoured: only &img.Pix[0] (a Go pointer to pointer-free memory) crosses the boundary,
+// the library retains no pointer after return, and every call is synchronous.
+package fennec
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../include
+#cgo LDFLAGS: -L${SRCDIR}/../fennec_b200 -lfennec_b200 -Wl,-rpath,${SRCDIR}/../fennec_b200
+#include "fennec_b200.h"
+*/
+import "C"
+
+import (
+	"image"
+	"unsafe"
+)
+
+func pix(img *image.NRGBA) *C.uint8_t {
+	if len(img.Pix) == 0 {
+		return nil
+	}
+	return (*C.uint8_t)(unsafe.Pointer(&img.Pix[img.PixOffset(img.Rect.Min.X, img.Rect.Min.Y)]))
+}
+
+// gpuSSIM replaces the tail of SSIM (ssim.go:35-42). ok=false → run the pure-Go body.
+func gpuSSIM(a, b *image.NRGBA) (float64, bool) {
+	var out C.double
+	st := C.fb_ssim(pix(a), C.int(a.Stride), pix(b), C.int(b.Stride),
+		C.int(a.Bounds().Dx()), C.int(a.Bounds().Dy()), &out)
+	return float64(out), st == C.FB_OK
+}
+
+// gpuSSIMFast replaces the body of SSIMFast (ssim.go:48-70).
+func gpuSSIMFast(a, b *image.NRGBA) (float64, bool) {
+	var out C.double
+	st := C.fb_ssim_fast(pix(a), C.int(a.Stride), pix(b), C.int(b.Stride),
+		C.int(a.Bounds().Dx()), C.int(a.Bounds().Dy()), &out)
+	return float64(out), st == C.FB_OK
+}
+
+// gpuMSSSIM replaces MSSSIM after the size check (ssim.go:324-364).
+func gpuMSSSIM(a, b *image.NRGBA) (float64, bool) {
+	var out C.double
+	st := C.fb_msssim(pix(a), C.int(a.Stride), pix(b), C.int(b.Stride),
+		C.int(a.Bounds().Dx()), C.int(a.Bounds().Dy()), &out)
+	return float64(out), st == C.FB_OK
+}
+
+// gpuBoxDownsample replaces the loops of boxDownsample (ssim.go:250-283); dst is image.NewNRGBA'd by the caller.
+func gpuBoxDownsample(src, dst *image.NRGBA) bool {
+	st := C.fb_box_downsample(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
+		pix(dst), C.int(dst.Stride), C.int(dst.Bounds().Dx()), C.int(dst.Bounds().Dy()))
+	return st == C.FB_OK
+}
+
+// gpuGaussianBlur replaces both passes of GaussianBlur (effects.go:167-217). The kernel slice is the one
+// GaussianBlur already builds with Go's math.Exp (effects.go:155-165), so pixel parity does not depend on libm.
+func gpuGaussianBlur(src, dst *image.NRGBA, kernel []float64, radius int) bool {
+	st := C.fb_gaussian_blur(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
+		(*C.double)(unsafe.Pointer(&kernel[0])), C.int(radius), pix(dst), C.int(dst.Stride))
+	return st == C.FB_OK
+}
+
+// gpuSharpen / gpuAdaptiveSharpen replace effects.go:24-42 / 63-87 (guards stay in Go: they return img itself).
+func gpuSharpen(src, dst *image.NRGBA, strength float64, adaptive bool) bool {
+	var st C.int
+	if adaptive {
+		st = C.fb_adaptive_sharpen(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
+			C.double(strength), pix(dst), C.int(dst.Stride))
+	} else {
+		st = C.fb_sharpen(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
+			C.double(strength), pix(dst), C.int(dst.Stride))
+	}
+	return st == C.FB_OK
+}
+
+// csr flattens precomputeWeights' [][]weightEntry (resize.go:164-197) for the ABI. The backing slices
+// are returned so the caller keeps them alive across the call; pointers to them are pinned for the
+// duration of the call because they sit inside a C struct (cgo rule: use runtime.Pinner, Go ≥ 1.21).
+func csr(w [][]weightEntry) (start, index []C.int, weight []C.double) {
+	start = make([]C.int, len(w)+1)
+	for d, e := range w {
+		start[d+1] = start[d] + C.int(len(e))
+	}
+	index = make([]C.int, start[len(w)])
+	weight = make([]C.double, start[len(w)])
+	n := 0
+	for _, e := range w {
+		for _, t := range e {
+			index[n], weight[n] = C.int(t.index), C.double(t.weight)
+			n++
+		}
+	}
+	return
+}
+
+// gpuLanczosResize replaces resizeH+resizeV (resize.go:51-52). Passing nil tables lets the library build
+// them (glibc sin); passing Go-built tables keeps bit parity independent of libm.
+func gpuLanczosResize(src, dst *image.NRGBA) bool {
+	st := C.fb_lanczos_resize(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
+		pix(dst), C.int(dst.Stride), C.int(dst.Bounds().Dx()), C.int(dst.Bounds().Dy()), nil, nil)
+	return st == C.FB_OK
+}
+
+// gpuShard is the partition CompressBatch uses when it hands whole sub-batches to per-GPU workers
+// (batch.go:63-81): shard s of n owns items [begin, end).
+func gpuShard(nItems, nShards, shard int) (begin, end int, ok bool) {
+	var b, e C.int
+	st := C.fb_batch_shard(C.int(nItems), C.int(nShards), C.int(shard), &b, &e)
+	return int(b), int(e), st == C.FB_OK
+}

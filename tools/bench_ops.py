@@ -1,0 +1,67 @@
+"""Device-resident timing of every op of the hot path at the BASELINE.json sizes (CUDA events, batch API).
+Prints one JSON object per op: ms/step, work rate and achieved algorithmic GB/s vs the measured HBM peak."""
+import json, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fennec_b200 import batch
+PEAK = 6533.8
+try:
+    PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+except Exception:
+    pass
+only = sys.argv[1:] 
+
+def noise(n, h, w, seed, alpha=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = torch.randint(0, 256, (n, h, w, 4), dtype=torch.uint8, device="cuda", generator=g)
+    if not alpha: t[..., 3] = 255
+    return t
+
+def timeit(fn, iters):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+def report(name, ms, n, mp_per_item, bytes_per_item, note=""):
+    gbs = n * bytes_per_item / ms / 1e6
+    print(json.dumps({"op": name, "n": n, "ms": round(ms, 4), "MP_per_s": round(n * mp_per_item / ms * 1e3, 1),
+                      "items_per_s": round(n / ms * 1e3, 1), "algorithmic_GBps": round(gbs, 1),
+                      "frac_of_measured_hbm": round(gbs / PEAK, 4), "note": note}), flush=True)
+
+def want(k): return not only or k in only
+
+if want("ssim"):
+    a, b = noise(16, 2160, 3840, 1), noise(16, 2160, 3840, 2)
+    report("SSIM 3840x2160 (metric)", timeit(lambda: batch.ssim_batch(a, b), 20), 16, 8.2944, 2 * 3840 * 2160 * 4)
+    del a, b
+if want("ssim_fast"):
+    a, b = noise(16, 3024, 4032, 3), noise(16, 3024, 4032, 4)
+    report("SSIMFast 4032x3024 (config 2)", timeit(lambda: batch.ssim_fast_batch(a, b), 20), 16, 12.192768, 2 * 4032 * 3024 * 4)
+    del a, b
+if want("blur"):
+    x = noise(16, 2160, 3840, 5); y = torch.empty_like(x)
+    report("GaussianBlur s=2 3840x2160", timeit(lambda: batch.gaussian_blur_batch(x, 2.0, out=y), 5), 16, 8.2944, 2 * 3840 * 2160 * 4)
+    report("Sharpen 0.5 3840x2160", timeit(lambda: batch.sharpen_batch(x, 0.5, out=y), 10), 16, 8.2944, 2 * 3840 * 2160 * 4)
+    report("AdaptiveSharpen 0.5 3840x2160", timeit(lambda: batch.adaptive_sharpen_batch(x, 0.5, out=y), 5), 16, 8.2944, 2 * 3840 * 2160 * 4)
+    z = torch.empty_like(x)
+    def both():
+        batch.gaussian_blur_batch(x, 2.0, out=y); batch.sharpen_batch(y, 0.5, out=z)
+    report("Blur s=2 + Sharpen 0.5 (config 3)", timeit(both, 5), 16, 8.2944, 4 * 3840 * 2160 * 4)
+    del x, y, z
+if want("lanczos"):
+    x = noise(8, 4320, 7680, 6); y = torch.zeros((8, 1080, 1920, 4), dtype=torch.uint8, device="cuda")
+    report("Lanczos3 7680x4320->1920x1080 (config 4)", timeit(lambda: batch.lanczos_resize_batch(x, 1920, 1080, out=y), 3), 8, 33.1776,
+           7680 * 4320 * 4 + 1920 * 1080 * 4)
+    del x, y
+if want("msssim"):
+    a, b = noise(4, 4320, 7680, 7), noise(4, 4320, 7680, 8)
+    report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 4, 33.1776, 2 * 7680 * 4320 * 4)
+    x = noise(8, 4320, 7680, 9)
+    y = torch.zeros((8, 288, 512, 4), dtype=torch.uint8, device="cuda")
+    report("boxDownsample 7680x4320->512x288", timeit(lambda: batch.box_downsample_batch(x, 512, 288, out=y), 10), 8, 33.1776, 7680 * 4320 * 4)
+    y2 = torch.zeros((8, 2160, 3840, 4), dtype=torch.uint8, device="cuda")
+    report("boxDownsample 7680x4320->3840x2160", timeit(lambda: batch.box_downsample_batch(x, 3840, 2160, out=y2), 10), 8, 33.1776, 7680 * 4320 * 4 * 1.25)
