@@ -13,6 +13,8 @@
 // the reference's.  The uint8 intermediate between the passes is kept (effects.go:186-188).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace fb {
 
 namespace {
@@ -88,6 +90,233 @@ __global__ void __launch_bounds__(256) blur_pass_kernel(const BlurParams p) {
                            (long long)x * 4) & 0xFF000000u;
     *reinterpret_cast<uint32_t *>(p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride +
                                   (long long)x * 4) = out[0] | (out[1] << 8) | (out[2] << 16) | a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-tiled fast passes for radius <= 8 (sigma <= 2.66; config 3 uses sigma = 2 → radius 6).
+// Each thread produces 16 consecutive outputs along the filter axis, so every input byte is converted
+// to float once (PRMT into the mantissa of 2^23, one FADD — I2F runs at 1/8 of the FMA rate) and feeds
+// up to 2R+1 accumulators.  All tap indices are compile-time, accumulators never leave registers.
+// Outputs whose FP32 value lies within eps of a rounding boundary are recomputed by the same thread in
+// the reference's exact FP64 order (~0.1 % of channel values), so bytes stay identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTile = 16;   // outputs per thread
+constexpr int kChunkB = 80; // bytes per 16-px chunk in the staging buffer (64 + 16 pad: conflict-free LDS.128)
+
+__device__ __forceinline__ float byte_to_float(uint32_t px, int k) {
+    // [byte k, 0x00, 0x00, 0x4B] = bits of 2^23 + byte
+    uint32_t m = __byte_perm(px, 0x4B000000u, 0x7540u | (uint32_t)k);
+    return __uint_as_float(m) - 8388608.0f;
+}
+
+// Round v (known to be within [-0.25, 255.25]) to nearest; flag when within eps of a tie.
+__device__ __forceinline__ uint32_t round_flag(float v, float lim, bool &amb) {
+    float t = v + 12582912.0f;             // 1.5 * 2^23: the integer lands in the low mantissa bits
+    float rounded = t - 12582912.0f;
+    amb = fabsf(v - rounded) >= lim;       // lim = 0.5 - eps
+    return __float_as_uint(t) & 0x1FFu;
+}
+
+// Exact FP64 tap sum of one output (the reference's sequence, effects.go:172-188) over taps that were
+// staged as packed pixels at `px[k * strideWords]`, k = 0..2R (clamping already applied by the stager).
+__device__ __forceinline__ uint32_t blur_exact_taps(const uint32_t *px, int strideWords, int taps,
+                                                    const double *kernel) {
+    double r = 0.0, g = 0.0, b = 0.0;
+    for (int k = 0; k < taps; k++) {
+        uint32_t v = px[k * strideWords];
+        double wt = __ldg(kernel + k);
+        r = __dadd_rn(r, __dmul_rn((double)(v & 0xFF), wt));
+        g = __dadd_rn(g, __dmul_rn((double)((v >> 8) & 0xFF), wt));
+        b = __dadd_rn(b, __dmul_rn((double)((v >> 16) & 0xFF), wt));
+    }
+    return clampf_dev(r) | (clampf_dev(g) << 8) | (clampf_dev(b) << 16);
+}
+
+// acc pairs: outputs (2m, 2m+1) of one channel share an FFMA2; input i feeds output j with tap
+// k = i - off - j, so the pair uses weights (w[k], w[k-1]) — kept as register pairs wp[k], k = 0..2R+1,
+// with w[-1] = w[2R+1] = 0.  Halves the issue slots of the tap loop (the pipe time is unchanged).
+template <int R, int NIN, int OFF>
+__device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const float *kernel32,
+                                               float2 (&acc)[kTile / 2][3]) {
+    float2 wp[2 * R + 2];
+#pragma unroll
+    for (int k = 0; k <= 2 * R + 1; k++)
+        wp[k] = make_float2(k <= 2 * R ? __ldg(kernel32 + k) : 0.f, k >= 1 ? __ldg(kernel32 + k - 1) : 0.f);
+#pragma unroll
+    for (int m = 0; m < kTile / 2; m++) acc[m][0] = acc[m][1] = acc[m][2] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = OFF - R; i < OFF + kTile + R; i++) {
+        const float f0 = byte_to_float(raw[i], 0), f1 = byte_to_float(raw[i], 1), f2 = byte_to_float(raw[i], 2);
+        const float2 f00 = make_float2(f0, f0), f11 = make_float2(f1, f1), f22 = make_float2(f2, f2);
+#pragma unroll
+        for (int m = 0; m < kTile / 2; m++) {
+            const int k = i - OFF - 2 * m + R;  // tap of input i for output 2m (output 2m+1 uses k-1)
+            if (k >= 0 && k <= 2 * R + 1) {
+                acc[m][0] = __ffma2_rn(f00, wp[k], acc[m][0]);
+                acc[m][1] = __ffma2_rn(f11, wp[k], acc[m][1]);
+                acc[m][2] = __ffma2_rn(f22, wp[k], acc[m][2]);
+            }
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
+    __shared__ __align__(16) uint8_t stage[4][34 * kChunkB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y = blockIdx.y * 4 + warp, img = blockIdx.z;
+    if (y >= p.h) return;  // warp-uniform; no block barrier below
+    const int xs = blockIdx.x * (32 * kTile);
+    const uint8_t *srow = p.src + (long long)img * p.srcImgStride + (long long)y * p.srcRowStride;
+    uint8_t *st = stage[warp];
+    const bool vecOK = ((((uintptr_t)p.src | (uintptr_t)p.srcImgStride | (uintptr_t)p.srcRowStride) & 15) == 0);
+    // stage chunks -1..32 (34 chunks of 16 px) with clamp-to-edge (effects.go:173-178)
+    for (int v = lane; v < 34 * 4; v += 32) {
+        const int chunk = v >> 2, quad = v & 3;
+        const int px0 = xs + (chunk - 1) * kTile + quad * 4;
+        uint4 q;
+        if (vecOK && px0 >= 0 && px0 + 3 < p.w) {
+            q = *reinterpret_cast<const uint4 *>(srow + (long long)px0 * 4);
+        } else {
+            uint32_t t[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int sx = min(max(px0 + i, 0), p.w - 1);
+                t[i] = ld_nc_u32(srow + (long long)sx * 4);
+            }
+            q = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<uint4 *>(st + chunk * kChunkB + quad * 16) = q;
+    }
+    __syncwarp();
+    const int x0 = xs + lane * kTile;
+    if (x0 >= p.w) return;
+    // window: px x0-8 .. x0+23  =  stage chunks lane (second half), lane+1 (all), lane+2 (first half)
+    uint32_t raw[32];
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+        const int i0 = v * 4 + 8;  // px index relative to the start of stage chunk `lane`
+        uint4 q = *reinterpret_cast<const uint4 *>(st + (lane + i0 / kTile) * kChunkB + (i0 % kTile) * 4);
+        raw[v * 4 + 0] = q.x; raw[v * 4 + 1] = q.y; raw[v * 4 + 2] = q.z; raw[v * 4 + 3] = q.w;
+    }
+    float2 acc[kTile / 2][3];
+    blur_taps_fp32<R, 32, 8>(raw, p.kernel32, acc);
+    const float lim = 0.5f - p.eps;
+    uint32_t out[kTile];
+    uint32_t ambMask = 0;
+#pragma unroll
+    for (int j = 0; j < kTile; j++) {
+        bool a0, a1, a2;
+        const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
+        const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
+        const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
+        uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
+        out[j] = r | (g << 8) | (b << 16) | (raw[8 + j] & 0xFF000000u);  // alpha from the source (effects.go:189)
+        if (a0 | a1 | a2) ambMask |= 1u << j;
+    }
+    uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
+    const bool dvec = ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0);
+    if (dvec && x0 + kTile <= p.w) {
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            *reinterpret_cast<uint4 *>(drow + v * 16) = make_uint4(out[v * 4], out[v * 4 + 1], out[v * 4 + 2], out[v * 4 + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kTile; j++)
+            if (x0 + j < p.w) *reinterpret_cast<uint32_t *>(drow + j * 4) = out[j];
+    }
+    // Ambiguous outputs: exact FP64 sequence from the staged bytes, overwriting the pixel just stored
+    // (same thread, program order).  Taps of output j start at stage pixel 16*lane + 16 + j - R.
+    const uint32_t *stw = reinterpret_cast<const uint32_t *>(st);
+    while (ambMask) {
+        const int j = __ffs(ambMask) - 1;
+        ambMask &= ambMask - 1;
+        if (x0 + j < p.w) {
+            uint32_t taps[2 * R + 1];
+#pragma unroll
+            for (int k = 0; k <= 2 * R; k++) {
+                const int sp = 16 * lane + 16 + j - R + k;  // stage pixel index
+                taps[k] = stw[(sp >> 4) * (kChunkB / 4) + (sp & 15)];
+            }
+            uint32_t e = blur_exact_taps(taps, 1, 2 * R + 1, p.kernel);
+            uint32_t alpha = stw[((16 * lane + 16 + j) >> 4) * (kChunkB / 4) + ((16 * lane + 16 + j) & 15)] & 0xFF000000u;
+            *reinterpret_cast<uint32_t *>(drow + j * 4) = e | alpha;
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
+    constexpr int NIN = kTile + 2 * R;
+    __shared__ uint32_t dump[128 * (NIN + 1)];  // per-thread tap dump for the exact path (+1: bank spread)
+    const int x = blockIdx.x * 128 + threadIdx.x, img = blockIdx.z;
+    const int y0 = blockIdx.y * kTile;
+    if (x >= p.w) return;
+    const uint8_t *scol = p.src + (long long)img * p.srcImgStride + (long long)x * 4;
+    uint32_t raw[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) {
+        int sy = min(max(y0 - R + i, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
+        raw[i] = __ldg(reinterpret_cast<const uint32_t *>(scol + (long long)sy * p.srcRowStride));
+    }
+    float2 acc[kTile / 2][3];
+    blur_taps_fp32<R, NIN, R>(raw, p.kernel32, acc);
+    const float lim = 0.5f - p.eps;
+    const uint8_t *acol = p.alpha + (long long)img * p.alphaImgStride + (long long)x * 4;
+    uint8_t *dcol = p.dst + (long long)img * p.dstImgStride + (long long)x * 4;
+    uint32_t ambMask = 0;
+#pragma unroll
+    for (int j = 0; j < kTile; j++) {
+        const int y = y0 + j;
+        if (y < p.h) {
+            bool a0, a1, a2;
+            const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
+            const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
+            const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
+            uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
+            if (a0 | a1 | a2) ambMask |= 1u << j;
+            uint32_t a = ld_nc_u32(acol + (long long)y * p.alphaRowStride) & 0xFF000000u;  // effects.go:215
+            *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = r | (g << 8) | (b << 16) | a;
+        }
+    }
+    if (ambMask) {  // rare: dump this thread's taps to shared memory and redo the flagged outputs exactly
+        uint32_t *mine = dump + threadIdx.x * (NIN + 1);
+#pragma unroll
+        for (int i = 0; i < NIN; i++) mine[i] = raw[i];
+        while (ambMask) {
+            const int j = __ffs(ambMask) - 1;
+            ambMask &= ambMask - 1;
+            const int y = y0 + j;
+            uint32_t e = blur_exact_taps(mine + j, 1, 2 * R + 1, p.kernel);
+            uint32_t a = ld_nc_u32(acol + (long long)y * p.alphaRowStride) & 0xFF000000u;
+            *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = e | a;
+        }
+    }
+}
+
+template <int R>
+static void launch_blur_fast(cudaStream_t s, BlurParams p, int n, bool vertical) {
+    if (!vertical) {
+        dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + 3) / 4, n);
+        blur_h_fast_kernel<R><<<grid, 128, 0, s>>>(p);
+    } else {
+        dim3 grid((p.w + 127) / 128, (p.h + kTile - 1) / kTile, n);
+        blur_v_fast_kernel<R><<<grid, 128, 0, s>>>(p);
+    }
+}
+
+static bool launch_blur_fast_any(cudaStream_t s, const BlurParams &p, int n, bool vertical) {
+    switch (p.radius) {
+        case 1: launch_blur_fast<1>(s, p, n, vertical); return true;
+        case 2: launch_blur_fast<2>(s, p, n, vertical); return true;
+        case 3: launch_blur_fast<3>(s, p, n, vertical); return true;
+        case 4: launch_blur_fast<4>(s, p, n, vertical); return true;
+        case 5: launch_blur_fast<5>(s, p, n, vertical); return true;
+        case 6: launch_blur_fast<6>(s, p, n, vertical); return true;
+        case 7: launch_blur_fast<7>(s, p, n, vertical); return true;
+        case 8: launch_blur_fast<8>(s, p, n, vertical); return true;
+        default: return false;
+    }
 }
 
 struct FxParams {
@@ -187,18 +416,21 @@ int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long 
     BlurParams p;
     p.w = w; p.h = h; p.radius = radius;
     p.kernel = kernel_dev; p.kernel32 = kernel32_dev;
-    p.eps = (float)((2 * radius + 3) * 255.0 * 1.1920928955078125e-07);
+    // FP32 error bound of the tap sum: each of the `taps` FMAs rounds a partial sum <= 255 (<= 255*2^-24 each)
+    // and the FP32 weights differ from the FP64 ones by <= 2^-24 relative (<= 255*2^-24 in total); 25 % margin.
+    p.eps = (float)((2 * radius + 2) * 255.0 * 5.9604644775390625e-08 * 1.25);
     p.exactOnly = (p.eps >= 0.25f) ? 1 : 0;  // absurdly long kernels: no useful fast path
     dim3 grid((w + 255) / 256, h, n);
     // horizontal: src → tmp
     p.src = src; p.srcImgStride = imgStride; p.srcRowStride = rowStride;
     p.alpha = src; p.alphaImgStride = imgStride; p.alphaRowStride = rowStride;
     p.dst = tmp; p.dstImgStride = tmpImgStride; p.dstRowStride = tmpRowStride;
-    blur_pass_kernel<false><<<grid, 256, 0, s>>>(p);
+    const bool fastOK = !p.exactOnly && getenv("FB_BLUR_GENERIC") == nullptr;
+    if (!(fastOK && launch_blur_fast_any(s, p, n, false))) blur_pass_kernel<false><<<grid, 256, 0, s>>>(p);
     // vertical: tmp → dst, alpha from the original
     p.src = tmp; p.srcImgStride = tmpImgStride; p.srcRowStride = tmpRowStride;
     p.dst = dst; p.dstImgStride = imgStride; p.dstRowStride = rowStride;
-    blur_pass_kernel<true><<<grid, 256, 0, s>>>(p);
+    if (!(fastOK && launch_blur_fast_any(s, p, n, true))) blur_pass_kernel<true><<<grid, 256, 0, s>>>(p);
     FB_LAUNCHED(2);
     FB_CUDA(cudaGetLastError());
     return FB_OK;
