@@ -406,6 +406,170 @@ __global__ void __launch_bounds__(256) sharpen_kernel(const FxParams p) {
                                   (long long)x * 4) = result;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled Sharpen / AdaptiveSharpen / blur3x3: each thread owns 4 adjacent pixels (one 128-bit load per
+// row) and walks kFxRows rows down, keeping the horizontal 1-2-1 sums of the previous two rows in
+// registers, so every source pixel is loaded ~1.5 times instead of 9.  The 3x3 sums are SIMD-in-register
+// on 16-bit lanes (R|B and G|A words).  Finish per channel:
+//   INTK >= 0: amount * 2^INTK is an integer A (e.g. 1.75 = 7/4): V = (orig << k) + A*(orig - blur) is the
+//              reference's FP64 value times 2^k EXACTLY, so round-half-away is (V + 2^(k-1)) >> k.
+//   INTK <  0: FP64 with the reference's multiply/add order; int -> double through the 2^52 mantissa
+//              trick and rounding through u = x + 2^52 (no I2F/F2I/FRND: those run at 16/clk/SM).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFxRows = 8;
+
+__device__ __forceinline__ double small_int_to_double(int v) {  // exact for |v| < 2^31
+    return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// clampF (convert.go:149-158) for |x| < 2^31 without conversion instructions.
+__device__ __forceinline__ uint32_t clampf_magic(double x) {
+    if (!(x >= 0.5)) return 0u;        // (-inf, 0.5) rounds to <= 0
+    if (x >= 254.5) return 255u;
+    double u = x + 4503599627370496.0;  // RNE to integer in the low mantissa bits
+    double t = u - 4503599627370496.0;
+    uint32_t r = (uint32_t)__double2loint(u);
+    if (x - t == 0.5) r += 1;           // RNE went down on a tie; the reference rounds half away from zero
+    return r;
+}
+
+struct FxTileParams {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcImgStride, dstImgStride;
+    int srcRowStride, dstRowStride;
+    int w, h;
+    double amount;
+    int A, half;   // integer path: A = amount * 2^k, half = 2^(k-1)
+    int vecOK;
+};
+
+template <int MODE /*0 blur3x3, 1 sharpen, 2 adaptive*/, int INTK>
+__global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int yb = blockIdx.y * kFxRows, img = blockIdx.z;
+    if (x0 >= p.w) return;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *d = p.dst + (long long)img * p.dstImgStride;
+    const bool full = p.vecOK && x0 + 4 <= p.w;
+    const int xl = max(x0 - 1, 0), xr = min(x0 + 4, p.w - 1);
+
+    // px[0] = left neighbour, px[1..4] = own pixels, px[5] = right neighbour (clamped: only borders see the clamp)
+    auto load_row = [&](int y, uint32_t (&px)[6]) {
+        const uint8_t *row = s + (long long)min(max(y, 0), p.h - 1) * p.srcRowStride;
+        if (full) {
+            uint4 q = *reinterpret_cast<const uint4 *>(row + (long long)x0 * 4);
+            px[1] = q.x; px[2] = q.y; px[3] = q.z; px[4] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) px[1 + i] = ld_nc_u32(row + (long long)min(x0 + i, p.w - 1) * 4);
+        }
+        px[0] = ld_nc_u32(row + (long long)xl * 4);
+        px[5] = ld_nc_u32(row + (long long)xr * 4);
+    };
+    // horizontal 1-2-1 sums on packed 16-bit lanes: hrb = R|B, hga = G|A
+    auto hsum = [&](const uint32_t (&px)[6], uint32_t (&hrb)[4], uint32_t (&hga)[4]) {
+        uint32_t rb[6], ga[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { rb[i] = px[i] & 0x00FF00FFu; ga[i] = (px[i] >> 8) & 0x00FF00FFu; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            hrb[i] = rb[i] + 2 * rb[i + 1] + rb[i + 2];
+            hga[i] = ga[i] + 2 * ga[i + 1] + ga[i + 2];
+        }
+    };
+
+    uint32_t pPrev[6], pCur[6], pNext[6];
+    uint32_t hPrevRB[4], hPrevGA[4], hCurRB[4], hCurGA[4], hNextRB[4], hNextGA[4];
+    load_row(yb - 1, pPrev);
+    load_row(yb, pCur);
+    hsum(pPrev, hPrevRB, hPrevGA);
+    hsum(pCur, hCurRB, hCurGA);
+#pragma unroll 1
+    for (int r = 0; r < kFxRows; r++) {
+        const int y = yb + r;
+        if (y >= p.h) break;
+        load_row(y + 1, pNext);
+        hsum(pNext, hNextRB, hNextGA);
+        uint32_t out[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = x0 + i;
+            const uint32_t c = pCur[1 + i];
+            uint32_t res = c;
+            const bool interior = x >= 1 && x < p.w - 1 && y >= 1 && y < p.h - 1;
+            if (interior) {
+                // gaussianBlur3x3 (effects.go:124-136): (sum + 8) >> 4 on each 16-bit lane
+                const uint32_t brb = ((hPrevRB[i] + 2 * hCurRB[i] + hNextRB[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+                const uint32_t bga = ((hPrevGA[i] + 2 * hCurGA[i] + hNextGA[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+                const int bl[3] = {(int)(brb & 0xFF), (int)(bga & 0xFF), (int)(brb >> 16)};
+                if (MODE == 0) {
+                    res = (uint32_t)bl[0] | ((uint32_t)bl[1] << 8) | ((uint32_t)bl[2] << 16) | (c & 0xFF000000u);
+                } else {
+                    double amount = p.amount;
+                    if (MODE == 2) {  // localEdgeStrength (effects.go:93-112), expression order preserved
+                        const uint32_t n[9] = {pPrev[i], pPrev[i + 1], pPrev[i + 2], pCur[i], c, pCur[i + 2],
+                                               pNext[i], pNext[i + 1], pNext[i + 2]};
+                        auto lum = [](uint32_t v) {
+                            return __dadd_rn(__dadd_rn(__dmul_rn(0.299, small_int_to_double((int)(v & 0xFF))),
+                                                       __dmul_rn(0.587, small_int_to_double((int)((v >> 8) & 0xFF)))),
+                                             __dmul_rn(0.114, small_int_to_double((int)((v >> 16) & 0xFF))));
+                        };
+                        const double l00 = lum(n[0]), l10 = lum(n[1]), l20 = lum(n[2]), l01 = lum(n[3]), l21 = lum(n[5]);
+                        const double l02 = lum(n[6]), l12 = lum(n[7]), l22 = lum(n[8]);
+                        double gx = __dadd_rn(-l00, l20);
+                        gx = __dadd_rn(gx, -__dmul_rn(2.0, l01));
+                        gx = __dadd_rn(gx, __dmul_rn(2.0, l21));
+                        gx = __dadd_rn(gx, -l02);
+                        gx = __dadd_rn(gx, l22);
+                        double gy = __dadd_rn(-l00, -__dmul_rn(2.0, l10));
+                        gy = __dadd_rn(gy, -l20);
+                        gy = __dadd_rn(gy, l02);
+                        gy = __dadd_rn(gy, __dmul_rn(2.0, l12));
+                        gy = __dadd_rn(gy, l22);
+                        const double g2 = __dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy));
+                        double edge = 1.0;
+                        // sqrt and /400 are monotone and correctly rounded: g2 >= 160001 gives mag/400 > 1 → clamped to 1
+                        if (g2 < 160001.0) {
+                            edge = __ddiv_rn(__dsqrt_rn(g2), 400.0);
+                            if (edge > 1.0) edge = 1.0;
+                        }
+                        amount = __dmul_rn(p.amount, edge);  // effects.go:74
+                    }
+                    uint32_t o[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        const int orig = (int)((c >> (8 * ch)) & 0xFF);
+                        const int diff = orig - bl[ch];
+                        if (INTK >= 0) {
+                            int V = (orig << INTK) + p.A * diff + p.half;   // exact (see header comment)
+                            V = V < 0 ? 0 : (V >> INTK);
+                            o[ch] = (uint32_t)min(V, 255);
+                        } else {
+                            double val = __dadd_rn(small_int_to_double(orig), __dmul_rn(amount, small_int_to_double(diff)));
+                            o[ch] = clampf_magic(val);  // effects.go:37-38 / 82-83
+                        }
+                    }
+                    res = o[0] | (o[1] << 8) | (o[2] << 16) | (c & 0xFF000000u);
+                }
+            }
+            out[i] = res;
+        }
+        uint8_t *drow = d + (long long)y * p.dstRowStride + (long long)x0 * 4;
+        if (full && ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0)) {
+            *reinterpret_cast<uint4 *>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (x0 + i < p.w) *reinterpret_cast<uint32_t *>(drow + i * 4) = out[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { pPrev[i] = pCur[i]; pCur[i] = pNext[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { hPrevRB[i] = hCurRB[i]; hPrevGA[i] = hCurGA[i]; hCurRB[i] = hNextRB[i]; hCurGA[i] = hNextGA[i]; }
+    }
+}
+
 }  // namespace
 
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
@@ -444,8 +608,33 @@ static int launch_fx(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long
     p.srcImgStride = imgStride; p.dstImgStride = dstImgStride;
     p.srcRowStride = rowStride; p.dstRowStride = dstRowStride;
     p.w = w; p.h = h; p.amount = amount; p.mode = mode;
-    dim3 grid((w + 255) / 256, h, n);
-    sharpen_kernel<<<grid, 256, 0, s>>>(p);
+    if (getenv("FB_FX_GENERIC") == nullptr) {
+        FxTileParams t;
+        t.src = src; t.dst = dst;
+        t.srcImgStride = imgStride; t.dstImgStride = dstImgStride;
+        t.srcRowStride = rowStride; t.dstRowStride = dstRowStride;
+        t.w = w; t.h = h; t.amount = amount; t.A = 0; t.half = 0;
+        t.vecOK = (((uintptr_t)src | (uintptr_t)imgStride | (uintptr_t)rowStride) & 15) == 0;
+        dim3 tgrid((w + 511) / 512, (h + kFxRows - 1) / kFxRows, n);
+        int k = -1;
+        if (mode == 1) {  // Sharpen: is amount * 2^k an integer for a small k?  (orig<<k) + A*diff must fit in int32
+            for (int kk = 0; kk <= 12 && k < 0; kk++) {
+                double scaled = amount * (double)(1 << kk);
+                if (scaled == (double)(long long)scaled && scaled < 32768.0) { k = kk; t.A = (int)scaled; t.half = kk ? 1 << (kk - 1) : 0; }
+            }
+        }
+        if (mode == 0) fx_tile_kernel<0, -1><<<tgrid, 128, 0, s>>>(t);
+        else if (mode == 2) fx_tile_kernel<2, -1><<<tgrid, 128, 0, s>>>(t);
+        else if (k == 0) fx_tile_kernel<1, 0><<<tgrid, 128, 0, s>>>(t);
+        else if (k == 1) fx_tile_kernel<1, 1><<<tgrid, 128, 0, s>>>(t);
+        else if (k == 2) fx_tile_kernel<1, 2><<<tgrid, 128, 0, s>>>(t);
+        else if (k == 3) fx_tile_kernel<1, 3><<<tgrid, 128, 0, s>>>(t);
+        else if (k == 4) fx_tile_kernel<1, 4><<<tgrid, 128, 0, s>>>(t);
+        else fx_tile_kernel<1, -1><<<tgrid, 128, 0, s>>>(t);
+    } else {
+        dim3 grid((w + 255) / 256, h, n);
+        sharpen_kernel<<<grid, 256, 0, s>>>(p);
+    }
     FB_LAUNCHED(1);
     FB_CUDA(cudaGetLastError());
     return FB_OK;
