@@ -93,8 +93,52 @@ struct LanczosTable {
     int *start = nullptr;
     int *index = nullptr;
     double *weight = nullptr;
+    float *weight32 = nullptr;
+    int *first = nullptr;      // grouped layout for the horizontal fast path (nullptr: taps not contiguous)
+    float *wpadT = nullptr;
+    int groups = 0;
     int entries = 0, maxTaps = 0;
+    double wabs = 0.0;  // max over destinations of sum |w| (error bound of the FP32 fast path)
 };
+
+// Grouped layout (see resize.cu ResizeParams): returns false when some destination's taps are not contiguous.
+static bool build_groups(const int *start, const int *index, const double *weight, int n, std::vector<int> &first,
+                         std::vector<float> &wpadT, int *groups) {
+    first.assign(n, 0);
+    int G = 1;
+    for (int d = 0; d < n; d++) {
+        int cnt = start[d + 1] - start[d];
+        if (cnt <= 0) { first[d] = 0; continue; }
+        int f = index[start[d]];
+        for (int k = 0; k < cnt; k++)
+            if (index[start[d] + k] != f + k) return false;
+        first[d] = f;
+        int ng = ((f + cnt - 1) >> 2) - (f >> 2) + 1;
+        if (ng > G) G = ng;
+    }
+    wpadT.assign((size_t)G * n * 4, 0.f);
+    for (int d = 0; d < n; d++) {
+        int cnt = start[d + 1] - start[d];
+        int g0 = first[d] & ~3;
+        for (int k = 0; k < cnt; k++) {
+            int rel = first[d] + k - g0;
+            wpadT[((size_t)(rel >> 2) * n + d) * 4 + (rel & 3)] = (float)weight[start[d] + k];
+        }
+    }
+    *groups = G;
+    return true;
+}
+
+static void table_stats(const int *start, const double *weight, int n, int *maxTaps, double *wabs) {
+    *maxTaps = 0;
+    *wabs = 0.0;
+    for (int d = 0; d < n; d++) {
+        double sabs = 0.0;
+        for (int t = start[d]; t < start[d + 1]; t++) sabs += fabs(weight[t]);
+        if (sabs > *wabs) *wabs = sabs;
+        if (start[d + 1] - start[d] > *maxTaps) *maxTaps = start[d + 1] - start[d];
+    }
+}
 struct ThreadState {
     std::vector<DevCtx> ctxs;
     std::vector<bool> pinBusy;
@@ -278,13 +322,25 @@ static int lanczos_table_cached(DevCtx *c, int dstSize, int srcSize, LanczosTabl
     int n = lanczos_build(dstSize, srcSize, start.data(), index.data(), weight.data());
     LanczosTable t;
     t.entries = n;
-    for (int d = 0; d < dstSize; d++) t.maxTaps = std::max(t.maxTaps, start[d + 1] - start[d]);
+    table_stats(start.data(), weight.data(), dstSize, &t.maxTaps, &t.wabs);
+    std::vector<float> w32(n + 1);
+    for (int i = 0; i < n; i++) w32[i] = (float)weight[i];
     FB_CUDA(cudaMalloc((void **)&t.start, sizeof(int) * (dstSize + 1)));
     FB_CUDA(cudaMalloc((void **)&t.index, sizeof(int) * (n + 1)));
     FB_CUDA(cudaMalloc((void **)&t.weight, sizeof(double) * (n + 1)));
+    FB_CUDA(cudaMalloc((void **)&t.weight32, sizeof(float) * (n + 1)));
     FB_CUDA(cudaMemcpy(t.start, start.data(), sizeof(int) * (dstSize + 1), cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(t.index, index.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     FB_CUDA(cudaMemcpy(t.weight, weight.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpy(t.weight32, w32.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    std::vector<int> first;
+    std::vector<float> wpadT;
+    if (build_groups(start.data(), index.data(), weight.data(), dstSize, first, wpadT, &t.groups)) {
+        FB_CUDA(cudaMalloc((void **)&t.first, sizeof(int) * dstSize));
+        FB_CUDA(cudaMalloc((void **)&t.wpadT, sizeof(float) * wpadT.size()));
+        FB_CUDA(cudaMemcpy(t.first, first.data(), sizeof(int) * dstSize, cudaMemcpyHostToDevice));
+        FB_CUDA(cudaMemcpy(t.wpadT, wpadT.data(), sizeof(float) * wpadT.size(), cudaMemcpyHostToDevice));
+    }
     t_state.lanczos[key] = t;
     *out = t;
     return FB_OK;
@@ -542,6 +598,9 @@ void fb_shutdown(void) {
         cudaFree(kv.second.start);
         cudaFree(kv.second.index);
         cudaFree(kv.second.weight);
+        cudaFree(kv.second.weight32);
+        cudaFree(kv.second.first);
+        cudaFree(kv.second.wpadT);
     }
     t_state.lanczos.clear();
     t_state.ctxs.clear();
@@ -720,23 +779,26 @@ static int upload_weights(DevCtx *c, cudaStream_t s, const fb_weights *w, Lanczo
     int *pstart = (int *)c->pin.take(sizeof(int) * (n + 1));
     int *pindex = (int *)c->pin.take(sizeof(int) * (entries + 1));
     double *pweight = (double *)c->pin.take(sizeof(double) * (entries + 1));
+    float *pw32 = (float *)c->pin.take(sizeof(float) * (entries + 1));
     t->start = (int *)c->ws.take(sizeof(int) * (n + 1));
     t->index = (int *)c->ws.take(sizeof(int) * (entries + 1));
     t->weight = (double *)c->ws.take(sizeof(double) * (entries + 1));
-    if (!pstart || !pindex || !pweight || !t->start || !t->index || !t->weight) {
+    t->weight32 = (float *)c->ws.take(sizeof(float) * (entries + 1));
+    if (!pstart || !pindex || !pweight || !pw32 || !t->start || !t->index || !t->weight || !t->weight32) {
         set_error("internal: workspace under-reserved (weights)");
         return FB_E_INVALID;
     }
     memcpy(pstart, w->start, sizeof(int) * (n + 1));
     memcpy(pindex, w->index, sizeof(int) * entries);
     memcpy(pweight, w->weight, sizeof(double) * entries);
+    for (int i = 0; i < entries; i++) pw32[i] = (float)w->weight[i];
+    FB_CUDA(cudaMemcpyAsync(t->weight32, pw32, sizeof(float) * entries, cudaMemcpyHostToDevice, s));
     FB_CUDA(cudaMemcpyAsync(t->start, pstart, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
     FB_CUDA(cudaMemcpyAsync(t->index, pindex, sizeof(int) * entries, cudaMemcpyHostToDevice, s));
     FB_CUDA(cudaMemcpyAsync(t->weight, pweight, sizeof(double) * entries, cudaMemcpyHostToDevice, s));
     mark_pin_busy(c, s);
     t->entries = entries;
-    t->maxTaps = 0;
-    for (int d = 0; d < n; d++) t->maxTaps = std::max(t->maxTaps, w->start[d + 1] - w->start[d]);
+    table_stats(w->start, w->weight, n, &t->maxTaps, &t->wabs);
     return FB_OK;
 }
 
@@ -762,9 +824,9 @@ static int resize_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, long
     uint8_t *tmp = (uint8_t *)c->ws.take((size_t)timg * n);
     if (!tmp) { set_error("internal: workspace under-reserved (resize tmp)"); return FB_E_INVALID; }
     FB_TRY(launch_resize_h(s, dsrc, srcImgStride, srcRowStride, srcW, srcH, tmp, timg, tpitch, dstW, n, tx.start,
-                           tx.index, tx.weight, tx.maxTaps));
+                           tx.index, tx.weight, tx.weight32, tx.maxTaps, tx.wabs, tx.first, tx.wpadT, tx.groups));
     return launch_resize_v(s, tmp, timg, tpitch, dstW, srcH, ddst, dstImgStride, dstRowStride, dstH, n, ty.start,
-                           ty.index, ty.weight, ty.maxTaps);
+                           ty.index, ty.weight, ty.weight32, ty.maxTaps, ty.wabs);
 }
 
 int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH, uint8_t *dst, int dstStride, int dstW,
@@ -781,8 +843,8 @@ int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH, uin
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     size_t tabBytes = 0;
-    if (wx) tabBytes += 16 * (size_t)(wx->start[dstW] + dstW + 8);
-    if (wy) tabBytes += 16 * (size_t)(wy->start[dstH] + dstH + 8);
+    if (wx) tabBytes += 24 * (size_t)(wx->start[dstW] + dstW + 8);
+    if (wy) tabBytes += 24 * (size_t)(wy->start[dstH] + dstH + 8);
     size_t need = (size_t)dev_pitch(srcW) * srcH + (size_t)dev_pitch(dstW) * srcH + (size_t)dev_pitch(dstW) * dstH +
                   tabBytes + 8192;
     FB_TRY(reserve(c, need, tabBytes + 4096));

@@ -29,6 +29,7 @@ struct BoxParams {
     int srcW, srcH, dstW, dstH;
     double xRatio, yRatio;
     int dxChunk;   // output columns per CTA
+    int dyPerCta;  // output rows per CTA (small boxes: amortise the CTA over more source rows)
     int vecOK;
 };
 
@@ -52,9 +53,11 @@ __device__ __forceinline__ uint32_t box_finish(uint32_t sr, uint32_t sg, uint32_
 
 __global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams p) {
     __shared__ uint2 colsum[kSpanMax + 8];  // per source column: (R | B<<16, G | A<<16) 16-bit sums
-    const int dy = blockIdx.y, img = blockIdx.z;
+    const int img = blockIdx.z;
     const int dx0 = blockIdx.x * p.dxChunk;
     const int dx1 = min(dx0 + p.dxChunk, p.dstW);
+    const int dyEnd = min((int)(blockIdx.y + 1) * p.dyPerCta, p.dstH);
+  for (int dy = blockIdx.y * p.dyPerCta; dy < dyEnd; dy++) {
     int sy0, sy1, sxa, sxb, tmp;
     box_edge(dy, p.yRatio, p.srcH, sy0, sy1);
     box_edge(dx0, p.xRatio, p.srcW, sxa, tmp);
@@ -100,6 +103,8 @@ __global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams p) {
         }
         *reinterpret_cast<uint32_t *>(drow + (long long)dx * 4) = box_finish(sr, sg, sb, sa, count_y * (sx1 - sx0));
     }
+    __syncthreads();  // colsum is reused by the next output row
+  }
 }
 
 // Generic fallback: one thread per output pixel walks its own box (upsampling, boxes taller than
@@ -172,10 +177,13 @@ int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int s
         if (chunk < 1) chunk = 1;
         if (chunk > dstW) chunk = dstW;
         p.dxChunk = chunk;
-        dim3 grid((dstW + chunk - 1) / chunk, dstH, n);
+        // ~32 source rows per CTA: one output row for 15x15 boxes, 16 output rows for the 2x cascade
+        p.dyPerCta = maxBoxH >= 32 ? 1 : (32 / maxBoxH < 1 ? 1 : 32 / maxBoxH);
+        dim3 grid((dstW + chunk - 1) / chunk, (dstH + p.dyPerCta - 1) / p.dyPerCta, n);
         box_rows_kernel<<<grid, kThreads, 0, s>>>(p);
     } else {
         p.dxChunk = 0;
+        p.dyPerCta = 1;
         dim3 grid((dstW + kThreads - 1) / kThreads, dstH, n);
         box_naive_kernel<<<grid, kThreads, 0, s>>>(p);
     }

@@ -101,10 +101,13 @@ int launch_sharpen(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long i
 // resize.cu
 int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,
-                    const int *start_dev, const int *index_dev, const double *weight_dev, int maxTaps);
+                    const int *start_dev, const int *index_dev, const double *weight_dev,
+                    const float *weight32_dev, int maxTaps, double wabs, const int *first_dev,
+                    const float *wpadT_dev, int groups);
 int launch_resize_v(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstH, int n,
-                    const int *start_dev, const int *index_dev, const double *weight_dev, int maxTaps);
+                    const int *start_dev, const int *index_dev, const double *weight_dev,
+                    const float *weight32_dev, int maxTaps, double wabs);
 
 #ifdef __CUDACC__
 // ---- device helpers ---------------------------------------------------------------------------

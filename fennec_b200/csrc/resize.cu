@@ -12,6 +12,8 @@
 // warp's taps cover one contiguous span of the source row that stays in L1.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace fb {
 
 namespace {
@@ -25,6 +27,16 @@ struct ResizeParams {
     const int *start;        // CSR over the resampled axis
     const int *index;
     const double *weight;
+    const float *weight32;   // the same weights rounded to FP32 (fast path)
+    float Er, Ea;            // FP32 error bounds of the colour sums and of the alpha sum (see launch_pass)
+    // horizontal fast path: taps of destination d are the contiguous pixels first[d].. ; they are read as
+    // 16-byte groups starting at first[d] & ~3, with FP32 weights zero-padded to whole groups and stored
+    // transposed, wpadT[(q * n + d) * 4 + j], so that a warp's weight loads are contiguous.
+    const int *first;
+    const float *wpadT;
+    int groups;              // max groups per destination
+    int srcW;
+    int vecOK;
 };
 
 __device__ __forceinline__ void finish_px(double r, double g, double b, double a, uint8_t *d) {
@@ -60,19 +72,153 @@ __global__ void __launch_bounds__(256) resize_pass_kernel(const ResizeParams p) 
     finish_px(r, g, b, a, p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x * 4);
 }
 
+__device__ __forceinline__ float byte_f(uint32_t px, int k) {  // byte k of px as float, without I2F
+    return __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u | (uint32_t)k)) - 8388608.0f;
+}
+
+// Round v in [0,255] to nearest; `amb` when within eps of a tie (the exact path then decides).
+__device__ __forceinline__ uint32_t round_flag255(float v, float eps, bool &amb) {
+    v = fminf(fmaxf(v, 0.f), 255.f);  // ties at -0.5 and 255.5 cannot change the clamped result
+    float t = v + 12582912.0f;
+    float rounded = t - 12582912.0f;
+    amb = amb || (fabsf(v - rounded) >= 0.5f - eps);
+    return __float_as_uint(t) & 0x1FFu;
+}
+
+// Fast pass: the premultiplied sums are accumulated with FP32 FMAs.  |r32 - r64| <= Er and
+// |a32 - a64| <= Ea (bounds from the tap count and max sum|w| of the table), so the quotient is within
+// eps = (Er + |v|*Ea)/a + |v|*2^-21 of the reference value; a pixel whose channel (or alpha, or the
+// a > 0.5 gate) lies within that distance of a decision boundary is recomputed in the exact FP64 order.
+// Ambiguous pixels are compacted per block through shared memory so the exact path runs with full
+// warps instead of one divergent lane per warp.
+__device__ __forceinline__ void tap_fp32(uint32_t v, float w, float &r, float &g, float &b, float &a) {
+    const float aw = byte_f(v, 3) * w;
+    r = fmaf(byte_f(v, 0), aw, r);
+    g = fmaf(byte_f(v, 1), aw, g);
+    b = fmaf(byte_f(v, 2), aw, b);
+    a += aw;
+}
+
+// Returns the packed fast result, or sets amb.
+__device__ __forceinline__ uint32_t finish_fp32(float r, float g, float b, float a, float Er, float Ea, bool &amb) {
+    amb = fabsf(a - 0.5f) <= Ea;  // the a > 0.5 gate itself (resize.go:107)
+    uint32_t out = 0u;
+    if (!amb && a > 0.5f) {
+        const float inv = __frcp_rn(a);
+        const float vr = r * inv, vg = g * inv, vb = b * inv;
+        const float vmax = fmaxf(fmaxf(fabsf(vr), fabsf(vg)), fabsf(vb));
+        const float eps = (Er + vmax * Ea) * inv + vmax * 4.76837158203125e-07f;
+        amb = !(eps < 0.25f);
+        const uint32_t cr = round_flag255(vr, eps, amb), cg = round_flag255(vg, eps, amb), cb = round_flag255(vb, eps, amb);
+        const uint32_t ca = round_flag255(a, Ea, amb);
+        out = cr | (cg << 8) | (cb << 16) | (ca << 24);
+    }
+    return out;
+}
+
+// Exact FP64 sequence of the reference for one destination pixel (resize.go:93-113).
+template <bool VERTICAL>
+__device__ __forceinline__ void exact_px(const ResizeParams &p, const uint8_t *s, int x, int y, uint8_t *dpx) {
+    const int d = VERTICAL ? y : x;
+    const int t0 = __ldg(p.start + d), t1 = __ldg(p.start + d + 1);
+    double r2 = 0.0, g2 = 0.0, b2 = 0.0, a2 = 0.0;
+    for (int t = t0; t < t1; t++) {
+        const int si = __ldg(p.index + t);
+        const double w = __ldg(p.weight + t);
+        const uint32_t v = VERTICAL ? __ldg(reinterpret_cast<const uint32_t *>(s + (long long)si * p.srcRowStride + (long long)x * 4))
+                                    : __ldg(reinterpret_cast<const uint32_t *>(s + (long long)y * p.srcRowStride + (long long)si * 4));
+        const double aw = __dmul_rn((double)(v >> 24), w);
+        r2 = __dadd_rn(r2, __dmul_rn((double)(v & 0xFF), aw));
+        g2 = __dadd_rn(g2, __dmul_rn((double)((v >> 8) & 0xFF), aw));
+        b2 = __dadd_rn(b2, __dmul_rn((double)((v >> 16) & 0xFF), aw));
+        a2 = __dadd_rn(a2, aw);
+    }
+    finish_px(r2, g2, b2, a2, dpx);
+}
+
+template <bool VERTICAL, bool GROUPED>
+__global__ void __launch_bounds__(256) resize_pass_fast_kernel(const ResizeParams p) {
+    __shared__ int nAmb;
+    __shared__ unsigned short ambList[256];
+    if (threadIdx.x == 0) nAmb = 0;
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, img = blockIdx.z;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride;
+    if (x < p.outW) {
+        float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
+        if (GROUPED) {  // horizontal: 128-bit pixel groups + transposed padded weights
+            const int first = __ldg(p.first + x);
+            const int g0 = first & ~3;
+            const int ng = ((first + (__ldg(p.start + x + 1) - __ldg(p.start + x)) - 1) >> 2) - (g0 >> 2) + 1;
+            const uint8_t *row = s + (long long)y * p.srcRowStride;
+            for (int q = 0; q < ng; q++) {
+                const int px0 = g0 + 4 * q;
+                const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.wpadT) + (size_t)q * p.outW + x);
+                uint32_t v[4];
+                if (p.vecOK && px0 + 4 <= p.srcW) {
+                    uint4 t = __ldg(reinterpret_cast<const uint4 *>(row + (long long)px0 * 4));
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)  // pixels past the row end carry zero weights
+                        v[j] = (px0 + j < p.srcW) ? __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(px0 + j) * 4)) : 0u;
+                }
+                tap_fp32(v[0], w4.x, r, g, b, a);
+                tap_fp32(v[1], w4.y, r, g, b, a);
+                tap_fp32(v[2], w4.z, r, g, b, a);
+                tap_fp32(v[3], w4.w, r, g, b, a);
+            }
+        } else {
+            const int d = VERTICAL ? y : x;
+            const int t0 = __ldg(p.start + d), t1 = __ldg(p.start + d + 1);
+            for (int t = t0; t < t1; t++) {
+                const int si = __ldg(p.index + t);
+                const float w = __ldg(p.weight32 + t);
+                const uint32_t v = VERTICAL ? __ldg(reinterpret_cast<const uint32_t *>(s + (long long)si * p.srcRowStride + (long long)x * 4))
+                                            : __ldg(reinterpret_cast<const uint32_t *>(s + (long long)y * p.srcRowStride + (long long)si * 4));
+                tap_fp32(v, w, r, g, b, a);
+            }
+        }
+        bool amb;
+        const uint32_t out = finish_fp32(r, g, b, a, p.Er, p.Ea, amb);
+        if (amb) ambList[atomicAdd(&nAmb, 1)] = (unsigned short)threadIdx.x;
+        else *reinterpret_cast<uint32_t *>(drow + (long long)x * 4) = out;
+    }
+    __syncthreads();
+    const int n = nAmb;
+    if ((int)threadIdx.x < n) {
+        const int xa = blockIdx.x * blockDim.x + ambList[threadIdx.x];
+        exact_px<VERTICAL>(p, s, xa, y, drow + (long long)xa * 4);
+    }
+}
+
 template <bool VERTICAL>
 int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, uint8_t *dst,
                 long long dstImgStride, int dstRowStride, int outW, int outH, int n, const int *start,
-                const int *index, const double *weight) {
+                const int *index, const double *weight, const float *weight32, int maxTaps, double wabs,
+                const int *first = nullptr, const float *wpadT = nullptr, int groups = 0, int srcSize = 0) {
     if (n <= 0 || outW <= 0 || outH <= 0) return FB_OK;
     ResizeParams p;
     p.src = src; p.dst = dst;
     p.srcImgStride = srcImgStride; p.dstImgStride = dstImgStride;
     p.srcRowStride = srcRowStride; p.dstRowStride = dstRowStride;
     p.outW = outW; p.outH = outH;
-    p.start = start; p.index = index; p.weight = weight;
+    p.start = start; p.index = index; p.weight = weight; p.weight32 = weight32;
+    // Each of the <= maxTaps FMAs rounds a partial sum bounded by 255*255*wabs (colour) or 255*wabs (alpha);
+    // aw = alpha*w and the FP32 weights add 2 more relative roundings. 25 % margin.
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    p.Er = (float)((maxTaps + 3) * u * 65025.0 * wabs * 1.25);
+    p.Ea = (float)((maxTaps + 3) * u * 255.0 * wabs * 1.25);
     dim3 grid((outW + 255) / 256, outH, n);
-    resize_pass_kernel<VERTICAL><<<grid, 256, 0, s>>>(p);
+    p.first = first; p.wpadT = wpadT; p.groups = groups; p.srcW = srcSize;
+    p.vecOK = (((uintptr_t)src | (uintptr_t)srcImgStride | (uintptr_t)srcRowStride) & 15) == 0;
+    if (weight32 != nullptr && p.Ea < 0.2f && getenv("FB_RESIZE_GENERIC") == nullptr) {
+        if (!VERTICAL && wpadT != nullptr) resize_pass_fast_kernel<VERTICAL, true><<<grid, 256, 0, s>>>(p);
+        else resize_pass_fast_kernel<VERTICAL, false><<<grid, 256, 0, s>>>(p);
+    } else
+        resize_pass_kernel<VERTICAL><<<grid, 256, 0, s>>>(p);
     FB_LAUNCHED(1);
     FB_CUDA(cudaGetLastError());
     return FB_OK;
@@ -82,18 +228,21 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
 
 int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,
-                    const int *start_dev, const int *index_dev, const double *weight_dev, int maxTaps) {
-    (void)srcW; (void)maxTaps;
+                    const int *start_dev, const int *index_dev, const double *weight_dev,
+                    const float *weight32_dev, int maxTaps, double wabs, const int *first_dev,
+                    const float *wpadT_dev, int groups) {
     return launch_pass<false>(s, src, srcImgStride, srcRowStride, dst, dstImgStride, dstRowStride, dstW, srcH, n,
-                              start_dev, index_dev, weight_dev);
+                              start_dev, index_dev, weight_dev, weight32_dev, maxTaps, wabs, first_dev, wpadT_dev,
+                              groups, srcW);
 }
 
 int launch_resize_v(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstH, int n,
-                    const int *start_dev, const int *index_dev, const double *weight_dev, int maxTaps) {
-    (void)srcH; (void)maxTaps;
+                    const int *start_dev, const int *index_dev, const double *weight_dev,
+                    const float *weight32_dev, int maxTaps, double wabs) {
+    (void)srcH;
     return launch_pass<true>(s, src, srcImgStride, srcRowStride, dst, dstImgStride, dstRowStride, srcW, dstH, n,
-                             start_dev, index_dev, weight_dev);
+                             start_dev, index_dev, weight_dev, weight32_dev, maxTaps, wabs);
 }
 
 }  // namespace fb
