@@ -256,6 +256,8 @@ __device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
                 mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
             }
             // mab = (mua', mub'); mqp = (E[a'^2+b'^2] + C2, E[a'b'] + C2/2)
+            // (packing this formula two pixels per FFMA2/FMUL2 was measured: the pair transposes cost
+            //  more MOVs than the packed ops save — 1.11 ms vs 1.05 ms per 32 pairs)
             float m = mab.x * mab.y;
             float nn = fmaf(mab.x, mab.x, mab.y * mab.y);
             float th = fmaf(c, mab.x + mab.y, kTh);
@@ -337,6 +339,220 @@ __global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_stri
     if (fast && q.nvalid == 0) q.nvalid = CPL;
 
     double dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) p.partials[seg] = dsum * 4.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised variant (aligned inputs only).  The monolithic kernel above is register-limited to
+// 8 warps/SM (its 8-row ring alone is 128 registers) and leaves the FMA pipe ~35 % idle.  Here a CTA is
+// two warpgroups: warps 0-3 ("V") keep the ring and do planes + the vertical pass, warps 4-7 ("H") do the
+// horizontal pass + SSIM formula + reduction.  V-warp i and H-warp i+4 share a strip and live on the
+// same SM sub-partition; rows travel through a 4-deep shared-memory ring guarded by full/empty
+// mbarriers.  setmaxnreg moves registers from the H warpgroup (72) to the V warpgroup (184), so two
+// such CTAs (16 warps) fit an SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWsPairs = 4;
+constexpr int kVStages = 4;
+constexpr int kVLanesWs = 36;
+constexpr int kVRowF4 = 4 * kVLanesWs;  // float4 per V row
+
+struct __align__(16) WsSmem {
+    float4 vrows[kWsPairs][kVStages][kVRowF4];
+    uint8_t pxring[kWsPairs][kStages][2][512];
+    unsigned long long full[kWsPairs][kVStages];
+    unsigned long long empty[kWsPairs][kVStages];
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) ssim_ws_kernel(const SsimParams p) {
+    constexpr int CPL = 4, INC = 128, OUTC = 120;
+    extern __shared__ __align__(16) uint8_t ws_raw[];
+    WsSmem &sm = *reinterpret_cast<WsSmem *>(ws_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int pair = warp & 3;
+    const bool isV = warp < 4;
+
+    if (threadIdx.x < kWsPairs * kVStages) {
+        mbar_init(smem_u32(&sm.full[0][0]) + 8u * threadIdx.x, 32);
+        mbar_init(smem_u32(&sm.empty[0][0]) + 8u * threadIdx.x, 32);
+    }
+    // pad slots of the V rows (read by lanes 30/31 for masked outputs) must stay finite
+    for (int i = threadIdx.x; i < kWsPairs * kVStages * 4 * 4; i += 256) {
+        int row = i >> 4, item = (i >> 2) & 3, padl = i & 3;
+        (&sm.vrows[0][0][0])[row * kVRowF4 + item * kVLanesWs + 32 + padl] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const long long segsPerImg = (long long)p.nsx * p.nsy;
+    const long long seg = (long long)blockIdx.x * kWsPairs + pair;
+    const bool active = seg < segsPerImg * p.n;  // inactive pairs still execute their warpgroup's setmaxnreg
+    const int img = active ? (int)(seg / segsPerImg) : 0;
+    const int rseg = (int)(seg - (long long)img * segsPerImg);
+    const int sy = rseg / p.nsx, sx = rseg - sy * p.nsx;
+    const int X0 = sx * OUTC, Y0 = sy * p.rs;
+    const int nOut = min(p.rs, (p.h - 8) - Y0);
+    const int nIn = nOut + 7;
+    const int xl = X0 + CPL * lane;
+    const uint8_t *ia = p.a + (long long)img * p.imgStrideA;
+    const uint8_t *ib = p.b + (long long)img * p.imgStrideB;
+    float K = 0.f, c = 0.f;
+    if (active) {   // centring constant, identical in both warps of the pair
+        int cx = min(X0 + OUTC / 2, p.w - 1), cy = min(Y0 + nIn / 2, p.h - 1);
+        float f = luma_magic(ld_nc_u32(ia + (long long)cy * p.rowStrideA + (long long)cx * 4));
+        K = -(f * kLumaScale);
+        c = -fmaf(8388608.0f, kLumaScale, K);
+    }
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(p.g[j], p.g[j]);
+    const uint32_t fullBase = smem_u32(&sm.full[pair][0]);
+    const uint32_t emptyBase = smem_u32(&sm.empty[pair][0]);
+    float4 *vrows = &sm.vrows[pair][0][0];
+
+    if (isV) {
+        // ---------------- producer: pixels → planes → vertical 8-tap → V row ring ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        if (!active) return;
+        const int xld = (xl + CPL <= p.w) ? xl : X0;  // lanes right of the image re-read the strip start (masked)
+        const uint8_t *pa = ia + (long long)Y0 * p.rowStrideA + (long long)xld * 4;
+        const uint8_t *pb = ib + (long long)Y0 * p.rowStrideB + (long long)xld * 4;
+        const float2 s2 = make_float2(kLumaScale, kLumaScale);
+        const float2 K2 = make_float2(K, K);
+        const uint32_t myRing = smem_u32(&sm.pxring[pair][0][0][0]) + lane * 16;
+        const uint8_t *myRingP = &sm.pxring[pair][0][0][0] + lane * 16;
+#pragma unroll
+        for (int row = 0; row < kStages; row++) {
+            cp_async<16>(myRing + (2 * row) * 512, pa);
+            cp_async<16>(myRing + (2 * row + 1) * 512, pb);
+            cp_async_commit();
+            pa += p.rowStrideA;
+            pb += p.rowStrideB;
+        }
+        float2 rab[8][CPL], rqp[8][CPL];
+#define WS_PLANES(S, R)                                                                         \
+    {                                                                                           \
+        cp_async_wait<kStages - 1>();                                                           \
+        const uint8_t *rb_ = myRingP + (2 * ((S) & (kStages - 1))) * 512;                       \
+        const uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                                \
+        const uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + 512);                          \
+        const uint32_t xa_[4] = {va_.x, va_.y, va_.z, va_.w}, xb_[4] = {vb_.x, vb_.y, vb_.z, vb_.w}; \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
+            float2 t = __ffma2_rn(f, s2, K2);                                                   \
+            float2 sq = __fmul2_rn(t, t);                                                       \
+            rab[S][i] = t;                                                                      \
+            rqp[S][i] = make_float2(sq.x + sq.y, t.x * t.y);                                    \
+        }                                                                                       \
+        if ((R) + kStages < nIn) {                                                              \
+            cp_async<16>(myRing + (2 * ((S) & (kStages - 1))) * 512, pa);                       \
+            cp_async<16>(myRing + (2 * ((S) & (kStages - 1)) + 1) * 512, pb);                   \
+            pa += p.rowStrideA;                                                                 \
+            pb += p.rowStrideB;                                                                 \
+        }                                                                                       \
+        cp_async_commit();                                                                      \
+    }
+#pragma unroll
+        for (int r = 0; r < 7; r++) WS_PLANES(r, r)
+
+#pragma unroll 1
+        for (int r = 7; r < nIn; r++) {
+            const int o = r - 7;
+            const int st = o & (kVStages - 1);
+            mbar_wait(emptyBase + 8u * st, ((o / kVStages) & 1) ^ 1);  // slot free (first lap passes at once)
+            float4 *dst = vrows + st * kVRowF4 + lane;
+#define WS_STEP(S)                                                                              \
+    case S: {                                                                                   \
+        WS_PLANES(S, r)                                                                         \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 vab = __fmul2_rn(rab[(S + 1) & 7][i], g2[0]);                                \
+            float2 vqp = __fmul2_rn(rqp[(S + 1) & 7][i], g2[0]);                                \
+            _Pragma("unroll") for (int j = 1; j < 8; j++) {                                     \
+                vab = __ffma2_rn(rab[(S + 1 + j) & 7][i], g2[j], vab);                          \
+                vqp = __ffma2_rn(rqp[(S + 1 + j) & 7][i], g2[j], vqp);                          \
+            }                                                                                   \
+            dst[i * kVLanesWs] = make_float4(vab.x, vab.y, vqp.x, vqp.y);                       \
+        }                                                                                       \
+    } break;
+            switch (r & 7) {
+                WS_STEP(0) WS_STEP(1) WS_STEP(2) WS_STEP(3) WS_STEP(4) WS_STEP(5) WS_STEP(6) WS_STEP(7)
+            }
+#undef WS_STEP
+            mbar_arrive(fullBase + 8u * st);  // release: the row's stores are visible to the consumer
+        }
+#undef WS_PLANES
+        return;
+    }
+
+    // ---------------- consumer: horizontal 8-tap + SSIM + reduction ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (!active) return;
+    bool valid[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) valid[i] = (CPL * lane + i < OUTC) && (xl + i < p.w - 8);
+    const float kTh = fmaf(c, c, 0.5f * kC1f);
+    const float2 qpInit = make_float2(kC2f, 0.5f * kC2f);
+    float fs[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) fs[i] = 0.f;
+#pragma unroll 1
+    for (int o = 0; o < nOut; o++) {
+        const int st = o & (kVStages - 1);
+        mbar_wait(fullBase + 8u * st, (o / kVStages) & 1);
+        const float4 *src = vrows + st * kVRowF4 + lane;
+        float2 mab[CPL], mqp[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; i++) { mab[i] = make_float2(0.f, 0.f); mqp[i] = qpInit; }
+        // scatter form: item k (column 4*lane + k) feeds outputs i = k-7..k with tap k - i
+#pragma unroll
+        for (int k = 0; k < CPL + 7; k++) {
+            const float4 v = src[(k % CPL) * kVLanesWs + k / CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; i++) {
+                const int t = k - i;
+                if (t >= 0 && t < 8) {
+                    mab[i] = __ffma2_rn(make_float2(v.x, v.y), g2[t], mab[i]);
+                    mqp[i] = __ffma2_rn(make_float2(v.z, v.w), g2[t], mqp[i]);
+                }
+            }
+        }
+        mbar_arrive(emptyBase + 8u * st);  // all of this lane's reads of the slot are done
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            float m = mab[i].x * mab[i].y;
+            float nn = fmaf(mab[i].x, mab[i].x, mab[i].y * mab[i].y);
+            float th = fmaf(c, mab[i].x + mab[i].y, kTh);
+            float A1h = m + th;
+            float B1 = fmaf(2.f, th, nn);
+            float A2h = mqp[i].y - m;
+            float B2 = mqp[i].x - nn;
+            float ssim4 = __fdividef(A1h * A2h, B1 * B2);
+            fs[i] += valid[i] ? ssim4 : 0.f;
+        }
+    }
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if (lane == 0) p.partials[seg] = dsum * 4.0;
@@ -501,7 +717,15 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
     gaussian1d(p.g);
     long long segs = (long long)n * g.nsx * g.nsy;
     long long blocks = (segs + 3) / 4;
-    if (g.cpl == 4) ssim_strip_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(p);
+    static const bool useWs = [] { const char *e = getenv("FB_SSIM_WS"); return e && e[0] == '1'; }();
+    if (useWs && g.cpl == 4 && p.vecOK && (w & 3) == 0) {
+        static bool attrSet = false;
+        if (!attrSet) {
+            FB_CUDA(cudaFuncSetAttribute(ssim_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
+            attrSet = true;
+        }
+        ssim_ws_kernel<<<(unsigned)blocks, 256, sizeof(WsSmem), s>>>(p);
+    } else if (g.cpl == 4) ssim_strip_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(p);
     else ssim_strip_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(p);
     FB_CUDA(cudaGetLastError());
     ssim_finalize_kernel<<<n, 32, 0, s>>>(p.partials, g.nsx * g.nsy, (long long)(w - 8) * (h - 8), scores,

@@ -133,6 +133,18 @@ __global__ void __launch_bounds__(256) bench(float *out, int iters, float seed) 
                 asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(u[i + 4]) : "r"(299u | (587u << 16)), "r"(u[i]), "r"(t));
                 u[i] += u[i + 4];
             }
+        } else if (MODE == 18 || MODE == 19 || MODE == 20) {  // FFMA2 x8 (+ FFMA x8 | + IDP x8)
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                unsigned long long p, q, r;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(a[2 * i]), "f"(a[2 * i + 1]));
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(q) : "f"(w));
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(c));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p) : "l"(q), "l"(r));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a[2 * i]), "=f"(a[2 * i + 1]) : "l"(p));
+                if (MODE == 19) { float t = __uint_as_float(u[i]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(t) : "f"(w), "f"(c)); u[i] = __float_as_uint(t); }
+                if (MODE == 20) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]), "r"(0x01020304));
+            }
         } else if (MODE == 16) {  // HFMA2 x8 (fp16x2)
 #pragma unroll
             for (int i = 0; i < 8; i++) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(0x3c003c00), "r"(0x00010001));
@@ -250,6 +262,9 @@ int main() {
     run<11>("FFMA2 x8 + DFMA x4 [fma32-ops]", 16, out, sms, clk);
     run<12>("FFMA x16 + LDS.128 x2 [fma]", 16, out, sms, clk);
     run<17>("DP2A x8 (+4 IADD)", 8, out, sms, clk);
+    run<18>("FFMA2 x8 alone [ffma2-instr]", 8, out, sms, clk);
+    run<19>("FFMA2 x8 + FFMA x8 [ffma2-instr]", 8, out, sms, clk);
+    run<20>("FFMA2 x8 + DP4A x8 [ffma2-instr]", 8, out, sms, clk);
     run_filt<1>("filter pattern FFMA2", out, sms, clk, 2);
     run_filt<1>("filter pattern FFMA2", out, sms, clk, 4);
     run_filt<0>("filter pattern FFMA", out, sms, clk, 2);
