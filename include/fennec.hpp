@@ -1,0 +1,111 @@
+// fennec.hpp — C++ host-side mirror of fennec's Go API for the hot path, over the C ABI (fennec_b200.h).
+//
+// The reference is compiled Go; no Go toolchain exists in the build image, so the host layer above the
+// C ABI is provided in C++ (this header) and in Python (fennec_b200/api.py).  Names, argument meaning and
+// guard behaviour follow the Go functions (file:line cited per function): where Go returns its input
+// pointer unchanged, the SAME shared_ptr is returned; where it returns an empty image, an empty NRGBA.
+// Every function calls libfennec_b200.so; there is no CPU compute here.  Errors (no GPU, OOM, bad
+// arguments) throw fennec::Error — the Go shim falls back to the pure-Go body instead.
+#pragma once
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fennec_b200.h"
+
+namespace fennec {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string &m) : std::runtime_error("libfennec_b200 status " + std::to_string(s) + ": " + m), status(s) {}
+};
+
+inline int check(int status) {
+    if (status < 0) throw Error(status, fb_last_error());
+    return status;
+}
+
+// image.NRGBA: Pix (R,G,B,A interleaved, non-premultiplied), Stride bytes per row.
+struct NRGBA {
+    std::vector<uint8_t> Pix;
+    int Stride = 0, W = 0, H = 0;
+    NRGBA() = default;
+    NRGBA(int w, int h) : Pix((size_t)(w > 0 ? w : 0) * (h > 0 ? h : 0) * 4, 0), Stride((w > 0 ? w : 0) * 4), W(w > 0 ? w : 0), H(h > 0 ? h : 0) {}
+    uint8_t *at(int x, int y) { return Pix.data() + (size_t)y * Stride + (size_t)x * 4; }
+    const uint8_t *data() const { return Pix.empty() ? nullptr : Pix.data(); }
+    uint8_t *data() { return Pix.empty() ? nullptr : Pix.data(); }
+};
+using Image = std::shared_ptr<NRGBA>;
+inline Image NewNRGBA(int w, int h) { return std::make_shared<NRGBA>(w, h); }  // zero-filled like image.NewNRGBA
+
+// lanczosResize — resize.go:37-53
+inline Image lanczosResize(const Image &img, int dstW, int dstH) {
+    if (img->W <= 0 || img->H <= 0 || dstW <= 0 || dstH <= 0) return NewNRGBA(0, 0);
+    Image dst = NewNRGBA(dstW, dstH);
+    check(fb_lanczos_resize(img->data(), img->Stride, img->W, img->H, dst->data(), dst->Stride, dstW, dstH, nullptr, nullptr));
+    return dst;
+}
+
+// smartResize — resize.go:12-32 (returns img itself when it already fits)
+inline Image smartResize(const Image &img, int maxW, int maxH) {
+    int dw = 0, dh = 0;
+    if (fb_smart_resize_dims(img->W, img->H, maxW, maxH, &dw, &dh) == 1) return img;
+    return lanczosResize(img, dw, dh);
+}
+
+namespace detail {
+typedef int (*score_fn)(const uint8_t *, int, const uint8_t *, int, int, int, double *);
+inline double score(score_fn fn, const Image &a, Image b, bool resize) {
+    if (resize && (b->W != a->W || b->H != a->H)) b = lanczosResize(b, a->W, a->H);  // ssim.go:31-33 / 320-322
+    if (b->W != a->W || b->H != a->H) throw Error(FB_E_INVALID, "images must have equal dimensions");
+    double out = 0.0;
+    check(fn(a->data(), a->Stride, b->data(), b->Stride, a->W, a->H, &out));
+    return out;
+}
+}  // namespace detail
+
+inline double SSIM(const Image &a, const Image &b) { return detail::score(fb_ssim, a, b, true); }          // ssim.go:24-43
+inline double SSIMFast(const Image &a, const Image &b) { return detail::score(fb_ssim_fast, a, b, false); }  // ssim.go:48-70
+inline double MSSSIM(const Image &a, const Image &b) { return detail::score(fb_msssim, a, b, true); }       // ssim.go:313-365
+
+// boxDownsample — ssim.go:244-309
+inline Image boxDownsample(const Image &img, int dstW, int dstH) {
+    if (img->W <= 0 || img->H <= 0 || dstW <= 0 || dstH <= 0) return NewNRGBA(0, 0);
+    Image dst = NewNRGBA(dstW, dstH);
+    check(fb_box_downsample(img->data(), img->Stride, img->W, img->H, dst->data(), dst->Stride, dstW, dstH));
+    return dst;
+}
+
+// GaussianBlur — effects.go:146-220 (sigma <= 0 → the same pointer)
+inline Image GaussianBlur(const Image &img, double sigma) {
+    if (sigma <= 0) return img;
+    Image dst = NewNRGBA(img->W, img->H);
+    check(fb_gaussian_blur_sigma(img->data(), img->Stride, img->W, img->H, sigma, dst->data(), dst->Stride));
+    return dst;
+}
+
+namespace detail {
+typedef int (*fx_fn)(const uint8_t *, int, int, int, double, uint8_t *, int);
+inline Image fx(fx_fn fn, const Image &img, double strength) {
+    if (strength <= 0 || img->W < 3 || img->H < 3) return img;  // effects.go:11-22 / 50-61
+    Image dst = NewNRGBA(img->W, img->H);
+    if (check(fn(img->data(), img->Stride, img->W, img->H, strength, dst->data(), dst->Stride)) == FB_IDENTITY) return img;
+    return dst;
+}
+}  // namespace detail
+
+inline Image Sharpen(const Image &img, double strength) { return detail::fx(fb_sharpen, img, strength); }                  // effects.go:10-45
+inline Image AdaptiveSharpen(const Image &img, double strength) { return detail::fx(fb_adaptive_sharpen, img, strength); }  // effects.go:49-90
+
+// The sharder part of CompressBatch (batch.go:58-128): items [begin, end) of shard `shard`.
+struct ShardRange { int begin, end; };
+inline ShardRange BatchShard(int nItems, int nShards, int shard) {
+    ShardRange r{0, 0};
+    check(fb_batch_shard(nItems, nShards, shard, &r.begin, &r.end));
+    return r;
+}
+
+}  // namespace fennec
