@@ -670,7 +670,7 @@ Geo geometry(int w, int h, int n) {
     g.nsx = (ow + g.outc - 1) / g.outc;
     // Aim for >= ~8 warps per SM over 148 SMs while keeping the 7-row warm-up overhead small.
     long long want = 148LL * 16;
-    int rs = 128;
+    int rs = 128;  // 256 was measured slightly slower (tail effects outweigh the smaller 7-row warm-up)
     while (rs > 16 && (long long)n * g.nsx * ((oh + rs - 1) / rs) < want) rs >>= 1;
     g.rs = rs;
     g.nsy = (oh + rs - 1) / rs;

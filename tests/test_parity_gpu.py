@@ -220,6 +220,19 @@ def test_4k_ssim_properties(lib):
     assert np.all(np.abs((top * n_top + bot * n_bot) / (n_top + n_bot) - s_ab) <= 2e-6)
 
 
+def test_4k_ssim_vs_oracle(lib, oracle):
+    # BASELINE.json's metric shape itself: the multi-threaded oracle needs ~0.2 s per 4K pair
+    for seed, kind in ((11, "noise"), (12, "grad")):
+        a = S.noise_image(3840, 2160, seed) if kind == "noise" else S.gradient_noise_image(3840, 2160, seed)
+        b = S.perturb(a, seed + 1, 6)
+        want = oracle.ssim(a, b)
+        assert abs(api.SSIM(a, b) - want) <= SCORE_TIGHT
+        da = torch.from_numpy(np.stack([a] * 24)).cuda()   # a batch large enough to pick the tallest strip segments
+        db = torch.from_numpy(np.stack([b] * 24)).cuda()
+        got = batch.ssim_batch(da, db).cpu().numpy()
+        assert np.all(np.abs(got - want) <= SCORE_TIGHT)
+
+
 def test_4k_blur_sharpen_properties(lib):
     flat = torch.full((1, 2160, 3840, 4), 137, dtype=torch.uint8, device="cuda")
     assert torch.equal(batch.gaussian_blur_batch(flat, 2.0), flat)      # a convex combination of a constant
