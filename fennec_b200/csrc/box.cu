@@ -107,6 +107,48 @@ __global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams p) {
   }
 }
 
+// Exact 2x2 boxes (srcW == 2*dstW, srcH == 2*dstH: the MSSSIM cascade, ssim.go:354-360): the mean of four
+// bytes times 0.25 is exact in binary64, so clampF(sum * (1.0/4)) == (sum + 2) >> 2.  Pure streaming:
+// each thread reads 4 pixels from two rows (two 128-bit loads) and writes 2 pixels; SIMD on 16-bit lanes.
+__global__ void __launch_bounds__(kThreads) box2x_kernel(const BoxParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;   // 4 source px = 2 dest px per thread
+    const int dy = blockIdx.y, img = blockIdx.z;
+    const int sx = t * 4;
+    if (sx >= p.srcW) return;
+    const uint8_t *r0 = p.src + (long long)img * p.srcImgStride + (long long)(2 * dy) * p.srcRowStride + (long long)sx * 4;
+    const uint8_t *r1 = r0 + p.srcRowStride;
+    uint32_t a[4], b[4];
+    if (p.vecOK && sx + 4 <= p.srcW) {
+        uint4 u = ld_nc_u128(r0), v = ld_nc_u128(r1);
+        a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w;
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            a[i] = (sx + i < p.srcW) ? ld_nc_u32(r0 + 4 * i) : 0u;
+            b[i] = (sx + i < p.srcW) ? ld_nc_u32(r1 + 4 * i) : 0u;
+        }
+    }
+    uint32_t out[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t rb = (a[2 * k] & 0x00FF00FFu) + (a[2 * k + 1] & 0x00FF00FFu) + (b[2 * k] & 0x00FF00FFu) + (b[2 * k + 1] & 0x00FF00FFu);
+        const uint32_t ga = ((a[2 * k] >> 8) & 0x00FF00FFu) + ((a[2 * k + 1] >> 8) & 0x00FF00FFu) +
+                            ((b[2 * k] >> 8) & 0x00FF00FFu) + ((b[2 * k + 1] >> 8) & 0x00FF00FFu);
+        const uint32_t mrb = ((rb + 0x00020002u) >> 2) & 0x00FF00FFu;
+        const uint32_t mga = ((ga + 0x00020002u) >> 2) & 0x00FF00FFu;
+        out[k] = mrb | (mga << 8);
+    }
+    uint8_t *d = p.dst + (long long)img * p.dstImgStride + (long long)dy * p.dstRowStride + (long long)(sx / 2) * 4;
+    const int dx = sx / 2;
+    if (dx + 2 <= p.dstW && (((uintptr_t)d) & 7) == 0) {
+        *reinterpret_cast<uint2 *>(d) = make_uint2(out[0], out[1]);
+    } else {
+        if (dx < p.dstW) *reinterpret_cast<uint32_t *>(d) = out[0];
+        if (dx + 1 < p.dstW) *reinterpret_cast<uint32_t *>(d + 4) = out[1];
+    }
+}
+
 // Generic fallback: one thread per output pixel walks its own box (upsampling, boxes taller than
 // 256 rows or wider than the shared-memory span). Same arithmetic.
 __global__ void __launch_bounds__(kThreads) box_naive_kernel(const BoxParams p) {
@@ -172,7 +214,11 @@ int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int s
     // and at least one output column per shared-memory span.
     int maxBoxW = (int)p.xRatio + 2, maxBoxH = (int)p.yRatio + 2;
     bool fast = p.xRatio >= 1.0 && p.yRatio >= 1.0 && maxBoxH <= 256 && maxBoxW <= kSpanMax / 2;
-    if (fast) {
+    if (srcW == 2 * dstW && srcH == 2 * dstH) {  // every box is exactly 2x2
+        p.dxChunk = 0; p.dyPerCta = 1;
+        dim3 grid(((srcW + 3) / 4 + kThreads - 1) / kThreads, dstH, n);
+        box2x_kernel<<<grid, kThreads, 0, s>>>(p);
+    } else if (fast) {
         int chunk = (int)((double)(kSpanMax - maxBoxW - 4) / p.xRatio);
         if (chunk < 1) chunk = 1;
         if (chunk > dstW) chunk = dstW;

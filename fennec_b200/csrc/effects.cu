@@ -259,10 +259,10 @@ __global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
         int sy = min(max(y0 - R + i, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
         raw[i] = __ldg(reinterpret_cast<const uint32_t *>(scol + (long long)sy * p.srcRowStride));
     }
+    const uint8_t *acol = p.alpha + (long long)img * p.alphaImgStride + (long long)x * 4;
     float2 acc[kTile / 2][3];
     blur_taps_fp32<R, NIN, R>(raw, p.kernel32, acc);
     const float lim = 0.5f - p.eps;
-    const uint8_t *acol = p.alpha + (long long)img * p.alphaImgStride + (long long)x * 4;
     uint8_t *dcol = p.dst + (long long)img * p.dstImgStride + (long long)x * 4;
     uint32_t ambMask = 0;
 #pragma unroll
@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
             const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
             uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
             if (a0 | a1 | a2) ambMask |= 1u << j;
+            // (hoisting these 16 alpha loads above the tap loop was measured slower: +16 registers cost occupancy)
             uint32_t a = ld_nc_u32(acol + (long long)y * p.alphaRowStride) & 0xFF000000u;  // effects.go:215
             *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = r | (g << 8) | (b << 16) | a;
         }

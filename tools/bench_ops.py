@@ -58,8 +58,9 @@ if want("lanczos"):
            7680 * 4320 * 4 + 1920 * 1080 * 4)
     del x, y
 if want("msssim"):
-    a, b = noise(4, 4320, 7680, 7), noise(4, 4320, 7680, 8)
-    report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 4, 33.1776, 2 * 7680 * 4320 * 4)
+    a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
+    report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)
+    del a, b
     x = noise(8, 4320, 7680, 9)
     y = torch.zeros((8, 288, 512, 4), dtype=torch.uint8, device="cuda")
     report("boxDownsample 7680x4320->512x288", timeit(lambda: batch.box_downsample_batch(x, 512, 288, out=y), 10), 8, 33.1776, 7680 * 4320 * 4)
