@@ -99,7 +99,38 @@ struct LanczosTable {
     int groups = 0;
     int entries = 0, maxTaps = 0;
     double wabs = 0.0;  // max over destinations of sum |w| (error bound of the FP32 fast path)
+    IntRatioInfo ir;    // ir.ratio >= 2 when the integer-ratio kernel applies
 };
+
+// Integer ratio (srcSize == R*dstSize): find the range of destinations whose taps are R*d + off with weights
+// bit-identical to a reference interior destination (precomputeWeights gives that for every unclipped d).
+static void detect_int_ratio(const int *start, const int *index, const double *weight, int dstSize, int srcSize,
+                             IntRatioInfo *ir) {
+    *ir = IntRatioInfo();
+    if (dstSize <= 0 || srcSize % dstSize != 0) return;
+    const int R = srcSize / dstSize;
+    if (R < 2 || R > 4) return;
+    const int mid = dstSize / 2;
+    const int T = start[mid + 1] - start[mid];
+    if (T <= 0 || T > 24) return;
+    const int off = index[start[mid]] - R * mid;
+    auto same = [&](int d) {
+        if (start[d + 1] - start[d] != T) return false;
+        for (int k = 0; k < T; k++) {
+            if (index[start[d] + k] != R * d + off + k) return false;
+            if ((float)weight[start[d] + k] != (float)weight[start[mid] + k]) return false;
+        }
+        return true;
+    };
+    int lo = mid, hi = mid + 1;
+    while (lo > 0 && same(lo - 1)) lo--;
+    while (hi < dstSize && same(hi)) hi++;
+    if (hi - lo < 8) return;
+    ir->ratio = R; ir->taps = T; ir->off = off; ir->dLo = lo; ir->dHi = hi;
+    float ws = 0.f;
+    for (int k = 0; k < T; k++) { ir->w[k] = (float)weight[start[mid] + k]; ws += ir->w[k]; }
+    ir->wsum = ws;
+}
 
 // Grouped layout (see resize.cu ResizeParams): returns false when some destination's taps are not contiguous.
 static bool build_groups(const int *start, const int *index, const double *weight, int n, std::vector<int> &first,
@@ -323,6 +354,7 @@ static int lanczos_table_cached(DevCtx *c, int dstSize, int srcSize, LanczosTabl
     LanczosTable t;
     t.entries = n;
     table_stats(start.data(), weight.data(), dstSize, &t.maxTaps, &t.wabs);
+    detect_int_ratio(start.data(), index.data(), weight.data(), dstSize, srcSize, &t.ir);
     std::vector<float> w32(n + 1);
     for (int i = 0; i < n; i++) w32[i] = (float)weight[i];
     FB_CUDA(cudaMalloc((void **)&t.start, sizeof(int) * (dstSize + 1)));
@@ -824,9 +856,9 @@ static int resize_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, long
     uint8_t *tmp = (uint8_t *)c->ws.take((size_t)timg * n);
     if (!tmp) { set_error("internal: workspace under-reserved (resize tmp)"); return FB_E_INVALID; }
     FB_TRY(launch_resize_h(s, dsrc, srcImgStride, srcRowStride, srcW, srcH, tmp, timg, tpitch, dstW, n, tx.start,
-                           tx.index, tx.weight, tx.weight32, tx.maxTaps, tx.wabs, tx.first, tx.wpadT, tx.groups));
+                           tx.index, tx.weight, tx.weight32, tx.maxTaps, tx.wabs, tx.first, tx.wpadT, tx.groups, &tx.ir));
     return launch_resize_v(s, tmp, timg, tpitch, dstW, srcH, ddst, dstImgStride, dstRowStride, dstH, n, ty.start,
-                           ty.index, ty.weight, ty.weight32, ty.maxTaps, ty.wabs);
+                           ty.index, ty.weight, ty.weight32, ty.maxTaps, ty.wabs, &ty.ir);
 }
 
 int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH, uint8_t *dst, int dstStride, int dstW,

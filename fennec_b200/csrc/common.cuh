@@ -99,15 +99,21 @@ int launch_sharpen(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long i
                    int w, int h, int n, long long dstImgStride, int dstRowStride, double amount, int adaptive);
 
 // resize.cu
+// When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.
+struct IntRatioInfo {
+    int ratio = 0, taps = 0, off = 0, dLo = 0, dHi = 0;
+    float wsum = 0.f;
+    float w[28];
+};
 int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,
                     const int *start_dev, const int *index_dev, const double *weight_dev,
                     const float *weight32_dev, int maxTaps, double wabs, const int *first_dev,
-                    const float *wpadT_dev, int groups);
+                    const float *wpadT_dev, int groups, const IntRatioInfo *ir);
 int launch_resize_v(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstH, int n,
                     const int *start_dev, const int *index_dev, const double *weight_dev,
-                    const float *weight32_dev, int maxTaps, double wabs);
+                    const float *weight32_dev, int maxTaps, double wabs, const IntRatioInfo *ir);
 
 #ifdef __CUDACC__
 // ---- device helpers ---------------------------------------------------------------------------

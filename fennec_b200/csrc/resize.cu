@@ -116,24 +116,81 @@ __device__ __forceinline__ uint32_t finish_fp32(float r, float g, float b, float
     return out;
 }
 
-// Exact FP64 sequence of the reference for one destination pixel (resize.go:93-113).
+// Exact FP64 sequence of the reference for one destination pixel (resize.go:93-113).  Taps are fetched eight at
+// a time (independent loads in flight) and bytes become doubles through the 2^52 mantissa trick, so the rare
+// exact path is neither a chain of dependent global loads nor a queue on the conversion unit.
+__device__ __forceinline__ double byte_to_double(uint32_t b) {
+    return __hiloint2double(0x43300000, (int)b) - 4503599627370496.0;  // (2^52 + b) - 2^52, exact
+}
+
 template <bool VERTICAL>
 __device__ __forceinline__ void exact_px(const ResizeParams &p, const uint8_t *s, int x, int y, uint8_t *dpx) {
     const int d = VERTICAL ? y : x;
     const int t0 = __ldg(p.start + d), t1 = __ldg(p.start + d + 1);
     double r2 = 0.0, g2 = 0.0, b2 = 0.0, a2 = 0.0;
-    for (int t = t0; t < t1; t++) {
-        const int si = __ldg(p.index + t);
-        const double w = __ldg(p.weight + t);
-        const uint32_t v = VERTICAL ? __ldg(reinterpret_cast<const uint32_t *>(s + (long long)si * p.srcRowStride + (long long)x * 4))
-                                    : __ldg(reinterpret_cast<const uint32_t *>(s + (long long)y * p.srcRowStride + (long long)si * 4));
-        const double aw = __dmul_rn((double)(v >> 24), w);
-        r2 = __dadd_rn(r2, __dmul_rn((double)(v & 0xFF), aw));
-        g2 = __dadd_rn(g2, __dmul_rn((double)((v >> 8) & 0xFF), aw));
-        b2 = __dadd_rn(b2, __dmul_rn((double)((v >> 16) & 0xFF), aw));
-        a2 = __dadd_rn(a2, aw);
+    for (int tb = t0; tb < t1; tb += 8) {
+        uint32_t v[8];
+        double w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int t = min(tb + k, t1 - 1);
+            const int si = __ldg(p.index + t);
+            w[k] = __ldg(p.weight + t);
+            v[k] = VERTICAL ? __ldg(reinterpret_cast<const uint32_t *>(s + (long long)si * p.srcRowStride + (long long)x * 4))
+                            : __ldg(reinterpret_cast<const uint32_t *>(s + (long long)y * p.srcRowStride + (long long)si * 4));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (tb + k < t1) {
+                const double aw = __dmul_rn(byte_to_double(v[k] >> 24), w[k]);
+                r2 = __dadd_rn(r2, __dmul_rn(byte_to_double(v[k] & 0xFF), aw));
+                g2 = __dadd_rn(g2, __dmul_rn(byte_to_double((v[k] >> 8) & 0xFF), aw));
+                b2 = __dadd_rn(b2, __dmul_rn(byte_to_double((v[k] >> 16) & 0xFF), aw));
+                a2 = __dadd_rn(a2, aw);
+            }
+        }
     }
     finish_px(r2, g2, b2, a2, dpx);
+}
+
+// FP32 sums of one destination pixel through the general (CSR / grouped) tables.
+template <bool VERTICAL, bool GROUPED>
+__device__ __forceinline__ void general_sums(const ResizeParams &p, const uint8_t *s, int x, int y,
+                                             float &r, float &g, float &b, float &a) {
+    r = g = b = a = 0.f;
+    if (GROUPED) {  // horizontal: 128-bit pixel groups + transposed padded weights
+        const int first = __ldg(p.first + x);
+        const int g0 = first & ~3;
+        const int ng = ((first + (__ldg(p.start + x + 1) - __ldg(p.start + x)) - 1) >> 2) - (g0 >> 2) + 1;
+        const uint8_t *row = s + (long long)y * p.srcRowStride;
+        for (int q = 0; q < ng; q++) {
+            const int px0 = g0 + 4 * q;
+            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.wpadT) + (size_t)q * p.outW + x);
+            uint32_t v[4];
+            if (p.vecOK && px0 + 4 <= p.srcW) {
+                uint4 t = __ldg(reinterpret_cast<const uint4 *>(row + (long long)px0 * 4));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)  // pixels past the row end carry zero weights
+                    v[j] = (px0 + j < p.srcW) ? __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(px0 + j) * 4)) : 0u;
+            }
+            tap_fp32(v[0], w4.x, r, g, b, a);
+            tap_fp32(v[1], w4.y, r, g, b, a);
+            tap_fp32(v[2], w4.z, r, g, b, a);
+            tap_fp32(v[3], w4.w, r, g, b, a);
+        }
+    } else {
+        const int d = VERTICAL ? y : x;
+        const int t0 = __ldg(p.start + d), t1 = __ldg(p.start + d + 1);
+        for (int t = t0; t < t1; t++) {
+            const int si = __ldg(p.index + t);
+            const float w = __ldg(p.weight32 + t);
+            const uint32_t v = VERTICAL ? __ldg(reinterpret_cast<const uint32_t *>(s + (long long)si * p.srcRowStride + (long long)x * 4))
+                                        : __ldg(reinterpret_cast<const uint32_t *>(s + (long long)y * p.srcRowStride + (long long)si * 4));
+            tap_fp32(v, w, r, g, b, a);
+        }
+    }
 }
 
 template <bool VERTICAL, bool GROUPED>
@@ -147,40 +204,8 @@ __global__ void __launch_bounds__(256) resize_pass_fast_kernel(const ResizeParam
     const uint8_t *s = p.src + (long long)img * p.srcImgStride;
     uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride;
     if (x < p.outW) {
-        float r = 0.f, g = 0.f, b = 0.f, a = 0.f;
-        if (GROUPED) {  // horizontal: 128-bit pixel groups + transposed padded weights
-            const int first = __ldg(p.first + x);
-            const int g0 = first & ~3;
-            const int ng = ((first + (__ldg(p.start + x + 1) - __ldg(p.start + x)) - 1) >> 2) - (g0 >> 2) + 1;
-            const uint8_t *row = s + (long long)y * p.srcRowStride;
-            for (int q = 0; q < ng; q++) {
-                const int px0 = g0 + 4 * q;
-                const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.wpadT) + (size_t)q * p.outW + x);
-                uint32_t v[4];
-                if (p.vecOK && px0 + 4 <= p.srcW) {
-                    uint4 t = __ldg(reinterpret_cast<const uint4 *>(row + (long long)px0 * 4));
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)  // pixels past the row end carry zero weights
-                        v[j] = (px0 + j < p.srcW) ? __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(px0 + j) * 4)) : 0u;
-                }
-                tap_fp32(v[0], w4.x, r, g, b, a);
-                tap_fp32(v[1], w4.y, r, g, b, a);
-                tap_fp32(v[2], w4.z, r, g, b, a);
-                tap_fp32(v[3], w4.w, r, g, b, a);
-            }
-        } else {
-            const int d = VERTICAL ? y : x;
-            const int t0 = __ldg(p.start + d), t1 = __ldg(p.start + d + 1);
-            for (int t = t0; t < t1; t++) {
-                const int si = __ldg(p.index + t);
-                const float w = __ldg(p.weight32 + t);
-                const uint32_t v = VERTICAL ? __ldg(reinterpret_cast<const uint32_t *>(s + (long long)si * p.srcRowStride + (long long)x * 4))
-                                            : __ldg(reinterpret_cast<const uint32_t *>(s + (long long)y * p.srcRowStride + (long long)si * 4));
-                tap_fp32(v, w, r, g, b, a);
-            }
-        }
+        float r, g, b, a;
+        general_sums<VERTICAL, GROUPED>(p, s, x, y, r, g, b, a);
         bool amb;
         const uint32_t out = finish_fp32(r, g, b, a, p.Er, p.Ea, amb);
         if (amb) ambList[atomicAdd(&nAmb, 1)] = (unsigned short)threadIdx.x;
@@ -194,11 +219,192 @@ __global__ void __launch_bounds__(256) resize_pass_fast_kernel(const ResizeParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Integer-ratio kernel (srcSize == R * dstSize; config 4 is R = 4).  Every interior destination index d
+// then has the same T taps at source R*d + off with the SAME weights (verified on the host), so a thread
+// can produce kOut adjacent outputs from one window of T + (kOut-1)*R pixels with compile-time tap
+// indices: every byte is converted once and feeds up to kOut outputs (FFMA2 on output pairs with the
+// weight pairs (w[t], w[t-R])).  Windows that are fully opaque (alpha == 255 everywhere) skip the
+// premultiplication: v = sum(R*w) / sum(w).  Edge outputs and windows with any translucent pixel take the
+// general path per output.  Ambiguous results go to the block-compacted exact FP64 path as above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOut = 4;
+
+struct IntRatioParams {
+    ResizeParams base;
+    int off;        // first tap of destination d is R*d + off
+    int dLo, dHi;   // destinations in [dLo, dHi) are interior (identical weights, no clipping)
+    float wsum;     // FP32 sum of the weights
+    float w[28];    // the T shared weights (T <= 24 used)
+};
+
+template <bool VERTICAL, int R, int T>
+__global__ void __launch_bounds__(128) resize_int_ratio_kernel(const IntRatioParams q) {
+    constexpr int NIN = T + (kOut - 1) * R;          // window of one thread
+    constexpr int SPAN = R * kOut * 128 + T - R;      // source pixels one block's row segment needs (horizontal)
+    constexpr int CHUNKS = (SPAN + 15) / 16 + 2;
+    constexpr int CHB = 80;                           // 16-px chunk + 16 B pad: conflict-free LDS.128 at 1 chunk / thread
+    static_assert(R * kOut == 16 || VERTICAL, "horizontal staging assumes one 16-px chunk per thread");
+    const ResizeParams &p = q.base;
+    __shared__ int nAmb;
+    __shared__ unsigned short ambList[128 * kOut];
+    __shared__ __align__(16) uint8_t stage[VERTICAL ? 16 : CHUNKS * CHB];
+    if (threadIdx.x == 0) nAmb = 0;
+    // HORIZONTAL: thread = kOut adjacent output columns of row y.  VERTICAL: thread = column x, kOut adjacent rows.
+    const int img = blockIdx.z;
+    const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = VERTICAL ? tix : tix * kOut;
+    const int y0 = VERTICAL ? blockIdx.y * kOut : blockIdx.y;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
+    const int d0 = VERTICAL ? y0 : x0;
+    const int nd = VERTICAL ? p.outH : p.outW;
+    const bool inRange = VERTICAL ? (x0 < p.outW && y0 < p.outH) : (x0 < p.outW);
+    if (!VERTICAL) {
+        // Stage the block's source span with coalesced 64-bit loads (the span starts at an even pixel: R*d+off
+        // with R*kOut == 16 and even off), zero outside the row.  Staging pixel u <-> source pixel sBase + u.
+        const int sBase = R * (blockIdx.x * blockDim.x * kOut) + q.off;
+        const uint8_t *row = s + (long long)y0 * p.srcRowStride;
+        const bool al8 = (((uintptr_t)row + (long long)sBase * 4) & 7) == 0;
+        for (int u = threadIdx.x * 2; u < SPAN + 1; u += 256) {
+            const int sx = sBase + u;
+            uint2 v = make_uint2(0u, 0u);
+            if (al8 && sx >= 0 && sx + 1 < p.srcW) v = __ldg(reinterpret_cast<const uint2 *>(row + (long long)sx * 4));
+            else {
+                if (sx >= 0 && sx < p.srcW) v.x = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)sx * 4));
+                if (sx + 1 >= 0 && sx + 1 < p.srcW) v.y = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(sx + 1) * 4));
+            }
+            *reinterpret_cast<uint2 *>(stage + (u >> 4) * CHB + (u & 15) * 4) = v;
+        }
+    }
+    __syncthreads();
+    if (inRange) {
+        uint32_t outv[kOut];
+        bool ambv[kOut];
+        bool done = false;
+        if (d0 >= q.dLo && d0 + kOut <= q.dHi) {
+            uint32_t raw[NIN];
+            if (VERTICAL) {
+                const int s0 = R * d0 + q.off;  // first source row of the window
+#pragma unroll
+                for (int i = 0; i < NIN; i++)
+                    raw[i] = __ldg(reinterpret_cast<const uint32_t *>(s + (long long)(s0 + i) * p.srcRowStride + (long long)x0 * 4));
+            } else {
+                // window = staging pixels 16*t .. 16*t + NIN - 1: chunks t, t+1, t+2
+                const uint8_t *wbase = stage + threadIdx.x * CHB;
+#pragma unroll
+                for (int v4 = 0; v4 < (NIN + 3) / 4; v4++) {
+                    const int u = v4 * 4;
+                    const uint4 t4 = *reinterpret_cast<const uint4 *>(wbase + (u >> 4) * CHB + (u & 15) * 4);
+                    raw[u] = t4.x;
+                    if (u + 1 < NIN) raw[u + 1] = t4.y;
+                    if (u + 2 < NIN) raw[u + 2] = t4.z;
+                    if (u + 3 < NIN) raw[u + 3] = t4.w;
+                }
+            }
+            uint32_t andA = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < NIN; i++) andA &= raw[i];
+            if ((andA >> 24) == 0xFFu) {  // fully opaque window: v = sum(R*w) / sum(w)
+                float2 acc[kOut / 2][3];
+#pragma unroll
+                for (int m = 0; m < kOut / 2; m++) acc[m][0] = acc[m][1] = acc[m][2] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < NIN; i++) {
+                    const float f0 = byte_f(raw[i], 0), f1 = byte_f(raw[i], 1), f2 = byte_f(raw[i], 2);
+                    const float2 f00 = make_float2(f0, f0), f11 = make_float2(f1, f1), f22 = make_float2(f2, f2);
+#pragma unroll
+                    for (int m = 0; m < kOut / 2; m++) {
+                        const int t = i - 2 * m * R;  // tap of input i for output 2m; output 2m+1 uses t - R
+                        const bool v0 = t >= 0 && t < T, v1 = t - R >= 0 && t - R < T;
+                        if (v0 || v1) {
+                            const float2 wp = make_float2(v0 ? q.w[v0 ? t : 0] : 0.f, v1 ? q.w[v1 ? t - R : 0] : 0.f);
+                            acc[m][0] = __ffma2_rn(f00, wp, acc[m][0]);
+                            acc[m][1] = __ffma2_rn(f11, wp, acc[m][1]);
+                            acc[m][2] = __ffma2_rn(f22, wp, acc[m][2]);
+                        }
+                    }
+                }
+                const float a = 255.f * q.wsum;
+#pragma unroll
+                for (int j = 0; j < kOut; j++) {
+                    const float r = 255.f * ((j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x);
+                    const float g = 255.f * ((j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x);
+                    const float b = 255.f * ((j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x);
+                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
+                }
+            } else {  // translucent window: premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
+                float2 acc[kOut / 2][4];
+#pragma unroll
+                for (int m = 0; m < kOut / 2; m++) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < NIN; i++) {
+                    const float fa = byte_f(raw[i], 3);
+                    const float f0 = byte_f(raw[i], 0) * fa, f1 = byte_f(raw[i], 1) * fa, f2 = byte_f(raw[i], 2) * fa;
+                    const float2 f00 = make_float2(f0, f0), f11 = make_float2(f1, f1), f22 = make_float2(f2, f2),
+                                 faa = make_float2(fa, fa);
+#pragma unroll
+                    for (int m = 0; m < kOut / 2; m++) {
+                        const int t = i - 2 * m * R;
+                        const bool v0 = t >= 0 && t < T, v1 = t - R >= 0 && t - R < T;
+                        if (v0 || v1) {
+                            const float2 wp = make_float2(v0 ? q.w[v0 ? t : 0] : 0.f, v1 ? q.w[v1 ? t - R : 0] : 0.f);
+                            acc[m][0] = __ffma2_rn(f00, wp, acc[m][0]);
+                            acc[m][1] = __ffma2_rn(f11, wp, acc[m][1]);
+                            acc[m][2] = __ffma2_rn(f22, wp, acc[m][2]);
+                            acc[m][3] = __ffma2_rn(faa, wp, acc[m][3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kOut; j++) {
+                    const float r = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
+                    const float g = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
+                    const float b = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
+                    const float a = (j & 1) ? acc[j / 2][3].y : acc[j / 2][3].x;
+                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
+                }
+            }
+            done = true;
+        }
+        if (!done) {  // edge outputs (clipped / renormalised taps): general tables, one output at a time
+#pragma unroll
+            for (int j = 0; j < kOut; j++) {
+                ambv[j] = false;
+                outv[j] = 0u;
+                if (d0 + j < nd) {
+                    float r, g, b, a;
+                    if (VERTICAL) general_sums<true, false>(p, s, x0, y0 + j, r, g, b, a);
+                    else general_sums<false, true>(p, s, x0 + j, y0, r, g, b, a);
+                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kOut; j++) {
+            if (d0 + j < nd) {
+                const int ox = VERTICAL ? x0 : x0 + j, oy = VERTICAL ? y0 + j : y0;
+                if (ambv[j]) ambList[atomicAdd(&nAmb, 1)] = (unsigned short)(threadIdx.x * kOut + j);
+                else *reinterpret_cast<uint32_t *>(dimg + (long long)oy * p.dstRowStride + (long long)ox * 4) = outv[j];
+            }
+        }
+    }
+    __syncthreads();
+    const int n = nAmb;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int lt = ambList[e] / kOut, j = ambList[e] % kOut;
+        const int t2 = blockIdx.x * blockDim.x + lt;
+        const int ox = VERTICAL ? t2 : t2 * kOut + j, oy = VERTICAL ? blockIdx.y * kOut + j : blockIdx.y;
+        exact_px<VERTICAL>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
+    }
+}
+
 template <bool VERTICAL>
 int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, uint8_t *dst,
                 long long dstImgStride, int dstRowStride, int outW, int outH, int n, const int *start,
                 const int *index, const double *weight, const float *weight32, int maxTaps, double wabs,
-                const int *first = nullptr, const float *wpadT = nullptr, int groups = 0, int srcSize = 0) {
+                const int *first = nullptr, const float *wpadT = nullptr, int groups = 0, int srcSize = 0,
+                const IntRatioInfo *ir = nullptr) {
     if (n <= 0 || outW <= 0 || outH <= 0) return FB_OK;
     ResizeParams p;
     p.src = src; p.dst = dst;
@@ -214,6 +420,24 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
     dim3 grid((outW + 255) / 256, outH, n);
     p.first = first; p.wpadT = wpadT; p.groups = groups; p.srcW = srcSize;
     p.vecOK = (((uintptr_t)src | (uintptr_t)srcImgStride | (uintptr_t)srcRowStride) & 15) == 0;
+    if (weight32 != nullptr && p.Ea < 0.2f && getenv("FB_RESIZE_GENERIC") == nullptr && ir && ir->ratio >= 2 &&
+        (VERTICAL || wpadT != nullptr) && getenv("FB_RESIZE_NO_INTRATIO") == nullptr) {
+        IntRatioParams q;
+        q.base = p; q.off = ir->off; q.dLo = ir->dLo; q.dHi = ir->dHi; q.wsum = ir->wsum;
+        for (int i = 0; i < 28; i++) q.w[i] = i < ir->taps ? ir->w[i] : 0.f;
+        dim3 g2 = VERTICAL ? dim3((outW + 127) / 128, (outH + kOut - 1) / kOut, n)
+                           : dim3(((outW + kOut - 1) / kOut + 127) / 128, outH, n);
+        bool launched = true;
+        if (ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_int_ratio_kernel<VERTICAL, 4, 24><<<g2, 128, 0, s>>>(q);
+        else if (VERTICAL && ir->ratio == 2 && ir->taps == 12) resize_int_ratio_kernel<true, 2, 12><<<g2, 128, 0, s>>>(q);
+        else if (VERTICAL && ir->ratio == 3 && ir->taps == 17) resize_int_ratio_kernel<true, 3, 17><<<g2, 128, 0, s>>>(q);
+        else launched = false;
+        if (launched) {
+            FB_LAUNCHED(1);
+            FB_CUDA(cudaGetLastError());
+            return FB_OK;
+        }
+    }
     if (weight32 != nullptr && p.Ea < 0.2f && getenv("FB_RESIZE_GENERIC") == nullptr) {
         if (!VERTICAL && wpadT != nullptr) resize_pass_fast_kernel<VERTICAL, true><<<grid, 256, 0, s>>>(p);
         else resize_pass_fast_kernel<VERTICAL, false><<<grid, 256, 0, s>>>(p);
@@ -230,19 +454,18 @@ int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, 
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,
                     const int *start_dev, const int *index_dev, const double *weight_dev,
                     const float *weight32_dev, int maxTaps, double wabs, const int *first_dev,
-                    const float *wpadT_dev, int groups) {
+                    const float *wpadT_dev, int groups, const IntRatioInfo *ir) {
     return launch_pass<false>(s, src, srcImgStride, srcRowStride, dst, dstImgStride, dstRowStride, dstW, srcH, n,
                               start_dev, index_dev, weight_dev, weight32_dev, maxTaps, wabs, first_dev, wpadT_dev,
-                              groups, srcW);
+                              groups, srcW, ir);
 }
 
 int launch_resize_v(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstH, int n,
                     const int *start_dev, const int *index_dev, const double *weight_dev,
-                    const float *weight32_dev, int maxTaps, double wabs) {
-    (void)srcH;
+                    const float *weight32_dev, int maxTaps, double wabs, const IntRatioInfo *ir) {
     return launch_pass<true>(s, src, srcImgStride, srcRowStride, dst, dstImgStride, dstRowStride, srcW, dstH, n,
-                             start_dev, index_dev, weight_dev, weight32_dev, maxTaps, wabs);
+                             start_dev, index_dev, weight_dev, weight32_dev, maxTaps, wabs, nullptr, nullptr, 0, srcH, ir);
 }
 
 }  // namespace fb

@@ -56,6 +56,9 @@ if want("lanczos"):
     x = noise(8, 4320, 7680, 6); y = torch.zeros((8, 1080, 1920, 4), dtype=torch.uint8, device="cuda")
     report("Lanczos3 7680x4320->1920x1080 (config 4)", timeit(lambda: batch.lanczos_resize_batch(x, 1920, 1080, out=y), 3), 8, 33.1776,
            7680 * 4320 * 4 + 1920 * 1080 * 4)
+    x[..., 3] = 255
+    report("Lanczos3 7680x4320->1920x1080 opaque (config 4)", timeit(lambda: batch.lanczos_resize_batch(x, 1920, 1080, out=y), 3), 8, 33.1776,
+           7680 * 4320 * 4 + 1920 * 1080 * 4)
     del x, y
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
