@@ -1,7 +1,7 @@
 """Tiny driver for `ncu --set full` captures: runs one op of the hot path a few times on device-resident
 synthetic data and nothing else (keeps the replayed launch count small).
 
-    python tools/profile_driver.py ssim|ssim_fast|msssim|blur|sharpen|lanczos|box [--pairs P] [--iters I]
+    python tools/profile_driver.py ssim|ssim_fast|msssim|blur|sharpen|adaptive|lanczos|box [--pairs P] [--iters I]
 """
 import argparse
 import os
@@ -34,6 +34,8 @@ for _ in range(args.iters):
         r = batch.gaussian_blur_batch(a, 2.0)
     elif args.op == "sharpen":
         r = batch.sharpen_batch(a, 0.5)
+    elif args.op == "adaptive":
+        r = batch.adaptive_sharpen_batch(a, 0.5)
     elif args.op == "lanczos":
         r = batch.lanczos_resize_batch(a, args.w // 4, args.h // 4)
     elif args.op == "box":
