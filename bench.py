@@ -279,7 +279,7 @@ def run_ours(args):
                        "parallelism": f"item-sharded x{world}, all_gather of float64 scores" if world > 1 else "single GPU",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic": (traffic["dram_bytes_per_launch"] * P / traffic.get("pairs_per_launch", P)) if traffic else None,
                          "peak_source": peak_src, "kernel": "ssim_strip_kernel<4> (+32-thread finalize)", "fma_pipe_note": "FP32-FMA-pipe-bound stencil, not HBM-bound: see profiles/ and DESIGN.md K1",
                          "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": P * BYTES_PER_PAIR,
                          },

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "fb_msssim_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_box_downsample_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fb_msssim_level_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "fb_gaussian_blur_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                              C.c_int, C.c_int, dp, C.c_int]),
     "fb_sharpen_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,

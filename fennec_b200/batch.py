@@ -69,6 +69,20 @@ def box_downsample_batch(src: torch.Tensor, dst_w: int, dst_h: int, out: Optiona
     return out
 
 
+def msssim_level_batch(a: torch.Tensor, b: torch.Tensor, tw: int, th: int):
+    """One MS-SSIM level step (ssim.go:57-58 + 354-360): (thumbA, thumbB, halfA, halfB) from one read of each image."""
+    pa, i_s, rs, w, h, n = _batch(a)
+    pb = _batch(b)[0]
+    thumbs = [torch.zeros((n, th, tw, 4), dtype=torch.uint8, device=a.device) for _ in range(2)]
+    halves = [torch.zeros((n, h // 2, w // 2, 4), dtype=torch.uint8, device=a.device) for _ in range(2)]
+    _, ti, tr, _, _, _ = _batch(thumbs[0])
+    _, hi, hr, _, _, _ = _batch(halves[0])
+    check(_lib.load().fb_msssim_level_batch_dev(_dev(a), _stream(a), pa, pb, i_s, rs, w, h, n, thumbs[0].data_ptr(),
+                                                thumbs[1].data_ptr(), ti, tr, tw, th, halves[0].data_ptr(),
+                                                halves[1].data_ptr(), hi, hr))
+    return thumbs[0], thumbs[1], halves[0], halves[1]
+
+
 def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Tensor] = None,
                         kernel: Optional[np.ndarray] = None) -> torch.Tensor:
     """fennec.GaussianBlur per image (effects.go:146-220); sigma <= 0 returns `src` itself."""

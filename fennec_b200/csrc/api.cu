@@ -488,19 +488,50 @@ static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, in
     mark_pin_busy(c, s);
     ImgBatch ca = a, cb = b;
     for (int l = 0; l < L; l++) {
-        FB_TRY(pipeline_ssim_fast(c, s, ca, cb, plan[l].w, plan[l].h, n, levelScores + l, L));
+        const int lw = plan[l].w, lh = plan[l].h;
+        ImgBatch na{nullptr, 0, 0}, nb{nullptr, 0, 0};
         if (l + 1 < L) {  // 2x box cascade (ssim.go:354-360)
             int nw = plan[l + 1].w, nh = plan[l + 1].h;
             int pitch = dev_pitch(nw);
             long long imgBytes = (long long)pitch * nh;
-            uint8_t *na = (uint8_t *)c->ws.take((size_t)imgBytes * n);
-            uint8_t *nb = (uint8_t *)c->ws.take((size_t)imgBytes * n);
-            if (!na || !nb) { set_error("internal: workspace under-reserved (msssim level)"); return FB_E_INVALID; }
-            FB_TRY(launch_box(s, ca.p, ca.imgStride, ca.rowStride, plan[l].w, plan[l].h, na, imgBytes, pitch, nw, nh, n, nullptr));
-            FB_TRY(launch_box(s, cb.p, cb.imgStride, cb.rowStride, plan[l].w, plan[l].h, nb, imgBytes, pitch, nw, nh, n, nullptr));
-            ca = ImgBatch{na, imgBytes, pitch};
-            cb = ImgBatch{nb, imgBytes, pitch};
+            uint8_t *pa = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+            uint8_t *pb = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+            if (!pa || !pb) { set_error("internal: workspace under-reserved (msssim level)"); return FB_E_INVALID; }
+            na = ImgBatch{pa, imgBytes, pitch};
+            nb = ImgBatch{pb, imgBytes, pitch};
         }
+        // Fused level step: when this level needs both a thumbnail (SSIMFast, > 512 px) and the next level's
+        // image, one kernel reads it once and writes both (box.cu: box_fused_kernel).
+        int tw, th;
+        bool fused = false;
+        if (l + 1 < L && ssim_fast_dims(lw, lh, &tw, &th) && plan[l + 1].w * 2 == lw && plan[l + 1].h * 2 == lh) {
+            int tpitch = dev_pitch(tw);
+            long long tBytes = (long long)tpitch * th;
+            size_t mark = c->ws.off;
+            uint8_t *ta = (uint8_t *)c->ws.take((size_t)tBytes * n);
+            uint8_t *tb = (uint8_t *)c->ws.take((size_t)tBytes * n);
+            if (!ta || !tb) { set_error("internal: workspace under-reserved (msssim thumbs)"); return FB_E_INVALID; }
+            int rc = launch_box_fused(s, ca.p, ca.imgStride, ca.rowStride, cb.p, cb.imgStride, cb.rowStride, lw, lh, ta, tb,
+                                      tBytes, tpitch, tw, th, (uint8_t *)na.p, (uint8_t *)nb.p, na.imgStride, na.rowStride, n);
+            if (rc < 0) return rc;
+            if (rc == FB_OK) {
+                void *scratch = c->ws.take(ssim_scratch_bytes(tw, th, n));
+                if (!scratch) { set_error("internal: workspace under-reserved (ssim)"); return FB_E_INVALID; }
+                FB_TRY(launch_ssim(c, s, ta, tb, tBytes, tBytes, tpitch, tpitch, tw, th, n, levelScores + l, L, scratch));
+                fused = true;
+            } else {
+                c->ws.off = mark;  // not applicable: give the thumbnails back, take the unfused path
+            }
+        }
+        if (!fused) {
+            FB_TRY(pipeline_ssim_fast(c, s, ca, cb, lw, lh, n, levelScores + l, L));
+            if (l + 1 < L) {
+                FB_TRY(launch_box(s, ca.p, ca.imgStride, ca.rowStride, lw, lh, (uint8_t *)na.p, na.imgStride, na.rowStride, plan[l + 1].w, plan[l + 1].h, n, nullptr));
+                FB_TRY(launch_box(s, cb.p, cb.imgStride, cb.rowStride, lw, lh, (uint8_t *)nb.p, nb.imgStride, nb.rowStride, plan[l + 1].w, plan[l + 1].h, n, nullptr));
+            }
+        }
+        ca = na;
+        cb = nb;
     }
     return launch_msssim_combine(s, levelScores, L, n, wdev, out);
 }
@@ -971,6 +1002,32 @@ int fb_box_downsample_batch_dev(int device, void *stream, const uint8_t *src, in
     FB_TRY(dev_ctx_for("fb_box_downsample_batch_dev", device, &c));
     return launch_box((cudaStream_t)stream, src, srcImgStride, srcRowStride, srcW, srcH, dst, dstImgStride,
                       dstRowStride, dstW, dstH, n, nullptr);
+}
+
+int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride,
+                              int rowStride, int w, int h, int n, uint8_t *thumbA, uint8_t *thumbB,
+                              int64_t thumbImgStride, int thumbRowStride, int tw, int th, uint8_t *halfA,
+                              uint8_t *halfB, int64_t halfImgStride, int halfRowStride) {
+    const char *fn = "fb_msssim_level_batch_dev";
+    if (w < 2 || h < 2 || tw <= 0 || th <= 0) { set_error("fb_msssim_level_batch_dev: bad dims"); return FB_E_INVALID; }
+    FB_TRY(check_batch(fn, a, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch(fn, b, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch(fn, thumbA, thumbImgStride, thumbRowStride, tw, th, n));
+    FB_TRY(check_batch(fn, thumbB, thumbImgStride, thumbRowStride, tw, th, n));
+    FB_TRY(check_batch(fn, halfA, halfImgStride, halfRowStride, w / 2, h / 2, n));
+    FB_TRY(check_batch(fn, halfB, halfImgStride, halfRowStride, w / 2, h / 2, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for(fn, device, &c));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launch_box_fused(s, a, imgStride, rowStride, b, imgStride, rowStride, w, h, thumbA, thumbB, thumbImgStride,
+                              thumbRowStride, tw, th, halfA, halfB, halfImgStride, halfRowStride, n);
+    if (rc <= 0) return rc;
+    // preconditions of the fused kernel not met: the four separate downsamples (same bytes)
+    FB_TRY(launch_box(s, a, imgStride, rowStride, w, h, thumbA, thumbImgStride, thumbRowStride, tw, th, n, nullptr));
+    FB_TRY(launch_box(s, b, imgStride, rowStride, w, h, thumbB, thumbImgStride, thumbRowStride, tw, th, n, nullptr));
+    FB_TRY(launch_box(s, a, imgStride, rowStride, w, h, halfA, halfImgStride, halfRowStride, w / 2, h / 2, n, nullptr));
+    return launch_box(s, b, imgStride, rowStride, w, h, halfB, halfImgStride, halfRowStride, w / 2, h / 2, n, nullptr);
 }
 
 int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst, int64_t imgStride,

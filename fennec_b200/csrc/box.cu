@@ -14,6 +14,9 @@
 // column sums of its box, multiplies by the reciprocal count in FP64 and writes 4 bytes.
 #include "common.cuh"
 
+#include <stdlib.h>
+#include <vector>
+
 namespace fb {
 
 namespace {
@@ -149,6 +152,108 @@ __global__ void __launch_bounds__(kThreads) box2x_kernel(const BoxParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MS-SSIM level kernel: ONE read of a level image produces both things ssim.go needs from it —
+// the SSIMFast thumbnail (boxDownsample to <= 512 px, ssim.go:57-58) and the next level's image
+// (boxDownsample to w/2 x h/2, ssim.go:354-360) — for both images of the pair batch in one launch.
+// Structure of box_rows_kernel; while a thread walks the rows of its thumbnail box it also pairs
+// every even row 2k with row 2k+1 (loading one extra row when the box ends on an even row) and
+// emits the 2x2 means of its four columns.  Each half-resolution row is produced exactly once, by
+// the box that contains its even source row.  Column groups that straddle two chunks are written
+// twice with identical bytes.  Preconditions (checked by launch_box_fused): srcW % 4 == 0,
+// srcH % 2 == 0, 16-byte aligned rows, thumbnail boxes tile the source exactly.
+// ------------------------------------------------------------------------------------------------
+struct BoxFusedParams {
+    const uint8_t *src[2];
+    uint8_t *thumb[2];
+    uint8_t *half[2];
+    long long srcImgStride[2];
+    int srcRowStride[2];
+    long long thumbImgStride, halfImgStride;
+    int thumbRowStride, halfRowStride;
+    int srcW, srcH, dstW, dstH, n;
+    double xRatio, yRatio;
+    int dxChunk, dyPerCta;
+};
+
+__device__ __forceinline__ uint2 mean2x2(const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+    uint32_t out[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t rb = (a[2 * k] & 0x00FF00FFu) + (a[2 * k + 1] & 0x00FF00FFu) + (b[2 * k] & 0x00FF00FFu) + (b[2 * k + 1] & 0x00FF00FFu);
+        const uint32_t ga = ((a[2 * k] >> 8) & 0x00FF00FFu) + ((a[2 * k + 1] >> 8) & 0x00FF00FFu) +
+                            ((b[2 * k] >> 8) & 0x00FF00FFu) + ((b[2 * k + 1] >> 8) & 0x00FF00FFu);
+        out[k] = (((rb + 0x00020002u) >> 2) & 0x00FF00FFu) | ((((ga + 0x00020002u) >> 2) & 0x00FF00FFu) << 8);
+    }
+    return make_uint2(out[0], out[1]);
+}
+
+__global__ void __launch_bounds__(kThreads) box_fused_kernel(const BoxFusedParams p) {
+    __shared__ uint2 colsum[kSpanMax + 8];
+    const int which = (int)blockIdx.z >= p.n ? 1 : 0;
+    const int img = (int)blockIdx.z - which * p.n;
+    const int rs = p.srcRowStride[which];
+    const uint8_t *s = p.src[which] + (long long)img * p.srcImgStride[which];
+    uint8_t *hd = p.half[which] + (long long)img * p.halfImgStride;
+    uint8_t *td = p.thumb[which] + (long long)img * p.thumbImgStride;
+    const int dx0 = blockIdx.x * p.dxChunk;
+    const int dx1 = min(dx0 + p.dxChunk, p.dstW);
+    const int dyEnd = min((int)(blockIdx.y + 1) * p.dyPerCta, p.dstH);
+    int sxa, sxb, tmp;
+    box_edge(dx0, p.xRatio, p.srcW, sxa, tmp);
+    box_edge(dx1 - 1, p.xRatio, p.srcW, tmp, sxb);
+    const int base = sxa & ~3;
+    const int span = sxb - base;
+    for (int dy = blockIdx.y * p.dyPerCta; dy < dyEnd; dy++) {
+        int sy0, sy1;
+        box_edge(dy, p.yRatio, p.srcH, sy0, sy1);
+        for (int c4 = threadIdx.x * 4; c4 < span; c4 += kThreads * 4) {
+            const int x = base + c4;   // x + 4 <= srcW (srcW % 4 == 0 and x < sxb <= srcW)
+            uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, prev[4] = {0, 0, 0, 0};
+            const uint8_t *q = s + (long long)sy0 * rs + (long long)x * 4;
+            uint8_t *hcol = hd + (long long)(x >> 1) * 4;
+            for (int y = sy0; y < sy1; y++, q += rs) {
+                const uint4 t = ld_nc_u128(q);
+                const uint32_t v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    lo[i] += v[i] & 0x00FF00FFu;          // R, B
+                    hi[i] += (v[i] >> 8) & 0x00FF00FFu;   // G, A
+                }
+                if (y & 1) {
+                    if (y > sy0) *reinterpret_cast<uint2 *>(hcol + (long long)(y >> 1) * p.halfRowStride) = mean2x2(prev, v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) prev[i] = v[i];
+                }
+            }
+            if (((sy1 - 1) & 1) == 0 && sy1 < p.srcH) {   // box ends on an even row: fetch its partner
+                const uint4 t = ld_nc_u128(q);
+                const uint32_t v[4] = {t.x, t.y, t.z, t.w};
+                *reinterpret_cast<uint2 *>(hcol + (long long)((sy1 - 1) >> 1) * p.halfRowStride) = mean2x2(prev, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) colsum[c4 + i] = make_uint2(lo[i], hi[i]);
+        }
+        __syncthreads();
+        const int count_y = sy1 - sy0;
+        uint8_t *drow = td + (long long)dy * p.thumbRowStride;
+        for (int dx = dx0 + threadIdx.x; dx < dx1; dx += kThreads) {
+            int sx0, sx1;
+            box_edge(dx, p.xRatio, p.srcW, sx0, sx1);
+            uint32_t sr = 0, sg = 0, sb = 0, sa = 0;
+            for (int xx = sx0; xx < sx1; xx++) {
+                uint2 c = colsum[xx - base];
+                sr += c.x & 0xFFFFu; sb += c.x >> 16;
+                sg += c.y & 0xFFFFu; sa += c.y >> 16;
+            }
+            *reinterpret_cast<uint32_t *>(drow + (long long)dx * 4) = box_finish(sr, sg, sb, sa, count_y * (sx1 - sx0));
+        }
+        __syncthreads();
+    }
+}
+
 // Generic fallback: one thread per output pixel walks its own box (upsampling, boxes taller than
 // 256 rows or wider than the shared-memory span). Same arithmetic.
 __global__ void __launch_bounds__(kThreads) box_naive_kernel(const BoxParams p) {
@@ -233,6 +338,52 @@ int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int s
         dim3 grid((dstW + kThreads - 1) / kThreads, dstH, n);
         box_naive_kernel<<<grid, kThreads, 0, s>>>(p);
     }
+    FB_LAUNCHED(1);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+}
+
+// Boxes [lo, hi) of a `src -> dst` downsample tile [0, src) exactly (contiguous, complete)?
+static bool boxes_tile(int src, int dst) {
+    std::vector<int> lo(dst), hi(dst);
+    box_edges_host(src, dst, lo.data(), hi.data());
+    if (lo[0] != 0 || hi[dst - 1] != src) return false;
+    for (int d = 0; d + 1 < dst; d++)
+        if (hi[d] != lo[d + 1] || hi[d] <= lo[d]) return false;
+    return true;
+}
+
+// Thumbnail (tw x th) + half-resolution image of both batches from one read.  Returns 1 (nothing launched)
+// when the preconditions of box_fused_kernel do not hold; the caller then uses launch_box twice per image.
+int launch_box_fused(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA,
+                     const uint8_t *srcB, long long srcImgStrideB, int srcRowStrideB, int srcW, int srcH,
+                     uint8_t *thumbA, uint8_t *thumbB, long long thumbImgStride, int thumbRowStride, int tw, int th,
+                     uint8_t *halfA, uint8_t *halfB, long long halfImgStride, int halfRowStride, int n) {
+    if (n <= 0) return FB_OK;
+    if (getenv("FB_BOX_NOFUSE") != nullptr) return 1;
+    if ((srcW & 3) || (srcH & 1) || tw < 1 || th < 1) return 1;
+    const uintptr_t al = (uintptr_t)srcA | (uintptr_t)srcB | (uintptr_t)srcImgStrideA | (uintptr_t)srcImgStrideB |
+                         (uintptr_t)srcRowStrideA | (uintptr_t)srcRowStrideB;
+    if ((al & 15) || (((uintptr_t)halfA | (uintptr_t)halfB | (uintptr_t)halfImgStride | (uintptr_t)halfRowStride) & 7)) return 1;
+    BoxFusedParams p;
+    p.src[0] = srcA; p.src[1] = srcB;
+    p.srcImgStride[0] = srcImgStrideA; p.srcImgStride[1] = srcImgStrideB;
+    p.srcRowStride[0] = srcRowStrideA; p.srcRowStride[1] = srcRowStrideB;
+    p.thumb[0] = thumbA; p.thumb[1] = thumbB; p.thumbImgStride = thumbImgStride; p.thumbRowStride = thumbRowStride;
+    p.half[0] = halfA; p.half[1] = halfB; p.halfImgStride = halfImgStride; p.halfRowStride = halfRowStride;
+    p.srcW = srcW; p.srcH = srcH; p.dstW = tw; p.dstH = th; p.n = n;
+    p.xRatio = (double)srcW / (double)tw;
+    p.yRatio = (double)srcH / (double)th;
+    const int maxBoxW = (int)p.xRatio + 2, maxBoxH = (int)p.yRatio + 2;
+    if (!(p.xRatio >= 1.0 && p.yRatio >= 1.0 && maxBoxH <= 256 && maxBoxW <= kSpanMax / 2)) return 1;
+    if (!boxes_tile(srcW, tw) || !boxes_tile(srcH, th)) return 1;
+    int chunk = (int)((double)(kSpanMax - maxBoxW - 4) / p.xRatio);
+    if (chunk < 1) chunk = 1;
+    if (chunk > tw) chunk = tw;
+    p.dxChunk = chunk;
+    p.dyPerCta = maxBoxH >= 32 ? 1 : (32 / maxBoxH < 1 ? 1 : 32 / maxBoxH);
+    dim3 grid((tw + chunk - 1) / chunk, (th + p.dyPerCta - 1) / p.dyPerCta, 2 * n);
+    box_fused_kernel<<<grid, kThreads, 0, s>>>(p);
     FB_LAUNCHED(1);
     FB_CUDA(cudaGetLastError());
     return FB_OK;

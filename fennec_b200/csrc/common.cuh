@@ -87,6 +87,11 @@ int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int s
                int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
                const int *reserved);
 void box_edges_host(int src, int dst, int *lo, int *hi);
+// MS-SSIM level step: thumbnail + half-resolution image of both batches from one read; returns 1 when not applicable.
+int launch_box_fused(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA,
+                     const uint8_t *srcB, long long srcImgStrideB, int srcRowStrideB, int srcW, int srcH,
+                     uint8_t *thumbA, uint8_t *thumbB, long long thumbImgStride, int thumbRowStride, int tw, int th,
+                     uint8_t *halfA, uint8_t *halfB, long long halfImgStride, int halfRowStride, int n);
 
 // effects.cu
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,

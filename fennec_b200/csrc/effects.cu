@@ -245,52 +245,75 @@ __global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
     }
 }
 
+// Vertical pass: a thread owns one column and walks down a segment of kVSeg rows in chunks of kTile
+// outputs.  Its window of kTile + 2R packed pixels slides in registers (2R rows are carried over to the next
+// chunk) and the kTile new rows of the NEXT chunk are loaded before the current chunk's taps are evaluated, so
+// the loads are hidden behind ~300 FFMA2s and every tmp row is read 1 + 2R/kVSeg times instead of
+// 1 + 2R/kTile.  Alpha: the horizontal pass has already copied the source alpha into tmp (effects.go:189), so the
+// centre tap carries exactly the byte effects.go:215 copies — the original image is not read again.
+constexpr int kVSeg = 240;  // rows per thread segment (2160 = 9 * 240; halo 12/240)
+
 template <int R>
 __global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
     constexpr int NIN = kTile + 2 * R;
     __shared__ uint32_t dump[128 * (NIN + 1)];  // per-thread tap dump for the exact path (+1: bank spread)
     const int x = blockIdx.x * 128 + threadIdx.x, img = blockIdx.z;
-    const int y0 = blockIdx.y * kTile;
+    const int ys = blockIdx.y * kVSeg;
+    const int yEnd = min(ys + kVSeg, p.h);
     if (x >= p.w) return;
     const uint8_t *scol = p.src + (long long)img * p.srcImgStride + (long long)x * 4;
-    uint32_t raw[NIN];
-#pragma unroll
-    for (int i = 0; i < NIN; i++) {
-        int sy = min(max(y0 - R + i, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
-        raw[i] = __ldg(reinterpret_cast<const uint32_t *>(scol + (long long)sy * p.srcRowStride));
-    }
-    const uint8_t *acol = p.alpha + (long long)img * p.alphaImgStride + (long long)x * 4;
-    float2 acc[kTile / 2][3];
-    blur_taps_fp32<R, NIN, R>(raw, p.kernel32, acc);
-    const float lim = 0.5f - p.eps;
     uint8_t *dcol = p.dst + (long long)img * p.dstImgStride + (long long)x * 4;
-    uint32_t ambMask = 0;
+    const float lim = 0.5f - p.eps;
+    auto ld_row = [&](int y) -> uint32_t {
+        const int sy = min(max(y, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
+        return __ldg(reinterpret_cast<const uint32_t *>(scol + (long long)sy * p.srcRowStride));
+    };
+    uint32_t raw[NIN], nxt[kTile];
 #pragma unroll
-    for (int j = 0; j < kTile; j++) {
-        const int y = y0 + j;
-        if (y < p.h) {
-            bool a0, a1, a2;
-            const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
-            const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
-            const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
-            uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
-            if (a0 | a1 | a2) ambMask |= 1u << j;
-            // (hoisting these 16 alpha loads above the tap loop was measured slower: +16 registers cost occupancy)
-            uint32_t a = ld_nc_u32(acol + (long long)y * p.alphaRowStride) & 0xFF000000u;  // effects.go:215
-            *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = r | (g << 8) | (b << 16) | a;
+    for (int i = 0; i < NIN; i++) raw[i] = ld_row(ys - R + i);
+#pragma unroll 1
+    for (int y0 = ys; y0 < yEnd; y0 += kTile) {
+        const bool more = y0 + kTile < yEnd;
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < kTile; i++) nxt[i] = ld_row(y0 + kTile + R + i);
         }
-    }
-    if (ambMask) {  // rare: dump this thread's taps to shared memory and redo the flagged outputs exactly
-        uint32_t *mine = dump + threadIdx.x * (NIN + 1);
+        float2 acc[kTile / 2][3];
+        blur_taps_fp32<R, NIN, R>(raw, p.kernel32, acc);
+        uint32_t ambMask = 0;
 #pragma unroll
-        for (int i = 0; i < NIN; i++) mine[i] = raw[i];
-        while (ambMask) {
-            const int j = __ffs(ambMask) - 1;
-            ambMask &= ambMask - 1;
+        for (int j = 0; j < kTile; j++) {
             const int y = y0 + j;
-            uint32_t e = blur_exact_taps(mine + j, 1, 2 * R + 1, p.kernel);
-            uint32_t a = ld_nc_u32(acol + (long long)y * p.alphaRowStride) & 0xFF000000u;
-            *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = e | a;
+            if (y < yEnd) {
+                bool a0, a1, a2;
+                const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
+                const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
+                const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
+                uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
+                if (a0 | a1 | a2) ambMask |= 1u << j;
+                *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) =
+                    r | (g << 8) | (b << 16) | (raw[R + j] & 0xFF000000u);
+            }
+        }
+        if (ambMask) {  // rare: dump this thread's taps to shared memory and redo the flagged outputs exactly
+            uint32_t *mine = dump + threadIdx.x * (NIN + 1);
+#pragma unroll
+            for (int i = 0; i < NIN; i++) mine[i] = raw[i];
+            while (ambMask) {
+                const int j = __ffs(ambMask) - 1;
+                ambMask &= ambMask - 1;
+                const int y = y0 + j;
+                if (y < yEnd) {
+                    uint32_t e = blur_exact_taps(mine + j, 1, 2 * R + 1, p.kernel);
+                    *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = e | (mine[R + j] & 0xFF000000u);
+                }
+            }
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < 2 * R; i++) raw[i] = raw[i + kTile];
+#pragma unroll
+            for (int i = 0; i < kTile; i++) raw[2 * R + i] = nxt[i];
         }
     }
 }
@@ -301,7 +324,7 @@ static void launch_blur_fast(cudaStream_t s, BlurParams p, int n, bool vertical)
         dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + 3) / 4, n);
         blur_h_fast_kernel<R><<<grid, 128, 0, s>>>(p);
     } else {
-        dim3 grid((p.w + 127) / 128, (p.h + kTile - 1) / kTile, n);
+        dim3 grid((p.w + 127) / 128, (p.h + kVSeg - 1) / kVSeg, n);
         blur_v_fast_kernel<R><<<grid, 128, 0, s>>>(p);
     }
 }
@@ -480,18 +503,34 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
         }
     };
 
+    // MODE 2 fast path: integer lumas x1000 (299R + 587G + 114B, exact) of the three live rows
+    auto lumas = [&](const uint32_t (&px)[6], int (&L)[6]) {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            L[i] = (int)__dp2a_lo(299u | (587u << 16), px[i], __dp2a_hi(114u, px[i], 0u));
+    };
+    const float amountF = (float)p.amount;
+
     uint32_t pPrev[6], pCur[6], pNext[6];
     uint32_t hPrevRB[4], hPrevGA[4], hCurRB[4], hCurGA[4], hNextRB[4], hNextGA[4];
+    int lPrev[6], lCur[6], lNext[6];
     load_row(yb - 1, pPrev);
     load_row(yb, pCur);
     hsum(pPrev, hPrevRB, hPrevGA);
     hsum(pCur, hCurRB, hCurGA);
+    if (MODE == 2) { lumas(pPrev, lPrev); lumas(pCur, lCur); }
 #pragma unroll 1
     for (int r = 0; r < kFxRows; r++) {
         const int y = yb + r;
         if (y >= p.h) break;
         load_row(y + 1, pNext);
         hsum(pNext, hNextRB, hNextGA);
+        int colsum[6];
+        if (MODE == 2) {
+            lumas(pNext, lNext);
+#pragma unroll
+            for (int i = 0; i < 6; i++) colsum[i] = lPrev[i] + 2 * lCur[i] + lNext[i];
+        }
         uint32_t out[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -507,6 +546,42 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
                 if (MODE == 0) {
                     res = (uint32_t)bl[0] | ((uint32_t)bl[1] << 8) | ((uint32_t)bl[2] << 16) | (c & 0xFF000000u);
                 } else {
+                    bool needExact = true;
+                    uint32_t o[3];
+                    if (MODE == 2) {
+                        // FP32 evaluation with a rigorous error bound; only results within the bound of a rounding
+                        // boundary take the exact FP64 sequence below.  GX, GY are the Sobel sums of the integer lumas
+                        // (units of 1/1000; |G| <= 1.02e6 < 2^22 so the magic-number conversion is exact; the reference's
+                        // FP64 gx, gy differ from G/1000 by ~1e-12).  Relative error of edge <= 2^-22 (g2: 2^-23, IEEE
+                        // sqrt: halves it + 2^-24, x fl(1/400000): 2^-23), of la*diff <= 3.5 * 2^-23, |la*diff| <= 765;
+                        // the final add rounds once more (<= 1020 * 2^-24).  eps = |t| * 5.3e-7 + 8e-5 has 25 % margin.
+                        const int GX = colsum[i + 2] - colsum[i];
+                        const int GY = (lNext[i] + 2 * lNext[i + 1] + lNext[i + 2]) - (lPrev[i] + 2 * lPrev[i + 1] + lPrev[i + 2]);
+                        const float gxf = __int_as_float(GX + 0x4B400000) - 12582912.0f;
+                        const float gyf = __int_as_float(GY + 0x4B400000) - 12582912.0f;
+                        const float g2f = fmaf(gxf, gxf, gyf * gyf);
+                        const float edgeF = fminf(__fsqrt_rn(g2f) * 2.5e-6f, 1.0f);
+                        const float la = amountF * edgeF;
+                        bool amb = false;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++) {
+                            const int orig = (int)((c >> (8 * ch)) & 0xFF);
+                            const int diff = orig - bl[ch];
+                            const float of = __int_as_float(orig + 0x4B400000) - 12582912.0f;
+                            const float df = __int_as_float(diff + 0x4B400000) - 12582912.0f;
+                            const float t = la * df;
+                            float v = of + t;
+                            const float lim = 0.5f - fmaf(fabsf(t), 5.3e-7f, 8e-5f);
+                            v = fminf(fmaxf(v, -1.0f), 256.0f);
+                            const float tt = v + 12582912.0f;
+                            const float rounded = tt - 12582912.0f;
+                            amb |= fabsf(v - rounded) >= lim;
+                            const int iv = (int)(__float_as_uint(tt) & 0x7FFFFFu) - 0x400000;
+                            o[ch] = (uint32_t)min(max(iv, 0), 255);
+                        }
+                        needExact = amb;
+                    }
+                    if (needExact) {
                     double amount = p.amount;
                     if (MODE == 2) {  // localEdgeStrength (effects.go:93-112), expression order preserved
                         const uint32_t n[9] = {pPrev[i], pPrev[i + 1], pPrev[i + 2], pCur[i], c, pCur[i + 2],
@@ -537,7 +612,6 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
                         }
                         amount = __dmul_rn(p.amount, edge);  // effects.go:74
                     }
-                    uint32_t o[3];
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++) {
                         const int orig = (int)((c >> (8 * ch)) & 0xFF);
@@ -550,6 +624,7 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
                             double val = __dadd_rn(small_int_to_double(orig), __dmul_rn(amount, small_int_to_double(diff)));
                             o[ch] = clampf_magic(val);  // effects.go:37-38 / 82-83
                         }
+                    }
                     }
                     res = o[0] | (o[1] << 8) | (o[2] << 16) | (c & 0xFF000000u);
                 }
@@ -566,6 +641,10 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) { pPrev[i] = pCur[i]; pCur[i] = pNext[i]; }
+        if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) { lPrev[i] = lCur[i]; lCur[i] = lNext[i]; }
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) { hPrevRB[i] = hCurRB[i]; hPrevGA[i] = hCurGA[i]; hCurRB[i] = hNextRB[i]; hCurGA[i] = hNextGA[i]; }
     }

@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) resize_pass_fast_kernel(const ResizeParam
 // Integer-ratio kernel (srcSize == R * dstSize; config 4 is R = 4).  Every interior destination index d
 // then has the same T taps at source R*d + off with the SAME weights (verified on the host), so a thread
 // can produce kOut adjacent outputs from one window of T + (kOut-1)*R pixels with compile-time tap
-// indices: every byte is converted once and feeds up to kOut outputs (FFMA2 on output pairs with the
-// weight pairs (w[t], w[t-R])).  Windows that are fully opaque (alpha == 255 everywhere) skip the
+// indices: every byte is converted once and feeds up to kOut outputs (FFMA2 on the (R,G) and (B,A) channel
+// pairs with the tap weight as a broadcast scalar).  Windows that are fully opaque (alpha == 255 everywhere) skip the
 // premultiplication: v = sum(R*w) / sum(w).  Edge outputs and windows with any translucent pixel take the
 // general path per output.  Ambiguous results go to the block-compacted exact FP64 path as above.
 // ------------------------------------------------------------------------------------------------
@@ -305,65 +305,59 @@ __global__ void __launch_bounds__(128) resize_int_ratio_kernel(const IntRatioPar
             uint32_t andA = 0xFFFFFFFFu;
 #pragma unroll
             for (int i = 0; i < NIN; i++) andA &= raw[i];
+            // Channel-paired accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar
+            // (w[t] straight from the parameter bank) and B (and alpha) ride in a second accumulator.  [An earlier
+            // version paired two OUTPUTS per FFMA2, which needs the weight pairs (w[t], w[t-R]) in registers: ptxas
+            // rebuilt every pair with two MOVs per FFMA2 — 3x the instructions, profiles/r1b_*.]
+            const float2 kMagic2 = make_float2(-8388608.0f, -8388608.0f);
             if ((andA >> 24) == 0xFFu) {  // fully opaque window: v = sum(R*w) / sum(w)
-                float2 acc[kOut / 2][3];
+                float2 accRG[kOut];
+                float accB[kOut];
 #pragma unroll
-                for (int m = 0; m < kOut / 2; m++) acc[m][0] = acc[m][1] = acc[m][2] = make_float2(0.f, 0.f);
+                for (int j = 0; j < kOut; j++) { accRG[j] = make_float2(0.f, 0.f); accB[j] = 0.f; }
 #pragma unroll
                 for (int i = 0; i < NIN; i++) {
-                    const float f0 = byte_f(raw[i], 0), f1 = byte_f(raw[i], 1), f2 = byte_f(raw[i], 2);
-                    const float2 f00 = make_float2(f0, f0), f11 = make_float2(f1, f1), f22 = make_float2(f2, f2);
+                    const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
+                                                             __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
+                    const float bl = byte_f(raw[i], 2);
 #pragma unroll
-                    for (int m = 0; m < kOut / 2; m++) {
-                        const int t = i - 2 * m * R;  // tap of input i for output 2m; output 2m+1 uses t - R
-                        const bool v0 = t >= 0 && t < T, v1 = t - R >= 0 && t - R < T;
-                        if (v0 || v1) {
-                            const float2 wp = make_float2(v0 ? q.w[v0 ? t : 0] : 0.f, v1 ? q.w[v1 ? t - R : 0] : 0.f);
-                            acc[m][0] = __ffma2_rn(f00, wp, acc[m][0]);
-                            acc[m][1] = __ffma2_rn(f11, wp, acc[m][1]);
-                            acc[m][2] = __ffma2_rn(f22, wp, acc[m][2]);
+                    for (int j = 0; j < kOut; j++) {
+                        const int t = i - j * R;  // tap of input i for output j
+                        if (t >= 0 && t < T) {
+                            const float w = q.w[t >= 0 && t < T ? t : 0];
+                            accRG[j] = __ffma2_rn(rg, make_float2(w, w), accRG[j]);
+                            accB[j] = fmaf(bl, w, accB[j]);
                         }
                     }
                 }
                 const float a = 255.f * q.wsum;
 #pragma unroll
-                for (int j = 0; j < kOut; j++) {
-                    const float r = 255.f * ((j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x);
-                    const float g = 255.f * ((j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x);
-                    const float b = 255.f * ((j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x);
-                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
-                }
+                for (int j = 0; j < kOut; j++)
+                    outv[j] = finish_fp32(255.f * accRG[j].x, 255.f * accRG[j].y, 255.f * accB[j], a, p.Er, p.Ea, ambv[j]);
             } else {  // translucent window: premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
-                float2 acc[kOut / 2][4];
+                float2 accRG[kOut], accBA[kOut];
 #pragma unroll
-                for (int m = 0; m < kOut / 2; m++) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = make_float2(0.f, 0.f);
+                for (int j = 0; j < kOut; j++) accRG[j] = accBA[j] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < NIN; i++) {
                     const float fa = byte_f(raw[i], 3);
-                    const float f0 = byte_f(raw[i], 0) * fa, f1 = byte_f(raw[i], 1) * fa, f2 = byte_f(raw[i], 2) * fa;
-                    const float2 f00 = make_float2(f0, f0), f11 = make_float2(f1, f1), f22 = make_float2(f2, f2),
-                                 faa = make_float2(fa, fa);
+                    const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
+                                                             __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
+                    const float2 prg = __fmul2_rn(rg, make_float2(fa, fa));
+                    const float2 pba = make_float2(byte_f(raw[i], 2) * fa, fa);
 #pragma unroll
-                    for (int m = 0; m < kOut / 2; m++) {
-                        const int t = i - 2 * m * R;
-                        const bool v0 = t >= 0 && t < T, v1 = t - R >= 0 && t - R < T;
-                        if (v0 || v1) {
-                            const float2 wp = make_float2(v0 ? q.w[v0 ? t : 0] : 0.f, v1 ? q.w[v1 ? t - R : 0] : 0.f);
-                            acc[m][0] = __ffma2_rn(f00, wp, acc[m][0]);
-                            acc[m][1] = __ffma2_rn(f11, wp, acc[m][1]);
-                            acc[m][2] = __ffma2_rn(f22, wp, acc[m][2]);
-                            acc[m][3] = __ffma2_rn(faa, wp, acc[m][3]);
+                    for (int j = 0; j < kOut; j++) {
+                        const int t = i - j * R;
+                        if (t >= 0 && t < T) {
+                            const float w = q.w[t >= 0 && t < T ? t : 0];
+                            accRG[j] = __ffma2_rn(prg, make_float2(w, w), accRG[j]);
+                            accBA[j] = __ffma2_rn(pba, make_float2(w, w), accBA[j]);
                         }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < kOut; j++) {
-                    const float r = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
-                    const float g = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
-                    const float b = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
-                    const float a = (j & 1) ? acc[j / 2][3].y : acc[j / 2][3].x;
-                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
-                }
+                for (int j = 0; j < kOut; j++)
+                    outv[j] = finish_fp32(accRG[j].x, accRG[j].y, accBA[j].x, accBA[j].y, p.Er, p.Ea, ambv[j]);
             }
             done = true;
         }

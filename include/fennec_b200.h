@@ -133,6 +133,13 @@ FB_API int fb_msssim_batch_dev(int device, void *stream, const uint8_t *a, const
 FB_API int fb_box_downsample_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride,
                                 int srcRowStride, int srcW, int srcH, uint8_t *dst, int64_t dstImgStride,
                                 int dstRowStride, int dstW, int dstH, int n);
+/* One MS-SSIM level step for both images of every pair (ssim.go:57-58 + 354-360): the SSIMFast thumbnail
+ * (tw x th, from fb_ssim_fast_dims) AND the next level's image (w/2 x h/2) from a single read of the level
+ * image. fb_msssim_batch_dev uses this internally; it is exported so the bytes can be checked directly. */
+FB_API int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride,
+                              int rowStride, int w, int h, int n, uint8_t *thumbA, uint8_t *thumbB,
+                              int64_t thumbImgStride, int thumbRowStride, int tw, int th, uint8_t *halfA,
+                              uint8_t *halfB, int64_t halfImgStride, int halfRowStride);
 FB_API int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst,
                                int64_t imgStride, int rowStride, int w, int h, int n,
                                const double *kernel_host, int radius);

@@ -279,3 +279,50 @@ def test_sharded_scores_gather_in_order(lib):
         lo, hi = batch.shard_range(6, 2, r)
         parts.append(batch.ssim_batch(pairs_a[lo:hi], pairs_b[lo:hi]).cpu())
     assert torch.equal(torch.cat(parts), full)
+
+
+# ---- round-1b kernels: fused MS-SSIM level step, sliding-window blur V pass, AdaptiveSharpen FP32 + exact fallback ----
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1300, 700), (1028, 770), (2048, 1152), (1302, 700)])
+def test_msssim_level_step_bit_exact(w, h, lib, oracle):
+    """Thumbnail + half-resolution image from one read (box.cu: box_fused_kernel) == two boxDownsample calls.
+    1302 is not a multiple of 4 → the entry point takes the unfused path; bytes must not change."""
+    imgs_a = [S.noise_image(w, h, 40 + i, alpha="random") for i in range(2)]
+    imgs_b = [S.gradient_noise_image(w, h, 50 + i) for i in range(2)]
+    ok, tw, th = api.ssim_fast_dims(w, h)
+    assert ok
+    lib.fb_take_launch_count()
+    ta, tb, ha, hb = batch.msssim_level_batch(_to_dev(imgs_a), _to_dev(imgs_b), tw, th)
+    launches = lib.fb_take_launch_count()
+    assert launches == (1 if w % 4 == 0 and h % 2 == 0 else 4)
+    for got_t, got_h, imgs in ((ta, ha, imgs_a), (tb, hb, imgs_b)):
+        for i, img in enumerate(imgs):
+            assert np.array_equal(got_t[i].cpu().numpy(), oracle.box_downsample(img, tw, th))
+            assert np.array_equal(got_h[i].cpu().numpy(), oracle.box_downsample(img, w // 2, h // 2))
+
+
+def test_msssim_multi_level_vs_oracle(lib, oracle):
+    # 2048x1152: levels 0 and 1 take the fused step (1024x576 still > 512), level 2 (512x288) scores directly
+    a = S.gradient_noise_image(2048, 1152, 61)
+    b = S.perturb(a, 62, 9)
+    assert abs(api.MSSSIM(a, b) - oracle.msssim(a, b)) <= SCORE_TIGHT
+
+
+@pytest.mark.parametrize("w,h,sigma", [(300, 700, 2.0), (130, 500, 1.0), (257, 241, 2.66), (64, 239, 2.0), (640, 480, 0.5)])
+def test_blur_tall_images_bit_exact(w, h, sigma, lib, oracle):
+    """The vertical pass walks 240-row segments with a sliding register window: cover segment seams,
+    partial last chunks and the clamp-to-edge rows at both ends."""
+    src = S.noise_image(w, h, w + h, alpha="random")
+    assert np.array_equal(api.GaussianBlur(src, sigma), oracle.gaussian_blur(src, sigma))
+
+
+@pytest.mark.parametrize("strength", [0.5, 0.3, 0.77, 1.0, 3.0])
+@pytest.mark.parametrize("kind", ["noise", "grad", "stripes"])
+def test_adaptive_sharpen_fast_path_bit_exact(kind, strength, lib, oracle):
+    if kind == "noise":
+        src = S.noise_image(640, 360, 71, alpha="random")
+    elif kind == "grad":
+        src = S.gradient_noise_image(640, 360, 72)
+    else:
+        src = S.make_striped_image(640, 360, 7)
+    assert np.array_equal(api.AdaptiveSharpen(src, strength), oracle.adaptive_sharpen(src, strength))
