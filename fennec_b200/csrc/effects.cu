@@ -160,88 +160,120 @@ __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const
     }
 }
 
+constexpr int kHRows = 8;  // rows one warp walks in the horizontal pass (double-buffered staging)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Horizontal pass: a warp owns 512 output pixels of a row (16 per lane) and walks kHRows consecutive rows; row
+// y+1 is staged into the warp's second shared-memory buffer with cp.async while row y is evaluated, so the
+// global-load latency is paid once per warp instead of once per row.  No block-wide barrier.
 template <int R>
 __global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
-    __shared__ __align__(16) uint8_t stage[4][34 * kChunkB];
+    __shared__ __align__(16) uint8_t stage[4][2][34 * kChunkB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int y = blockIdx.y * 4 + warp, img = blockIdx.z;
-    if (y >= p.h) return;  // warp-uniform; no block barrier below
+    const int yBeg = (blockIdx.y * 4 + warp) * kHRows, img = blockIdx.z;
+    const int yEnd = min(yBeg + kHRows, p.h);
+    if (yBeg >= p.h) return;  // warp-uniform; no block barrier below
     const int xs = blockIdx.x * (32 * kTile);
-    const uint8_t *srow = p.src + (long long)img * p.srcImgStride + (long long)y * p.srcRowStride;
-    uint8_t *st = stage[warp];
+    const uint8_t *simg = p.src + (long long)img * p.srcImgStride;
     const bool vecOK = ((((uintptr_t)p.src | (uintptr_t)p.srcImgStride | (uintptr_t)p.srcRowStride) & 15) == 0);
-    // stage chunks -1..32 (34 chunks of 16 px) with clamp-to-edge (effects.go:173-178)
-    for (int v = lane; v < 34 * 4; v += 32) {
-        const int chunk = v >> 2, quad = v & 3;
-        const int px0 = xs + (chunk - 1) * kTile + quad * 4;
-        uint4 q;
-        if (vecOK && px0 >= 0 && px0 + 3 < p.w) {
-            q = *reinterpret_cast<const uint4 *>(srow + (long long)px0 * 4);
-        } else {
-            uint32_t t[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                int sx = min(max(px0 + i, 0), p.w - 1);
-                t[i] = ld_nc_u32(srow + (long long)sx * 4);
-            }
-            q = make_uint4(t[0], t[1], t[2], t[3]);
-        }
-        *reinterpret_cast<uint4 *>(st + chunk * kChunkB + quad * 16) = q;
-    }
-    __syncwarp();
-    const int x0 = xs + lane * kTile;
-    if (x0 >= p.w) return;
-    // window: px x0-8 .. x0+23  =  stage chunks lane (second half), lane+1 (all), lane+2 (first half)
-    uint32_t raw[32];
-#pragma unroll
-    for (int v = 0; v < 8; v++) {
-        const int i0 = v * 4 + 8;  // px index relative to the start of stage chunk `lane`
-        uint4 q = *reinterpret_cast<const uint4 *>(st + (lane + i0 / kTile) * kChunkB + (i0 % kTile) * 4);
-        raw[v * 4 + 0] = q.x; raw[v * 4 + 1] = q.y; raw[v * 4 + 2] = q.z; raw[v * 4 + 3] = q.w;
-    }
-    float2 acc[kTile / 2][3];
-    blur_taps_fp32<R, 32, 8>(raw, p.kernel32, acc);
-    const float lim = 0.5f - p.eps;
-    uint32_t out[kTile];
-    uint32_t ambMask = 0;
-#pragma unroll
-    for (int j = 0; j < kTile; j++) {
-        bool a0, a1, a2;
-        const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
-        const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
-        const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
-        uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
-        out[j] = r | (g << 8) | (b << 16) | (raw[8 + j] & 0xFF000000u);  // alpha from the source (effects.go:189)
-        if (a0 | a1 | a2) ambMask |= 1u << j;
-    }
-    uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
     const bool dvec = ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0);
-    if (dvec && x0 + kTile <= p.w) {
+    // stage chunks -1..32 (34 chunks of 16 px) of row y with clamp-to-edge (effects.go:173-178)
+    auto stage_row = [&](int y, uint8_t *st) {
+        const uint8_t *srow = simg + (long long)y * p.srcRowStride;
 #pragma unroll
-        for (int v = 0; v < 4; v++)
-            *reinterpret_cast<uint4 *>(drow + v * 16) = make_uint4(out[v * 4], out[v * 4 + 1], out[v * 4 + 2], out[v * 4 + 3]);
-    } else {
+        for (int k = 0; k < (34 * 4 + 31) / 32; k++) {
+            const int v = lane + 32 * k;
+            if (v < 34 * 4) {
+                const int chunk = v >> 2, quad = v & 3;
+                const int px0 = xs + (chunk - 1) * kTile + quad * 4;
+                uint8_t *dstp = st + chunk * kChunkB + quad * 16;
+                if (vecOK && px0 >= 0 && px0 + 3 < p.w) {
+                    cp_async16(dstp, srow + (long long)px0 * 4);
+                } else {
+                    uint32_t t[4];
 #pragma unroll
-        for (int j = 0; j < kTile; j++)
-            if (x0 + j < p.w) *reinterpret_cast<uint32_t *>(drow + j * 4) = out[j];
-    }
-    // Ambiguous outputs: exact FP64 sequence from the staged bytes, overwriting the pixel just stored
-    // (same thread, program order).  Taps of output j start at stage pixel 16*lane + 16 + j - R.
-    const uint32_t *stw = reinterpret_cast<const uint32_t *>(st);
-    while (ambMask) {
-        const int j = __ffs(ambMask) - 1;
-        ambMask &= ambMask - 1;
-        if (x0 + j < p.w) {
-            uint32_t taps[2 * R + 1];
-#pragma unroll
-            for (int k = 0; k <= 2 * R; k++) {
-                const int sp = 16 * lane + 16 + j - R + k;  // stage pixel index
-                taps[k] = stw[(sp >> 4) * (kChunkB / 4) + (sp & 15)];
+                    for (int i = 0; i < 4; i++) {
+                        int sx = min(max(px0 + i, 0), p.w - 1);
+                        t[i] = ld_nc_u32(srow + (long long)sx * 4);
+                    }
+                    *reinterpret_cast<uint4 *>(dstp) = make_uint4(t[0], t[1], t[2], t[3]);
+                }
             }
-            uint32_t e = blur_exact_taps(taps, 1, 2 * R + 1, p.kernel);
-            uint32_t alpha = stw[((16 * lane + 16 + j) >> 4) * (kChunkB / 4) + ((16 * lane + 16 + j) & 15)] & 0xFF000000u;
-            *reinterpret_cast<uint32_t *>(drow + j * 4) = e | alpha;
         }
+        cp_async_commit_group();
+    };
+    stage_row(yBeg, stage[warp][0]);
+    const int x0 = xs + lane * kTile;
+    const float lim = 0.5f - p.eps;
+#pragma unroll 1
+    for (int y = yBeg; y < yEnd; y++) {
+        uint8_t *st = stage[warp][(y - yBeg) & 1];
+        if (y + 1 < yEnd) {
+            stage_row(y + 1, stage[warp][(y + 1 - yBeg) & 1]);
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
+        }
+        __syncwarp();
+        if (x0 < p.w) {
+            // window: px x0-8 .. x0+23  =  stage chunks lane (second half), lane+1 (all), lane+2 (first half)
+            uint32_t raw[32];
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                const int i0 = v * 4 + 8;  // px index relative to the start of stage chunk `lane`
+                uint4 q = *reinterpret_cast<const uint4 *>(st + (lane + i0 / kTile) * kChunkB + (i0 % kTile) * 4);
+                raw[v * 4 + 0] = q.x; raw[v * 4 + 1] = q.y; raw[v * 4 + 2] = q.z; raw[v * 4 + 3] = q.w;
+            }
+            float2 acc[kTile / 2][3];
+            blur_taps_fp32<R, 32, 8>(raw, p.kernel32, acc);
+            uint32_t out[kTile];
+            uint32_t ambMask = 0;
+#pragma unroll
+            for (int j = 0; j < kTile; j++) {
+                bool a0, a1, a2;
+                const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
+                const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
+                const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
+                uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
+                out[j] = r | (g << 8) | (b << 16) | (raw[8 + j] & 0xFF000000u);  // alpha from the source (effects.go:189)
+                if (a0 | a1 | a2) ambMask |= 1u << j;
+            }
+            uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
+            if (dvec && x0 + kTile <= p.w) {
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    *reinterpret_cast<uint4 *>(drow + v * 16) = make_uint4(out[v * 4], out[v * 4 + 1], out[v * 4 + 2], out[v * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kTile; j++)
+                    if (x0 + j < p.w) *reinterpret_cast<uint32_t *>(drow + j * 4) = out[j];
+            }
+            // Ambiguous outputs: exact FP64 sequence from the staged bytes, overwriting the pixel just stored
+            // (same thread, program order).  Taps of output j start at stage pixel 16*lane + 16 + j - R.
+            const uint32_t *stw = reinterpret_cast<const uint32_t *>(st);
+            while (ambMask) {
+                const int j = __ffs(ambMask) - 1;
+                ambMask &= ambMask - 1;
+                if (x0 + j < p.w) {
+                    uint32_t taps[2 * R + 1];
+#pragma unroll
+                    for (int k = 0; k <= 2 * R; k++) {
+                        const int sp = 16 * lane + 16 + j - R + k;  // stage pixel index
+                        taps[k] = stw[(sp >> 4) * (kChunkB / 4) + (sp & 15)];
+                    }
+                    uint32_t e = blur_exact_taps(taps, 1, 2 * R + 1, p.kernel);
+                    uint32_t alpha = stw[((16 * lane + 16 + j) >> 4) * (kChunkB / 4) + ((16 * lane + 16 + j) & 15)] & 0xFF000000u;
+                    *reinterpret_cast<uint32_t *>(drow + j * 4) = e | alpha;
+                }
+            }
+        }
+        __syncwarp();  // every lane is done with `st` before it is restaged two rows later
     }
 }
 
@@ -321,7 +353,7 @@ __global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
 template <int R>
 static void launch_blur_fast(cudaStream_t s, BlurParams p, int n, bool vertical) {
     if (!vertical) {
-        dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + 3) / 4, n);
+        dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + 4 * kHRows - 1) / (4 * kHRows), n);
         blur_h_fast_kernel<R><<<grid, 128, 0, s>>>(p);
     } else {
         dim3 grid((p.w + 127) / 128, (p.h + kVSeg - 1) / kVSeg, n);

@@ -238,60 +238,221 @@ struct IntRatioParams {
     float w[28];    // the T shared weights (T <= 24 used)
 };
 
-template <bool VERTICAL, int R, int T>
-__global__ void __launch_bounds__(128) resize_int_ratio_kernel(const IntRatioParams q) {
-    constexpr int NIN = T + (kOut - 1) * R;          // window of one thread
-    constexpr int SPAN = R * kOut * 128 + T - R;      // source pixels one block's row segment needs (horizontal)
-    constexpr int CHUNKS = (SPAN + 15) / 16 + 2;
-    constexpr int CHB = 80;                           // 16-px chunk + 16 B pad: conflict-free LDS.128 at 1 chunk / thread
-    static_assert(R * kOut == 16 || VERTICAL, "horizontal staging assumes one 16-px chunk per thread");
+constexpr int kRowsPerBlock = 8;  // horizontal pass: rows one block walks (double-buffered staging)
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// kOut interior outputs from one window of packed pixels (compile-time tap indices).
+template <int R, int T>
+__device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[T + (kOut - 1) * R], const IntRatioParams &q,
+                                                 uint32_t (&outv)[kOut], bool (&ambv)[kOut]) {
+    constexpr int NIN = T + (kOut - 1) * R;
+    const ResizeParams &p = q.base;
+    uint32_t andA = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NIN; i++) andA &= raw[i];
+    // Channel-paired accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar
+    // (w[t] straight from the parameter bank) and B (and alpha) ride in a second accumulator.  [An earlier
+    // version paired two OUTPUTS per FFMA2, which needs the weight pairs (w[t], w[t-R]) in registers: ptxas
+    // rebuilt every pair with two MOVs per FFMA2 — 3x the instructions, profiles/r1b_*.]
+    const float2 kMagic2 = make_float2(-8388608.0f, -8388608.0f);
+    if ((andA >> 24) == 0xFFu) {  // fully opaque window: v = sum(R*w) / sum(w)
+        float2 accRG[kOut];
+        float accB[kOut];
+#pragma unroll
+        for (int j = 0; j < kOut; j++) { accRG[j] = make_float2(0.f, 0.f); accB[j] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < NIN; i++) {
+            const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
+                                                     __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
+            const float bl = byte_f(raw[i], 2);
+#pragma unroll
+            for (int j = 0; j < kOut; j++) {
+                const int t = i - j * R;  // tap of input i for output j
+                if (t >= 0 && t < T) {
+                    const float w = q.w[t >= 0 && t < T ? t : 0];
+                    accRG[j] = __ffma2_rn(rg, make_float2(w, w), accRG[j]);
+                    accB[j] = fmaf(bl, w, accB[j]);
+                }
+            }
+        }
+        const float a = 255.f * q.wsum;
+#pragma unroll
+        for (int j = 0; j < kOut; j++)
+            outv[j] = finish_fp32(255.f * accRG[j].x, 255.f * accRG[j].y, 255.f * accB[j], a, p.Er, p.Ea, ambv[j]);
+    } else {  // translucent window: premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
+        float2 accRG[kOut], accBA[kOut];
+#pragma unroll
+        for (int j = 0; j < kOut; j++) accRG[j] = accBA[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NIN; i++) {
+            const float fa = byte_f(raw[i], 3);
+            const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
+                                                     __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
+            const float2 prg = __fmul2_rn(rg, make_float2(fa, fa));
+            const float2 pba = make_float2(byte_f(raw[i], 2) * fa, fa);
+#pragma unroll
+            for (int j = 0; j < kOut; j++) {
+                const int t = i - j * R;
+                if (t >= 0 && t < T) {
+                    const float w = q.w[t >= 0 && t < T ? t : 0];
+                    accRG[j] = __ffma2_rn(prg, make_float2(w, w), accRG[j]);
+                    accBA[j] = __ffma2_rn(pba, make_float2(w, w), accBA[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kOut; j++)
+            outv[j] = finish_fp32(accRG[j].x, accRG[j].y, accBA[j].x, accBA[j].y, p.Er, p.Ea, ambv[j]);
+    }
+}
+
+// Vertical pass: thread = column x, kOut adjacent rows; the window is NIN independent global loads (each a
+// coalesced 128-byte row segment per warp).  Edge rows (clipped / renormalised taps) take the general tables.
+template <int R, int T>
+__global__ void __launch_bounds__(128) resize_v_int_ratio_kernel(const IntRatioParams q) {
+    constexpr int NIN = T + (kOut - 1) * R;
     const ResizeParams &p = q.base;
     __shared__ int nAmb;
     __shared__ unsigned short ambList[128 * kOut];
-    __shared__ __align__(16) uint8_t stage[VERTICAL ? 16 : CHUNKS * CHB];
     if (threadIdx.x == 0) nAmb = 0;
-    // HORIZONTAL: thread = kOut adjacent output columns of row y.  VERTICAL: thread = column x, kOut adjacent rows.
     const int img = blockIdx.z;
-    const int tix = blockIdx.x * blockDim.x + threadIdx.x;
-    const int x0 = VERTICAL ? tix : tix * kOut;
-    const int y0 = VERTICAL ? blockIdx.y * kOut : blockIdx.y;
+    const int x0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y0 = blockIdx.y * kOut;
     const uint8_t *s = p.src + (long long)img * p.srcImgStride;
     uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
-    const int d0 = VERTICAL ? y0 : x0;
-    const int nd = VERTICAL ? p.outH : p.outW;
-    const bool inRange = VERTICAL ? (x0 < p.outW && y0 < p.outH) : (x0 < p.outW);
-    if (!VERTICAL) {
-        // Stage the block's source span with coalesced 64-bit loads (the span starts at an even pixel: R*d+off
-        // with R*kOut == 16 and even off), zero outside the row.  Staging pixel u <-> source pixel sBase + u.
-        const int sBase = R * (blockIdx.x * blockDim.x * kOut) + q.off;
-        const uint8_t *row = s + (long long)y0 * p.srcRowStride;
-        const bool al8 = (((uintptr_t)row + (long long)sBase * 4) & 7) == 0;
-        for (int u = threadIdx.x * 2; u < SPAN + 1; u += 256) {
-            const int sx = sBase + u;
-            uint2 v = make_uint2(0u, 0u);
-            if (al8 && sx >= 0 && sx + 1 < p.srcW) v = __ldg(reinterpret_cast<const uint2 *>(row + (long long)sx * 4));
-            else {
-                if (sx >= 0 && sx < p.srcW) v.x = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)sx * 4));
-                if (sx + 1 >= 0 && sx + 1 < p.srcW) v.y = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(sx + 1) * 4));
+    __syncthreads();
+    if (x0 < p.outW && y0 < p.outH) {
+        uint32_t outv[kOut];
+        bool ambv[kOut];
+        if (y0 >= q.dLo && y0 + kOut <= q.dHi) {
+            uint32_t raw[NIN];
+            const int s0 = R * y0 + q.off;  // first source row of the window
+#pragma unroll
+            for (int i = 0; i < NIN; i++)
+                raw[i] = __ldg(reinterpret_cast<const uint32_t *>(s + (long long)(s0 + i) * p.srcRowStride + (long long)x0 * 4));
+            int_ratio_window<R, T>(raw, q, outv, ambv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kOut; j++) {
+                ambv[j] = false;
+                outv[j] = 0u;
+                if (y0 + j < p.outH) {
+                    float r, g, b, a;
+                    general_sums<true, false>(p, s, x0, y0 + j, r, g, b, a);
+                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
+                }
             }
-            *reinterpret_cast<uint2 *>(stage + (u >> 4) * CHB + (u & 15) * 4) = v;
+        }
+#pragma unroll
+        for (int j = 0; j < kOut; j++) {
+            if (y0 + j < p.outH) {
+                if (ambv[j]) ambList[atomicAdd(&nAmb, 1)] = (unsigned short)(threadIdx.x * kOut + j);
+                else *reinterpret_cast<uint32_t *>(dimg + (long long)(y0 + j) * p.dstRowStride + (long long)x0 * 4) = outv[j];
+            }
         }
     }
     __syncthreads();
-    if (inRange) {
-        uint32_t outv[kOut];
-        bool ambv[kOut];
-        bool done = false;
-        if (d0 >= q.dLo && d0 + kOut <= q.dHi) {
-            uint32_t raw[NIN];
-            if (VERTICAL) {
-                const int s0 = R * d0 + q.off;  // first source row of the window
+    const int n = nAmb;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int lt = ambList[e] / kOut, j = ambList[e] % kOut;
+        const int ox = blockIdx.x * blockDim.x + lt, oy = y0 + j;
+        exact_px<true>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
+    }
+}
+
+// Horizontal pass: thread = kOut adjacent output columns; a block walks kRowsPerBlock rows of a 512-output column
+// segment.  Row y+1 is staged into the second shared-memory buffer with cp.async while row y is evaluated (the
+// first version staged one row with a load->store loop and paid the DRAM latency ~8 times per block: half of
+// its stall samples, profiles/r1b_*).  Ambiguous outputs AND the few edge outputs (clipped taps) are only
+// queued; the queue is drained by all 128 threads after the last row (or when it could overflow), so the
+// FP64 path runs with packed warps and the row loop has a single barrier.
+constexpr int kAmbCap = 2048;
+
+template <int R, int T>
+__global__ void __launch_bounds__(128) resize_h_int_ratio_kernel(const IntRatioParams q) {
+    constexpr int NIN = T + (kOut - 1) * R;          // window of one thread
+    constexpr int SPAN = R * kOut * 128 + T - R;      // source pixels one block's row segment needs
+    constexpr int CHUNKS = (SPAN + 15) / 16 + 2;
+    constexpr int CHB = 80;                           // 16-px chunk + 16 B pad: conflict-free LDS.128 at 1 chunk / thread
+    constexpr int STAGEB = CHUNKS * CHB;
+    constexpr int NLD = (SPAN + 1 + 255) / 256;       // 64-bit staging copies per thread
+    static_assert(R * kOut == 16, "staging assumes one 16-px chunk per thread");
+    const ResizeParams &p = q.base;
+    __shared__ int nAmb, flush;
+    __shared__ unsigned short ambList[kAmbCap];       // (row - yFirst) * 512 + thread * kOut + j
+    __shared__ __align__(16) uint8_t stage[2 * STAGEB];
+    if (threadIdx.x == 0) { nAmb = 0; flush = 0; }
+    const int img = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * kOut;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
+    const int yFirst = blockIdx.y * kRowsPerBlock;
+    const int yLast = min(yFirst + kRowsPerBlock, p.outH);  // exclusive
+    // Staging pixel u <-> source pixel sBase + u (sBase is even: R*kOut == 16 and even off); zero outside the row.
+    const int sBase = R * (blockIdx.x * blockDim.x * kOut) + q.off;
+    const bool interiorSpan = sBase >= 0 && sBase + SPAN + 2 <= p.srcW &&
+                              (((uintptr_t)s + (long long)sBase * 4) & 7) == 0 && (p.srcRowStride & 7) == 0;
+    auto stage_row = [&](int y, uint8_t *buf) {
+        const uint8_t *row = s + (long long)y * p.srcRowStride;
+        if (interiorSpan) {   // block-uniform: every copy is in range and 8-byte aligned
 #pragma unroll
-                for (int i = 0; i < NIN; i++)
-                    raw[i] = __ldg(reinterpret_cast<const uint32_t *>(s + (long long)(s0 + i) * p.srcRowStride + (long long)x0 * 4));
-            } else {
+            for (int k = 0; k < NLD; k++) {
+                const int u = threadIdx.x * 2 + k * 256;
+                if (k < NLD - 1 || u < SPAN + 1) cp_async8(buf + (u >> 4) * CHB + (u & 15) * 4, row + (long long)(sBase + u) * 4);
+            }
+        } else {
+            for (int u = threadIdx.x * 2; u < SPAN + 1; u += 256) {
+                const int sx = sBase + u;
+                uint2 v = make_uint2(0u, 0u);
+                if (sx >= 0 && sx < p.srcW) v.x = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)sx * 4));
+                if (sx + 1 >= 0 && sx + 1 < p.srcW) v.y = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(sx + 1) * 4));
+                *reinterpret_cast<uint2 *>(buf + (u >> 4) * CHB + (u & 15) * 4) = v;
+            }
+        }
+        cp_async_commit_group();
+    };
+    auto drain = [&]() {  // all threads; callers put barriers around it
+        const int n = nAmb;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int code = ambList[e];
+            const int oy = yFirst + (code >> 9), ox = blockIdx.x * (128 * kOut) + (code & 511);
+            exact_px<false>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
+        }
+    };
+    stage_row(yFirst, stage);
+#pragma unroll 1
+    for (int y0 = yFirst; y0 < yLast; y0++) {
+        const uint8_t *buf = stage + ((y0 - yFirst) & 1) * STAGEB;
+        if (y0 + 1 < yLast) {
+            stage_row(y0 + 1, stage + ((y0 + 1 - yFirst) & 1) * STAGEB);
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
+        }
+        // thread 0's view of the queue may miss pushes of the previous row that are still in flight (<= 512), and
+        // this row can add 512 more: ask for a drain while 1024 slots are still free.
+        if (threadIdx.x == 0) flush = nAmb > kAmbCap - 1024;
+        __syncthreads();  // row y0 is staged and visible; every push of rows < y0 is complete
+        if (flush) {      // block-uniform, rare
+            drain();
+            __syncthreads();
+            if (threadIdx.x == 0) nAmb = 0;
+            __syncthreads();
+        }
+        if (x0 < p.outW) {
+            uint32_t outv[kOut];
+            bool ambv[kOut];
+            const int rowCode = (y0 - yFirst) << 9;
+            if (x0 >= q.dLo && x0 + kOut <= q.dHi) {
+                uint32_t raw[NIN];
                 // window = staging pixels 16*t .. 16*t + NIN - 1: chunks t, t+1, t+2
-                const uint8_t *wbase = stage + threadIdx.x * CHB;
+                const uint8_t *wbase = buf + threadIdx.x * CHB;
 #pragma unroll
                 for (int v4 = 0; v4 < (NIN + 3) / 4; v4++) {
                     const int u = v4 * 4;
@@ -301,96 +462,22 @@ __global__ void __launch_bounds__(128) resize_int_ratio_kernel(const IntRatioPar
                     if (u + 2 < NIN) raw[u + 2] = t4.z;
                     if (u + 3 < NIN) raw[u + 3] = t4.w;
                 }
+                int_ratio_window<R, T>(raw, q, outv, ambv);
+            } else {  // edge outputs (clipped / renormalised taps): straight to the exact queue
+#pragma unroll
+                for (int j = 0; j < kOut; j++) { ambv[j] = true; outv[j] = 0u; }
             }
-            uint32_t andA = 0xFFFFFFFFu;
-#pragma unroll
-            for (int i = 0; i < NIN; i++) andA &= raw[i];
-            // Channel-paired accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar
-            // (w[t] straight from the parameter bank) and B (and alpha) ride in a second accumulator.  [An earlier
-            // version paired two OUTPUTS per FFMA2, which needs the weight pairs (w[t], w[t-R]) in registers: ptxas
-            // rebuilt every pair with two MOVs per FFMA2 — 3x the instructions, profiles/r1b_*.]
-            const float2 kMagic2 = make_float2(-8388608.0f, -8388608.0f);
-            if ((andA >> 24) == 0xFFu) {  // fully opaque window: v = sum(R*w) / sum(w)
-                float2 accRG[kOut];
-                float accB[kOut];
-#pragma unroll
-                for (int j = 0; j < kOut; j++) { accRG[j] = make_float2(0.f, 0.f); accB[j] = 0.f; }
-#pragma unroll
-                for (int i = 0; i < NIN; i++) {
-                    const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
-                                                             __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
-                    const float bl = byte_f(raw[i], 2);
-#pragma unroll
-                    for (int j = 0; j < kOut; j++) {
-                        const int t = i - j * R;  // tap of input i for output j
-                        if (t >= 0 && t < T) {
-                            const float w = q.w[t >= 0 && t < T ? t : 0];
-                            accRG[j] = __ffma2_rn(rg, make_float2(w, w), accRG[j]);
-                            accB[j] = fmaf(bl, w, accB[j]);
-                        }
-                    }
-                }
-                const float a = 255.f * q.wsum;
-#pragma unroll
-                for (int j = 0; j < kOut; j++)
-                    outv[j] = finish_fp32(255.f * accRG[j].x, 255.f * accRG[j].y, 255.f * accB[j], a, p.Er, p.Ea, ambv[j]);
-            } else {  // translucent window: premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
-                float2 accRG[kOut], accBA[kOut];
-#pragma unroll
-                for (int j = 0; j < kOut; j++) accRG[j] = accBA[j] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < NIN; i++) {
-                    const float fa = byte_f(raw[i], 3);
-                    const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
-                                                             __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
-                    const float2 prg = __fmul2_rn(rg, make_float2(fa, fa));
-                    const float2 pba = make_float2(byte_f(raw[i], 2) * fa, fa);
-#pragma unroll
-                    for (int j = 0; j < kOut; j++) {
-                        const int t = i - j * R;
-                        if (t >= 0 && t < T) {
-                            const float w = q.w[t >= 0 && t < T ? t : 0];
-                            accRG[j] = __ffma2_rn(prg, make_float2(w, w), accRG[j]);
-                            accBA[j] = __ffma2_rn(pba, make_float2(w, w), accBA[j]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kOut; j++)
-                    outv[j] = finish_fp32(accRG[j].x, accRG[j].y, accBA[j].x, accBA[j].y, p.Er, p.Ea, ambv[j]);
-            }
-            done = true;
-        }
-        if (!done) {  // edge outputs (clipped / renormalised taps): general tables, one output at a time
 #pragma unroll
             for (int j = 0; j < kOut; j++) {
-                ambv[j] = false;
-                outv[j] = 0u;
-                if (d0 + j < nd) {
-                    float r, g, b, a;
-                    if (VERTICAL) general_sums<true, false>(p, s, x0, y0 + j, r, g, b, a);
-                    else general_sums<false, true>(p, s, x0 + j, y0, r, g, b, a);
-                    outv[j] = finish_fp32(r, g, b, a, p.Er, p.Ea, ambv[j]);
+                if (x0 + j < p.outW) {
+                    if (ambv[j]) ambList[atomicAdd(&nAmb, 1)] = (unsigned short)(rowCode + threadIdx.x * kOut + j);
+                    else *reinterpret_cast<uint32_t *>(dimg + (long long)y0 * p.dstRowStride + (long long)(x0 + j) * 4) = outv[j];
                 }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kOut; j++) {
-            if (d0 + j < nd) {
-                const int ox = VERTICAL ? x0 : x0 + j, oy = VERTICAL ? y0 + j : y0;
-                if (ambv[j]) ambList[atomicAdd(&nAmb, 1)] = (unsigned short)(threadIdx.x * kOut + j);
-                else *reinterpret_cast<uint32_t *>(dimg + (long long)oy * p.dstRowStride + (long long)ox * 4) = outv[j];
             }
         }
     }
     __syncthreads();
-    const int n = nAmb;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const int lt = ambList[e] / kOut, j = ambList[e] % kOut;
-        const int t2 = blockIdx.x * blockDim.x + lt;
-        const int ox = VERTICAL ? t2 : t2 * kOut + j, oy = VERTICAL ? blockIdx.y * kOut + j : blockIdx.y;
-        exact_px<VERTICAL>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
-    }
+    drain();
 }
 
 template <bool VERTICAL>
@@ -420,11 +507,12 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
         q.base = p; q.off = ir->off; q.dLo = ir->dLo; q.dHi = ir->dHi; q.wsum = ir->wsum;
         for (int i = 0; i < 28; i++) q.w[i] = i < ir->taps ? ir->w[i] : 0.f;
         dim3 g2 = VERTICAL ? dim3((outW + 127) / 128, (outH + kOut - 1) / kOut, n)
-                           : dim3(((outW + kOut - 1) / kOut + 127) / 128, outH, n);
+                           : dim3(((outW + kOut - 1) / kOut + 127) / 128, (outH + kRowsPerBlock - 1) / kRowsPerBlock, n);
         bool launched = true;
-        if (ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_int_ratio_kernel<VERTICAL, 4, 24><<<g2, 128, 0, s>>>(q);
-        else if (VERTICAL && ir->ratio == 2 && ir->taps == 12) resize_int_ratio_kernel<true, 2, 12><<<g2, 128, 0, s>>>(q);
-        else if (VERTICAL && ir->ratio == 3 && ir->taps == 17) resize_int_ratio_kernel<true, 3, 17><<<g2, 128, 0, s>>>(q);
+        if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_h_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
+        else if (VERTICAL && ir->ratio == 4 && ir->taps == 24) resize_v_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
+        else if (VERTICAL && ir->ratio == 2 && ir->taps == 12) resize_v_int_ratio_kernel<2, 12><<<g2, 128, 0, s>>>(q);
+        else if (VERTICAL && ir->ratio == 3 && ir->taps == 17) resize_v_int_ratio_kernel<3, 17><<<g2, 128, 0, s>>>(q);
         else launched = false;
         if (launched) {
             FB_LAUNCHED(1);
