@@ -53,6 +53,15 @@ PROTOTYPES = {
     "fb_lanczos_resize": (C.c_int, _IMG + [C.c_int, C.c_int] + _IMG + [C.c_int, C.c_int,
                                                                         C.POINTER(FbWeights), C.POINTER(FbWeights)]),
     "fb_smart_resize_dims": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]),
+    "fb_ycbcr_to_nrgba": (C.c_int, [u8p, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]),
+    "fb_gray_to_nrgba": (C.c_int, [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]),
+    "fb_ssim_ref_create": (C.c_int, _IMG + [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fb_ssim_ref_score_ycbcr": (C.c_int, [C.c_void_p, u8p, C.c_int, u8p, u8p, C.c_int, C.c_int, dp]),
+    "fb_ssim_ref_score_nrgba": (C.c_int, [C.c_void_p] + _IMG + [dp]),
+    "fb_ssim_ref_destroy": (None, [C.c_void_p]),
+    "fb_ycbcr_to_nrgba_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                              C.c_int]),
     "fb_ssim_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_ssim_fast_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_msssim_batch_dev": (C.c_int, _BATCH_SCORE),

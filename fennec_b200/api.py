@@ -209,3 +209,92 @@ def Sharpen(img: np.ndarray, strength: float) -> np.ndarray:
 def AdaptiveSharpen(img: np.ndarray, strength: float) -> np.ndarray:
     """fennec.AdaptiveSharpen (effects.go:49-90)."""
     return _fx(_lib.load().fb_adaptive_sharpen, img, strength)
+
+
+# ---- convert.go:34-64 (SURVEY §8 f1) and the quality search's reference session (compress.go:45-74) ------
+
+# image.YCbCrSubsampleRatio constants, in Go's order
+YCBCR_444, YCBCR_422, YCBCR_420, YCBCR_440, YCBCR_411, YCBCR_410 = range(6)
+_SUBSAMPLE = {0: (1, 1), 1: (2, 1), 2: (2, 2), 3: (1, 2), 4: (4, 1), 5: (4, 2)}
+
+
+def chroma_dims(w: int, h: int, ratio: int) -> Tuple[int, int]:
+    """Plane size image.NewYCbCr allocates for a (0,0)-(w,h) rectangle."""
+    dx, dy = _SUBSAMPLE[ratio]
+    return (w + dx - 1) // dx, (h + dy - 1) // dy
+
+
+def _plane(a: np.ndarray):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.ndim == 2 and (a.size == 0 or a.strides[1] == 1)):
+        raise TypeError("expected a 2-D uint8 plane with contiguous rows")
+    return a.ctypes.data_as(u8p), (int(a.strides[0]) if a.shape[0] > 1 else a.shape[1])
+
+
+def ycbcr_to_nrgba(y: np.ndarray, cb: np.ndarray, cr: np.ndarray, ratio: int) -> np.ndarray:
+    """convertToNRGBA (convert.go:34-64) of a decoded *image.YCbCr (Y, Cb, Cr planes + subsample ratio)."""
+    h, w = y.shape
+    if cb.shape != cr.shape or cb.strides != cr.strides:
+        raise ValueError("Cb and Cr must share shape and stride (image.YCbCr.CStride)")
+    dst = _new(h, w)
+    py, sy = _plane(y)
+    pcb, sc = _plane(cb)
+    pcr, _ = _plane(cr)
+    pd, sd, _, _ = _img(dst)
+    check(_lib.load().fb_ycbcr_to_nrgba(py, sy, pcb, pcr, sc, w, h, ratio, pd, sd))
+    return dst
+
+
+def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
+    """convertToNRGBA (convert.go:34-64) of a decoded *image.Gray."""
+    h, w = g.shape
+    dst = _new(h, w)
+    pg, sg = _plane(g)
+    pd, sd, _, _ = _img(dst)
+    check(_lib.load().fb_gray_to_nrgba(pg, sg, w, h, pd, sd))
+    return dst
+
+
+class SSIMReference:
+    """The `src` side of compress.go:45-74's search, kept on the device: SSIMFast(src, candidate) per iteration
+    with only the candidate crossing PCIe (as YCbCr planes or NRGBA)."""
+
+    def __init__(self, src: np.ndarray):
+        p, stride, w, h = _img(src)
+        self._h = C.c_void_p()
+        self.w, self.h = w, h
+        check(_lib.load().fb_ssim_ref_create(p, stride, w, h, C.byref(self._h)))
+
+    def score_ycbcr(self, y: np.ndarray, cb: np.ndarray, cr: np.ndarray, ratio: int) -> float:
+        if y.shape != (self.h, self.w):
+            raise ValueError("candidate dims differ from the reference image")
+        py, sy = _plane(y)
+        pcb, sc = _plane(cb)
+        pcr, _ = _plane(cr)
+        out = C.c_double()
+        check(_lib.load().fb_ssim_ref_score_ycbcr(self._h, py, sy, pcb, pcr, sc, ratio, C.byref(out)))
+        return out.value
+
+    def score_nrgba(self, img: np.ndarray) -> float:
+        p, stride, w, h = _img(img)
+        if (w, h) != (self.w, self.h):
+            raise ValueError("candidate dims differ from the reference image")
+        out = C.c_double()
+        check(_lib.load().fb_ssim_ref_score_nrgba(self._h, p, stride, C.byref(out)))
+        return out.value
+
+    def close(self) -> None:
+        if self._h:
+            _lib.load().fb_ssim_ref_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -83,6 +83,24 @@ def msssim_level_batch(a: torch.Tensor, b: torch.Tensor, tw: int, th: int):
     return thumbs[0], thumbs[1], halves[0], halves[1]
 
 
+def ycbcr_to_nrgba_batch(y: torch.Tensor, cb: torch.Tensor, cr: torch.Tensor, ratio: int,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """convertToNRGBA (convert.go:34-64) for n device-resident YCbCr images: y (n,h,w), cb/cr (n,ch,cw), uint8."""
+    for t in (y, cb, cr):
+        if not (t.is_cuda and t.dtype == torch.uint8 and t.dim() == 3 and t.stride(2) == 1):
+            raise TypeError("expected CUDA uint8 planes of shape (n, rows, cols)")
+    if cb.shape != cr.shape or cb.stride() != cr.stride():
+        raise ValueError("Cb and Cr must share shape and strides")
+    n, h, w = y.shape
+    if out is None:
+        out = torch.empty((n, h, w, 4), dtype=torch.uint8, device=y.device)
+    pd, i_d, rd, _, _, _ = _batch(out)
+    check(_lib.load().fb_ycbcr_to_nrgba_batch_dev(_dev(y), _stream(y), y.data_ptr(), int(y.stride(0)), int(y.stride(1)),
+                                                  cb.data_ptr(), cr.data_ptr(), int(cb.stride(0)), int(cb.stride(1)), w, h,
+                                                  ratio, pd, i_d, rd, n))
+    return out
+
+
 def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Tensor] = None,
                         kernel: Optional[np.ndarray] = None) -> torch.Tensor:
     """fennec.GaussianBlur per image (effects.go:146-220); sigma <= 0 returns `src` itself."""

@@ -1117,3 +1117,184 @@ int fb_batch_shard(int n_items, int n_shards, int shard, int *begin, int *end) {
 }
 
 }  // extern "C"
+
+namespace fb {
+
+// ---- convertToNRGBA on decoded images, and the search loop's reference-image session ----
+
+static int check_planes(const char *fn, const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride,
+                        int w, int h, int ratio, int *cw, int *ch) {
+    int xs, ys;
+    if (!ycbcr_ratio_shifts(ratio, &xs, &ys)) { set_error("%s: unknown subsample ratio %d", fn, ratio); return FB_E_INVALID; }
+    if (w <= 0 || h <= 0) { set_error("%s: bad dims %dx%d", fn, w, h); return FB_E_INVALID; }
+    *cw = (w + (1 << xs) - 1) >> xs;
+    *ch = (h + (1 << ys) - 1) >> ys;
+    if (!y || !cb || !cr) { set_error("%s: null plane pointer", fn); return FB_E_INVALID; }
+    if (yStride < w || cStride < *cw) { set_error("%s: plane stride too small (y %d < %d or c %d < %d)", fn, yStride, w, cStride, *cw); return FB_E_INVALID; }
+    return FB_OK;
+}
+
+// Upload the three planes into the workspace and convert; *out is a workspace NRGBA image of pitch *pitch.
+static int ycbcr_upload_convert(DevCtx *c, const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride,
+                                int w, int h, int ratio, int cw, int ch, uint8_t **out, int *pitch) {
+    const int yp = (int)align_up((size_t)w, 16), cp = (int)align_up((size_t)cw, 16);
+    uint8_t *dy = (uint8_t *)c->ws.take((size_t)yp * h);
+    uint8_t *dcb = (uint8_t *)c->ws.take((size_t)cp * ch);
+    uint8_t *dcr = (uint8_t *)c->ws.take((size_t)cp * ch);
+    *pitch = dev_pitch(w);
+    *out = (uint8_t *)c->ws.take((size_t)*pitch * h + 16);
+    if (!dy || !dcb || !dcr || !*out) { set_error("internal: workspace under-reserved (ycbcr)"); return FB_E_INVALID; }
+    FB_CUDA(cudaMemcpy2DAsync(dy, yp, y, yStride, (size_t)w, h, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpy2DAsync(dcb, cp, cb, cStride, (size_t)cw, ch, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaMemcpy2DAsync(dcr, cp, cr, cStride, (size_t)cw, ch, cudaMemcpyHostToDevice, c->stream));
+    return launch_ycbcr_to_nrgba(c->stream, dy, 0, yp, dcb, dcr, 0, cp, w, h, ratio, *out, 0, *pitch, 1);
+}
+
+static size_t ycbcr_scratch(int w, int h, int cw, int ch) {
+    return align_up((size_t)w, 16) * h + 2 * align_up((size_t)cw, 16) * ch + (size_t)dev_pitch(w) * h + 4096;
+}
+
+}  // namespace fb
+
+struct fb_ssim_ref {
+    int dev, w, h;       // device and dims of the reference image
+    int tw, th, pitch;   // what is kept: the SSIMFast thumbnail (or the image itself when <= 512 px)
+    uint8_t *img;        // cudaMalloc'ed, owned
+};
+
+namespace fb {
+
+// SSIMFast(ref, img) with ref's downsample cached: box `img` if needed, then K1 (ssim.go:48-70).
+static int score_against_ref(DevCtx *c, const fb_ssim_ref *r, const uint8_t *dimg, int pitch, double *out) {
+    const uint8_t *b = dimg;
+    int bp = pitch;
+    if (r->tw != r->w || r->th != r->h) {
+        int tp = dev_pitch(r->tw);
+        uint8_t *t = (uint8_t *)c->ws.take((size_t)tp * r->th + 16);
+        if (!t) { set_error("internal: workspace under-reserved (ref thumb)"); return FB_E_INVALID; }
+        FB_TRY(launch_box(c->stream, dimg, 0, pitch, r->w, r->h, t, 0, tp, r->tw, r->th, 1, nullptr));
+        b = t;
+        bp = tp;
+    }
+    double *dscore = (double *)c->ws.take(sizeof(double) * 2);
+    void *scratch = c->ws.take(ssim_scratch_bytes(r->tw, r->th, 1));
+    if (!dscore || !scratch) { set_error("internal: workspace under-reserved (ref score)"); return FB_E_INVALID; }
+    FB_TRY(launch_ssim(c, c->stream, r->img, b, 0, 0, r->pitch, bp, r->tw, r->th, 1, dscore, 1, scratch));
+    return finish_score(c, dscore, out);
+}
+
+static size_t ref_score_scratch(const fb_ssim_ref *r) {
+    return (size_t)dev_pitch(r->tw) * r->th + ssim_scratch_bytes(r->tw, r->th, 1) + 4096;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride, int w, int h,
+                      int ratio, uint8_t *dst, int dstStride) {
+    int cw, ch;
+    FB_TRY(check_planes("fb_ycbcr_to_nrgba", y, yStride, cb, cr, cStride, w, h, ratio, &cw, &ch));
+    FB_TRY(check_img("fb_ycbcr_to_nrgba", dst, dstStride, w, h));
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    FB_TRY(reserve(c, ycbcr_scratch(w, h, cw, ch), 256));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(ycbcr_upload_convert(c, y, yStride, cb, cr, cStride, w, h, ratio, cw, ch, &d, &pitch));
+    FB_TRY(download(c, d, pitch, dst, dstStride, w, h));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride) {
+    if (w <= 0 || h <= 0 || !g || gStride < w) { set_error("fb_gray_to_nrgba: bad plane"); return FB_E_INVALID; }
+    FB_TRY(check_img("fb_gray_to_nrgba", dst, dstStride, w, h));
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    const int gp = (int)align_up((size_t)w, 16), pitch = dev_pitch(w);
+    FB_TRY(reserve(c, (size_t)gp * h + (size_t)pitch * h + 4096, 256));
+    uint8_t *dg = (uint8_t *)c->ws.take((size_t)gp * h);
+    uint8_t *d = (uint8_t *)c->ws.take((size_t)pitch * h + 16);
+    FB_CUDA(cudaMemcpy2DAsync(dg, gp, g, gStride, (size_t)w, h, cudaMemcpyHostToDevice, c->stream));
+    FB_TRY(launch_gray_to_nrgba(c->stream, dg, 0, gp, w, h, d, 0, pitch, 1));
+    FB_TRY(download(c, d, pitch, dst, dstStride, w, h));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_ycbcr_to_nrgba_batch_dev(int device, void *stream, const uint8_t *y, int64_t yImgStride, int yStride,
+                                const uint8_t *cb, const uint8_t *cr, int64_t cImgStride, int cStride, int w, int h,
+                                int ratio, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int n) {
+    int cw, ch;
+    FB_TRY(check_planes("fb_ycbcr_to_nrgba_batch_dev", y, yStride, cb, cr, cStride, w, h, ratio, &cw, &ch));
+    FB_TRY(check_batch("fb_ycbcr_to_nrgba_batch_dev", dst, dstImgStride, dstRowStride, w, h, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_ycbcr_to_nrgba_batch_dev", device, &c));
+    return launch_ycbcr_to_nrgba((cudaStream_t)stream, y, yImgStride, yStride, cb, cr, cImgStride, cStride, w, h, ratio, dst,
+                                 dstImgStride, dstRowStride, n);
+}
+
+int fb_ssim_ref_create(const uint8_t *src, int stride, int w, int h, fb_ssim_ref **out) {
+    if (!out) { set_error("fb_ssim_ref_create: null output"); return FB_E_INVALID; }
+    *out = nullptr;
+    FB_TRY(check_img("fb_ssim_ref_create", src, stride, w, h));
+    if (w <= 0 || h <= 0) { set_error("fb_ssim_ref_create: empty image"); return FB_E_INVALID; }
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    fb_ssim_ref r;
+    r.dev = c->dev; r.w = w; r.h = h; r.tw = w; r.th = h;
+    const bool down = ssim_fast_dims(w, h, &r.tw, &r.th) != 0;
+    r.pitch = dev_pitch(r.tw);
+    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h + 4096, 256));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(upload(c, src, stride, w, h, &d, &pitch));
+    void *own = nullptr;
+    cudaError_t e = cudaMalloc(&own, (size_t)r.pitch * r.th + 16);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("fb_ssim_ref_create: cudaMalloc failed"); return FB_E_OOM; }
+    r.img = (uint8_t *)own;
+    int rc = down ? launch_box(c->stream, d, 0, pitch, w, h, r.img, 0, r.pitch, r.tw, r.th, 1, nullptr)
+                  : (cudaMemcpy2DAsync(r.img, r.pitch, d, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess ? FB_OK : FB_E_CUDA);
+    if (rc == FB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = FB_E_CUDA;
+    if (rc != FB_OK) { cudaFree(own); if (rc == FB_E_CUDA) set_error("fb_ssim_ref_create: CUDA failure"); return rc; }
+    *out = new fb_ssim_ref(r);
+    return FB_OK;
+}
+
+void fb_ssim_ref_destroy(fb_ssim_ref *ref) {
+    if (!ref) return;
+    if (DevCtx *c = ctx(ref->dev)) { (void)c; cudaFree(ref->img); }
+    delete ref;
+}
+
+int fb_ssim_ref_score_nrgba(const fb_ssim_ref *ref, const uint8_t *img, int stride, double *score) {
+    if (!ref || !score) { set_error("fb_ssim_ref_score_nrgba: null argument"); return FB_E_INVALID; }
+    FB_TRY(check_img("fb_ssim_ref_score_nrgba", img, stride, ref->w, ref->h));
+    DevCtx *c = ctx(ref->dev);
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    FB_TRY(reserve(c, (size_t)dev_pitch(ref->w) * ref->h + ref_score_scratch(ref) + 4096, 256));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(upload(c, img, stride, ref->w, ref->h, &d, &pitch));
+    return score_against_ref(c, ref, d, pitch, score);
+}
+
+int fb_ssim_ref_score_ycbcr(const fb_ssim_ref *ref, const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr,
+                            int cStride, int ratio, double *score) {
+    if (!ref || !score) { set_error("fb_ssim_ref_score_ycbcr: null argument"); return FB_E_INVALID; }
+    int cw, ch;
+    FB_TRY(check_planes("fb_ssim_ref_score_ycbcr", y, yStride, cb, cr, cStride, ref->w, ref->h, ratio, &cw, &ch));
+    DevCtx *c = ctx(ref->dev);
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    FB_TRY(reserve(c, ycbcr_scratch(ref->w, ref->h, cw, ch) + ref_score_scratch(ref), 256));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(ycbcr_upload_convert(c, y, yStride, cb, cr, cStride, ref->w, ref->h, ratio, cw, ch, &d, &pitch));
+    return score_against_ref(c, ref, d, pitch, score);
+}
+
+}  // extern "C"

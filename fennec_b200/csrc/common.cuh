@@ -103,6 +103,14 @@ int launch_blur3x3(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long i
 int launch_sharpen(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride, int rowStride,
                    int w, int h, int n, long long dstImgStride, int dstRowStride, double amount, int adaptive);
 
+// ycbcr.cu — SURVEY §8(f1): convertToNRGBA (convert.go:34-64) for decoded *image.YCbCr / *image.Gray
+bool ycbcr_ratio_shifts(int ratio, int *xShift, int *yShift);
+int launch_ycbcr_to_nrgba(cudaStream_t s, const uint8_t *y, long long yImgStride, int yStride, const uint8_t *cb,
+                          const uint8_t *cr, long long cImgStride, int cStride, int w, int h, int ratio, uint8_t *dst,
+                          long long dstImgStride, int dstRowStride, int n);
+int launch_gray_to_nrgba(cudaStream_t s, const uint8_t *g, long long gImgStride, int gStride, int w, int h, uint8_t *dst,
+                         long long dstImgStride, int dstRowStride, int n);
+
 // resize.cu
 // When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.
 struct IntRatioInfo {

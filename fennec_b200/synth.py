@@ -111,3 +111,38 @@ def checker_flat_image(w: int, h: int, block: int, lo: int, hi: int, seed: int) 
     img[..., :3] = np.clip(level[..., None] + d, 0, 255).astype(np.uint8)
     img[..., 3] = 255
     return img
+
+
+_SUBSAMPLE = {0: (1, 1), 1: (2, 1), 2: (2, 2), 3: (1, 2), 4: (4, 1), 5: (4, 2)}  # image.YCbCrSubsampleRatio -> (dx, dy)
+
+
+def ycbcr_planes_from_nrgba(img: np.ndarray, ratio: int, seed: int = 0, amp: int = 0):
+    """A deterministic stand-in for "encode then jpeg.Decode": JFIF forward transform (float, rounded), chroma
+    averaged over each subsampling cell, optional +-amp noise on Y.  Only an input generator — the planes it
+    returns are what the conversion under test consumes."""
+    rgb = img[..., :3].astype(np.float64)
+    h, w = img.shape[:2]
+    y = 0.299 * rgb[..., 0] + 0.587 * rgb[..., 1] + 0.114 * rgb[..., 2]
+    cb = 128.0 - 0.168736 * rgb[..., 0] - 0.331264 * rgb[..., 1] + 0.5 * rgb[..., 2]
+    cr = 128.0 + 0.5 * rgb[..., 0] - 0.418688 * rgb[..., 1] - 0.081312 * rgb[..., 2]
+    if amp:
+        rng = np.random.Generator(np.random.PCG64(seed))
+        y = y + rng.integers(-amp, amp + 1, size=y.shape)
+    dx, dy = _SUBSAMPLE[ratio]
+    cw, ch = (w + dx - 1) // dx, (h + dy - 1) // dy
+
+    def sub(p):
+        pad = np.pad(p, ((0, ch * dy - h), (0, cw * dx - w)), mode="edge")
+        return pad.reshape(ch, dy, cw, dx).mean(axis=(1, 3))
+
+    q = lambda p: np.clip(np.rint(p), 0, 255).astype(np.uint8)  # noqa: E731
+    return q(y), q(sub(cb)), q(sub(cr))
+
+
+def noise_planes(w: int, h: int, ratio: int, seed: int):
+    """Uniform random Y/Cb/Cr planes (exercises the clamps of the colour transform)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    dx, dy = _SUBSAMPLE[ratio]
+    cw, ch = (w + dx - 1) // dx, (h + dy - 1) // dy
+    return (rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (ch, cw), dtype=np.uint8),
+            rng.integers(0, 256, (ch, cw), dtype=np.uint8))

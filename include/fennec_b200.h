@@ -120,6 +120,29 @@ FB_API int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int sr
 /* smartResize's dimension logic — resize.go:12-32. Returns 1 when it is a no-op (same pointer). */
 FB_API int fb_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int *dstH);
 
+/* ---- the step before SSIMFast in the quality search (compress.go:53-62) --------- */
+
+/* convertToNRGBA — convert.go:34-64 — for the concrete types jpeg.Decode returns, Rect.Min == (0,0).
+ * `ratio` is Go's image.YCbCrSubsampleRatio constant: 0 = 4:4:4, 1 = 4:2:2, 2 = 4:2:0, 3 = 4:4:0,
+ * 4 = 4:1:1, 5 = 4:1:0 (chroma planes hold ceil(w/2^xs) x ceil(h/2^ys) samples, stride cStride).
+ * Bytes are those of img.At(x,y).RGBA() >> 8 (Go's color.YCbCr.RGBA integer transform), alpha 255. */
+FB_API int fb_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride,
+                      int w, int h, int ratio, uint8_t *dst, int dstStride);
+/* The same for *image.Gray (grayscale JPEGs). */
+FB_API int fb_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride);
+
+/* Reference-image session for the binary search of compress.go:45-74: `src` is uploaded and box-
+ * downsampled ONCE (ssim.go:57 recomputes it every iteration); each iteration then sends only the
+ * decoded candidate — as YCbCr planes (1.5 B/px at 4:2:0) or NRGBA — and gets SSIMFast(src, candidate)
+ * (ssim.go:48-70) back.  Scores are identical to fb_ssim_fast on the converted image.  A handle is
+ * bound to the device of the creating thread and may be used from one thread at a time. */
+typedef struct fb_ssim_ref fb_ssim_ref;
+FB_API int fb_ssim_ref_create(const uint8_t *src, int stride, int w, int h, fb_ssim_ref **out);
+FB_API int fb_ssim_ref_score_ycbcr(const fb_ssim_ref *ref, const uint8_t *y, int yStride, const uint8_t *cb,
+                            const uint8_t *cr, int cStride, int ratio, double *score);
+FB_API int fb_ssim_ref_score_nrgba(const fb_ssim_ref *ref, const uint8_t *img, int stride, double *score);
+FB_API void fb_ssim_ref_destroy(fb_ssim_ref *ref);
+
 /* ---- device-resident batch entry points (configs 3-5 and the headline metric) ------------- */
 /* n images (or pairs) of identical dims; image i starts at base + i*imgStride bytes. All pointers
  * are device pointers on `device`; `stream` is a cudaStream_t. Scores land in device memory. */
@@ -140,6 +163,10 @@ FB_API int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a,
                               int rowStride, int w, int h, int n, uint8_t *thumbA, uint8_t *thumbB,
                               int64_t thumbImgStride, int thumbRowStride, int tw, int th, uint8_t *halfA,
                               uint8_t *halfB, int64_t halfImgStride, int halfRowStride);
+/* convertToNRGBA for n device-resident YCbCr images (planes of image i at base + i*ImgStride). */
+FB_API int fb_ycbcr_to_nrgba_batch_dev(int device, void *stream, const uint8_t *y, int64_t yImgStride, int yStride,
+                                const uint8_t *cb, const uint8_t *cr, int64_t cImgStride, int cStride, int w,
+                                int h, int ratio, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int n);
 FB_API int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst,
                                int64_t imgStride, int rowStride, int w, int h, int n,
                                const double *kernel_host, int radius);

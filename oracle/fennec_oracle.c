@@ -813,3 +813,61 @@ int fo_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int 
     *dstH = (int)fmax(1, round((double)srcH * ratio));
     return 0;
 }
+
+/* ---- §8(f1): convertToNRGBA on decoded images (convert.go:34-64) ---------------------------------
+ * The reference walks img.At(x, y).RGBA() for every pixel.  For the two concrete types jpeg.Decode returns this
+ * is Go standard-library arithmetic (image/ycbcr.go, image/color/ycbcr.go — Go 1.25.5 per go.mod:3, NOT under
+ * /root/reference; restated here from the published source):
+ *   (*image.YCbCr).At     -> YCbCrAt: Y[YOffset(x,y)], Cb/Cr[COffset(x,y)], COffset per subsample ratio
+ *   color.YCbCr.RGBA()    -> yy1 = Y*0x10101; cb1 = Cb-128; cr1 = Cr-128;
+ *                            r = yy1 + 91881*cr1; g = yy1 - 22554*cb1 - 46802*cr1; b = yy1 + 116130*cb1;
+ *                            each: if uint32(v)&0xff000000 == 0 { v >>= 8 } else { v = ^(v>>31) & 0xffff }; a = 0xffff
+ *   convertToNRGBA, a == 0xffff branch (convert.go:48-53): uint8(v >> 8)
+ * which composes to the 8-bit color.YCbCrToRGB result.  Rect.Min is (0,0) for decoded images. */
+static int fo_c_offset(int ratio, int x, int y, int cStride) {
+    switch (ratio) {            /* image.YCbCrSubsampleRatio constants, in Go's order */
+        case 1: return y * cStride + x / 2;        /* 4:2:2 */
+        case 2: return (y / 2) * cStride + x / 2;  /* 4:2:0 */
+        case 3: return (y / 2) * cStride + x;      /* 4:4:0 */
+        case 4: return y * cStride + x / 4;        /* 4:1:1 */
+        case 5: return (y / 2) * cStride + x / 4;  /* 4:1:0 */
+        default: return y * cStride + x;           /* 4:4:4 */
+    }
+}
+
+static uint8_t fo_ycc_channel(int32_t v) {
+    uint32_t c16;
+    if (((uint32_t)v & 0xff000000u) == 0) c16 = (uint32_t)(v >> 8);
+    else c16 = (uint32_t)(~(v >> 31)) & 0xffffu;   /* arithmetic shift: -1 for negatives, 0 for overflow */
+    return (uint8_t)(c16 >> 8);
+}
+
+int fo_ycbcr_to_nrgba(const uint8_t *yp, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride,
+                      int w, int h, int ratio, uint8_t *dst, int dstStride) {
+    if (ratio < 0 || ratio > 5) return -1;
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            int ci = fo_c_offset(ratio, x, y, cStride);
+            int32_t yy1 = (int32_t)yp[y * yStride + x] * 0x10101;
+            int32_t cb1 = (int32_t)cb[ci] - 128;
+            int32_t cr1 = (int32_t)cr[ci] - 128;
+            uint8_t *o = dst + (size_t)y * dstStride + (size_t)x * 4;
+            o[0] = fo_ycc_channel(yy1 + 91881 * cr1);
+            o[1] = fo_ycc_channel(yy1 - 22554 * cb1 - 46802 * cr1);
+            o[2] = fo_ycc_channel(yy1 + 116130 * cb1);
+            o[3] = 0xff;
+        }
+    }
+    return 0;
+}
+
+/* (*image.Gray).At -> color.Gray{Y}.RGBA() = (y|y<<8) x3, 0xffff; convert.go:48-53 takes the high byte. */
+void fo_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            uint8_t v = g[y * gStride + x];
+            uint8_t *o = dst + (size_t)y * dstStride + (size_t)x * 4;
+            o[0] = o[1] = o[2] = v;
+            o[3] = 0xff;
+        }
+}

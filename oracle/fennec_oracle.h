@@ -102,6 +102,13 @@ int fo_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH,
 /* resize.go:12-32 — writes the dims smartResize would produce; returns 1 if it is a no-op. */
 int fo_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int *dstH);
 
+/* convertToNRGBA (convert.go:34-64) on what jpeg.Decode returns.  ratio = Go's
+ * image.YCbCrSubsampleRatio constant (0: 4:4:4, 1: 4:2:2, 2: 4:2:0, 3: 4:4:0, 4: 4:1:1, 5: 4:1:0).  Go stdlib arithmetic
+ * (image/color/ycbcr.go, Go 1.25.5; not vendored) restated from the published source — see the .c file. */
+int fo_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride,
+                      int w, int h, int ratio, uint8_t *dst, int dstStride);
+void fo_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride);
+
 #ifdef __cplusplus
 }
 #endif

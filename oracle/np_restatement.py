@@ -395,3 +395,39 @@ def smart_resize_dims(sw: int, sh: int, max_w: int, max_h: int):
     dw = int(max(1.0, float(go_round(float(sw) * ratio))))
     dh = int(max(1.0, float(go_round(float(sh) * ratio))))
     return False, dw, dh
+
+
+# ---- §8(f1): convertToNRGBA (convert.go:34-64) on jpeg.Decode's output types ------------------------------
+# Independent of the C oracle: chroma planes are upsampled by index arithmetic (Go's COffset), the colour
+# transform is vectorised int32 (Go's color.YCbCr.RGBA(), image/color/ycbcr.go — stdlib, restated).
+
+_SUB = {0: (1, 1), 1: (2, 1), 2: (2, 2), 3: (1, 2), 4: (4, 1), 5: (4, 2)}  # ratio -> (x divisor, y divisor)
+
+
+def ycbcr_to_nrgba(y: np.ndarray, cb: np.ndarray, cr: np.ndarray, ratio: int) -> np.ndarray:
+    h, w = y.shape
+    dx, dy = _SUB[ratio]
+    yi = (np.arange(h) // dy)[:, None]
+    xi = (np.arange(w) // dx)[None, :]
+    yy1 = y.astype(np.int32) * 0x10101
+    cb1 = cb[yi, xi].astype(np.int32) - 128
+    cr1 = cr[yi, xi].astype(np.int32) - 128
+
+    def chan(v):
+        inrange = (v.astype(np.uint32) & np.uint32(0xFF000000)) == 0
+        c16 = np.where(inrange, v >> 8, np.where(v < 0, 0, 0xFFFF))      # ^(v>>31) & 0xffff
+        return (c16 >> 8).astype(np.uint8)                              # convert.go:50-52
+
+    out = np.empty((h, w, 4), np.uint8)
+    out[..., 0] = chan(yy1 + 91881 * cr1)
+    out[..., 1] = chan(yy1 - 22554 * cb1 - 46802 * cr1)
+    out[..., 2] = chan(yy1 + 116130 * cb1)
+    out[..., 3] = 255
+    return out
+
+
+def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
+    out = np.empty(g.shape + (4,), np.uint8)
+    out[..., 0] = out[..., 1] = out[..., 2] = g
+    out[..., 3] = 255
+    return out

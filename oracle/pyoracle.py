@@ -67,6 +67,8 @@ def lib():
         L.fo_resize_v.argtypes = img + [C.c_int, C.c_int] + img + [C.c_int]
         L.fo_lanczos_resize.argtypes = img + [C.c_int, C.c_int] + img + [C.c_int, C.c_int]
         L.fo_smart_resize_dims.argtypes = [C.c_int] * 4 + [_ip, _ip]
+        L.fo_ycbcr_to_nrgba.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
+        L.fo_gray_to_nrgba.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         _lib = L
     return _lib
 
@@ -244,3 +246,30 @@ def smart_resize_dims(sw: int, sh: int, max_w: int, max_h: int):
     dw, dh = C.c_int(), C.c_int()
     noop = lib().fo_smart_resize_dims(sw, sh, max_w, max_h, C.byref(dw), C.byref(dh))
     return bool(noop), dw.value, dh.value
+
+
+def _plane(a: np.ndarray):
+    assert a.dtype == np.uint8 and a.ndim == 2 and a.strides[1] == 1
+    return a.ctypes.data_as(_u8p), int(a.strides[0])
+
+
+def ycbcr_to_nrgba(y: np.ndarray, cb: np.ndarray, cr: np.ndarray, ratio: int) -> np.ndarray:
+    """convertToNRGBA (convert.go:34-64) of an *image.YCbCr with Rect.Min == (0,0); planes are 2-D uint8 arrays."""
+    h, w = y.shape
+    assert cb.shape == cr.shape and cb.strides == cr.strides
+    dst = _new(h, w)
+    py, sy = _plane(y)
+    pcb, sc = _plane(cb)
+    pcr, _ = _plane(cr)
+    pd, sd = _img(dst)
+    assert lib().fo_ycbcr_to_nrgba(py, sy, pcb, pcr, sc, w, h, ratio, pd, sd) == 0
+    return dst
+
+
+def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
+    h, w = g.shape
+    dst = _new(h, w)
+    pg, sg = _plane(g)
+    pd, sd = _img(dst)
+    lib().fo_gray_to_nrgba(pg, sg, w, h, pd, sd)
+    return dst

@@ -60,6 +60,36 @@ if want("lanczos"):
     report("Lanczos3 7680x4320->1920x1080 opaque (config 4)", timeit(lambda: batch.lanczos_resize_batch(x, 1920, 1080, out=y), 3), 8, 33.1776,
            7680 * 4320 * 4 + 1920 * 1080 * 4)
     del x, y
+if want("ycbcr"):
+    # convertToNRGBA of a decoded 4:2:0 JPEG, device-resident (1.5 B read + 4 B written per pixel)
+    n, h, w = 16, 3024, 4032
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ty = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device="cuda", generator=g)
+    tcb = torch.randint(0, 256, (n, h // 2, w // 2), dtype=torch.uint8, device="cuda", generator=g)
+    tcr = torch.randint(0, 256, (n, h // 2, w // 2), dtype=torch.uint8, device="cuda", generator=g)
+    out = torch.empty((n, h, w, 4), dtype=torch.uint8, device="cuda")
+    report("convertToNRGBA 4:2:0 4032x3024 (f1)", timeit(lambda: batch.ycbcr_to_nrgba_batch(ty, tcb, tcr, 2, out=out), 20), n, 12.192768,
+           int(4032 * 3024 * 5.5))
+    del ty, tcb, tcr, out
+    # one iteration of the quality search (compress.go:45-74), host buffers, PCIe inside the timed region:
+    # reference semantics (both NRGBA images uploaded, src downsampled again) vs the cached-source session + YCbCr upload
+    import time
+    import numpy as np
+    from fennec_b200 import api, synth
+    src = synth.gradient_noise_image(4032, 3024, 5)
+    py, pcb, pcr = synth.ycbcr_planes_from_nrgba(src, 2, 1, 3)
+    cand = api.ycbcr_to_nrgba(py, pcb, pcr, 2)
+    def wall(fn, iters=10):
+        fn(); t0 = time.perf_counter()
+        for _ in range(iters): fn()
+        return (time.perf_counter() - t0) / iters * 1e3
+    ms_ref = wall(lambda: api.SSIMFast(src, cand))
+    with api.SSIMReference(src) as ref:
+        ms_ses = wall(lambda: ref.score_ycbcr(py, pcb, pcr, 2))
+        ms_ses_n = wall(lambda: ref.score_nrgba(cand))
+    print(json.dumps({"op": "search iteration e2e 4032x3024 (config 2), pageable host buffers", "ms_fb_ssim_fast_both_nrgba": round(ms_ref, 3),
+                      "ms_session_ycbcr420": round(ms_ses, 3), "ms_session_nrgba": round(ms_ses_n, 3),
+                      "h2d_bytes": {"fb_ssim_fast": 2 * 4032 * 3024 * 4, "session_ycbcr420": int(4032 * 3024 * 1.5), "session_nrgba": 4032 * 3024 * 4}}), flush=True)
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
     report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)
