@@ -210,28 +210,46 @@ __global__ void __launch_bounds__(kThreads) box_fused_kernel(const BoxFusedParam
         box_edge(dy, p.yRatio, p.srcH, sy0, sy1);
         for (int c4 = threadIdx.x * 4; c4 < span; c4 += kThreads * 4) {
             const int x = base + c4;   // x + 4 <= srcW (srcW % 4 == 0 and x < sxb <= srcW)
-            uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, prev[4] = {0, 0, 0, 0};
+            uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
             const uint8_t *q = s + (long long)sy0 * rs + (long long)x * 4;
             uint8_t *hcol = hd + (long long)(x >> 1) * 4;
-            for (int y = sy0; y < sy1; y++, q += rs) {
-                const uint4 t = ld_nc_u128(q);
+            auto acc = [&](const uint4 &t) {
                 const uint32_t v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     lo[i] += v[i] & 0x00FF00FFu;          // R, B
                     hi[i] += (v[i] >> 8) & 0x00FF00FFu;   // G, A
                 }
-                if (y & 1) {
-                    if (y > sy0) *reinterpret_cast<uint2 *>(hcol + (long long)(y >> 1) * p.halfRowStride) = mean2x2(prev, v);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) prev[i] = v[i];
-                }
+            };
+            auto emit = [&](const uint4 &ta, const uint4 &tb, int hy) {
+                const uint32_t a[4] = {ta.x, ta.y, ta.z, ta.w}, b[4] = {tb.x, tb.y, tb.z, tb.w};
+                *reinterpret_cast<uint2 *>(hcol + (long long)hy * p.halfRowStride) = mean2x2(a, b);
+            };
+            int y = sy0;
+            if (y & 1) {  // the box starts on an odd row: its partner (and the output row) belong to the previous box
+                acc(ld_nc_u128(q));
+                q += rs;
+                y++;
             }
-            if (((sy1 - 1) & 1) == 0 && sy1 < p.srcH) {   // box ends on an even row: fetch its partner
-                const uint4 t = ld_nc_u128(q);
-                const uint32_t v[4] = {t.x, t.y, t.z, t.w};
-                *reinterpret_cast<uint2 *>(hcol + (long long)((sy1 - 1) >> 1) * p.halfRowStride) = mean2x2(prev, v);
+            // row pairs (2k, 2k+1) inside the box: two pairs (four independent 128-bit loads) in flight per thread
+            for (; y + 3 < sy1; y += 4, q += 4 * (long long)rs) {
+                const uint4 t0 = ld_nc_u128(q), t1 = ld_nc_u128(q + rs), t2 = ld_nc_u128(q + 2 * (long long)rs),
+                            t3 = ld_nc_u128(q + 3 * (long long)rs);
+                acc(t0); acc(t1); acc(t2); acc(t3);
+                emit(t0, t1, y >> 1);
+                emit(t2, t3, (y >> 1) + 1);
+            }
+            if (y + 1 < sy1) {
+                const uint4 t0 = ld_nc_u128(q), t1 = ld_nc_u128(q + rs);
+                acc(t0); acc(t1);
+                emit(t0, t1, y >> 1);
+                y += 2;
+                q += 2 * (long long)rs;
+            }
+            if (y < sy1) {  // the box ends on an even row: fetch its partner (first row of the next box; srcH is even)
+                const uint4 t0 = ld_nc_u128(q), t1 = ld_nc_u128(q + rs);
+                acc(t0);
+                emit(t0, t1, y >> 1);
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) colsum[c4 + i] = make_uint2(lo[i], hi[i]);
