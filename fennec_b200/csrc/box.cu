@@ -74,7 +74,23 @@ __global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams p) {
         uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
         const bool full = p.vecOK && (x + 4 <= p.srcW);
         const uint8_t *q = s + (long long)sy0 * p.srcRowStride + (long long)x * 4;
-        for (int y = sy0; y < sy1; y++, q += p.srcRowStride) {
+        int y = sy0;
+        if (full) {  // four independent 128-bit row loads in flight per thread
+            for (; y + 3 < sy1; y += 4, q += 4 * (long long)p.srcRowStride) {
+                const uint4 t[4] = {ld_nc_u128(q), ld_nc_u128(q + p.srcRowStride), ld_nc_u128(q + 2 * (long long)p.srcRowStride),
+                                    ld_nc_u128(q + 3 * (long long)p.srcRowStride)};
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t v[4] = {t[r].x, t[r].y, t[r].z, t[r].w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        lo[i] += v[i] & 0x00FF00FFu;
+                        hi[i] += (v[i] >> 8) & 0x00FF00FFu;
+                    }
+                }
+            }
+        }
+        for (; y < sy1; y++, q += p.srcRowStride) {
             uint32_t v[4];
             if (full) {
                 uint4 t = ld_nc_u128(q);

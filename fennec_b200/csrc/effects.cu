@@ -117,6 +117,104 @@ __device__ __forceinline__ uint32_t round_flag(float v, float lim, bool &amb) {
     return __float_as_uint(t) & 0x1FFu;
 }
 
+// Round + pack the kTile outputs of a thread.  The accumulators are (even output, odd output) pairs per channel, so
+// the magic-number rounding runs as packed FADD2/FFMA2 (t = v + 1.5*2^23, r = t - 1.5*2^23, d = v - r); the low byte of
+// t's bit pattern IS the rounded value (v is within [-0.25, 255.25]), so three PRMTs assemble R|G|B|alpha without
+// masks or shifts.  Returns the mask of outputs with a channel within eps of a tie (lim = 0.5 - eps).
+__device__ __forceinline__ uint32_t pack_rgba_low_bytes(float tr, float tg, float tb, uint32_t alphaWord) {
+    const uint32_t x = __byte_perm(__float_as_uint(tr), __float_as_uint(tg), 0x0040);   // [r, g, ., .]
+    const uint32_t z = __byte_perm(__float_as_uint(tb), alphaWord, 0x7000);              // [., ., b, alpha]
+    return __byte_perm(x, z, 0x7610);
+}
+
+template <typename AlphaFn>
+__device__ __forceinline__ uint32_t blur_round_pack(const float2 (&acc)[kTile / 2][3], float lim, uint32_t (&out)[kTile],
+                                                    AlphaFn alphaWord) {
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+    uint32_t ambMask = 0;
+#pragma unroll
+    for (int m = 0; m < kTile / 2; m++) {
+        float2 t[3], d[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            t[c] = __fadd2_rn(acc[m][c], magic);
+            const float2 r = __fadd2_rn(t[c], nmagic);
+            d[c] = __ffma2_rn(r, neg1, acc[m][c]);   // v - r, exact product
+        }
+        const float mx = fmaxf(fmaxf(fabsf(d[0].x), fabsf(d[1].x)), fabsf(d[2].x));
+        const float my = fmaxf(fmaxf(fabsf(d[0].y), fabsf(d[1].y)), fabsf(d[2].y));
+        if (mx >= lim) ambMask |= 1u << (2 * m);
+        if (my >= lim) ambMask |= 1u << (2 * m + 1);
+        out[2 * m] = pack_rgba_low_bytes(t[0].x, t[1].x, t[2].x, alphaWord(2 * m));
+        out[2 * m + 1] = pack_rgba_low_bytes(t[0].y, t[1].y, t[2].y, alphaWord(2 * m + 1));
+    }
+    return ambMask;
+}
+
+// ---- deferred exact path ---------------------------------------------------------------------------------
+// About 0.16 % of the outputs are ambiguous, but that is ~1 per warp per 16-output chunk: recomputing them on the
+// spot kept one or two lanes busy for ~200 FP64 instructions while the other 30 waited (and the I2F conversions
+// queued on the XU pipe: 23 % busy in profiles/r1c).  Instead each warp queues (x, y) of its ambiguous outputs in
+// shared memory and drains the queue 32 at a time, one output per lane, re-reading the taps through L1/L2.
+constexpr int kAmbQ = 32 * kTile + 32;   // a chunk can add at most 32*kTile entries to fewer than 32 leftovers
+
+__device__ __forceinline__ double byte_d(uint32_t b) {
+    return __hiloint2double(0x43300000, (int)b) - 4503599627370496.0;  // (2^52 + b) - 2^52: exact, no I2F
+}
+
+// Exact FP64 sequence (effects.go:172-188 / 198-214) for output (x, y) of a pass; taps are read from `img`
+// (row stride `rs`) with clamp-to-edge along the filter axis.  Returns R|G|B; the caller adds alpha.
+template <bool VERTICAL>
+__device__ __forceinline__ uint32_t blur_exact_at(const uint8_t *img, int rs, int w, int h, int x, int y, int radius,
+                                                  const double *kernel, uint32_t &centre) {
+    double r = 0.0, g = 0.0, b = 0.0;
+    const int n = VERTICAL ? h : w, pos = VERTICAL ? y : x;
+    for (int k = 0; k <= 2 * radius; k++) {
+        int qd = pos + k - radius;
+        qd = qd < 0 ? 0 : (qd >= n ? n - 1 : qd);
+        const uint32_t v = VERTICAL ? ld_nc_u32(img + (long long)qd * rs + (long long)x * 4)
+                                    : ld_nc_u32(img + (long long)y * rs + (long long)qd * 4);
+        if (k == radius) centre = v;
+        const double wt = __ldg(kernel + k);
+        r = __dadd_rn(r, __dmul_rn(byte_d(v & 0xFF), wt));
+        g = __dadd_rn(g, __dmul_rn(byte_d((v >> 8) & 0xFF), wt));
+        b = __dadd_rn(b, __dmul_rn(byte_d((v >> 16) & 0xFF), wt));
+    }
+    return clampf_dev(r) | (clampf_dev(g) << 8) | (clampf_dev(b) << 16);
+}
+
+// Queue this lane's flagged outputs: output j of the mask is pixel (x0 + j*dx, y0 + j*dy).
+__device__ __forceinline__ void amb_push(uint32_t mask, int x0, int y0, int dx, int dy, uint32_t *q, int *cnt) {
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        q[atomicAdd(cnt, 1)] = ((uint32_t)(y0 + j * dy) << 16) | (uint32_t)(x0 + j * dx);
+    }
+}
+
+// Drain the warp's queue in groups of 32 (all = true: until empty).  Warp-uniform; callers __syncwarp() before.
+template <bool VERTICAL>
+__device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *cnt, const uint8_t *taps, int tapsRs,
+                                          uint8_t *dst, int dstRs, int w, int h, int radius, const double *kernel) {
+    int n = *cnt;
+    if (n < (all ? 1 : 32)) return;
+    while (n >= (all ? 1 : 32)) {
+        const int take = min(n, 32);
+        n -= take;
+        if (lane < take) {
+            const uint32_t code = q[n + lane];
+            const int x = (int)(code & 0xFFFFu), y = (int)(code >> 16);
+            uint32_t centre;
+            const uint32_t e = blur_exact_at<VERTICAL>(taps, tapsRs, w, h, x, y, radius, kernel, centre);
+            *reinterpret_cast<uint32_t *>(dst + (long long)y * dstRs + (long long)x * 4) = e | (centre & 0xFF000000u);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *cnt = n;
+    __syncwarp();
+}
+
 // Exact FP64 tap sum of one output (the reference's sequence, effects.go:172-188) over taps that were
 // staged as packed pixels at `px[k * strideWords]`, k = 0..2R (clamping already applied by the stager).
 __device__ __forceinline__ uint32_t blur_exact_taps(const uint32_t *px, int strideWords, int taps,
@@ -173,9 +271,13 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // y+1 is staged into the warp's second shared-memory buffer with cp.async while row y is evaluated, so the
 // global-load latency is paid once per warp instead of once per row.  No block-wide barrier.
 template <int R>
-__global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
+__global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p) {
     __shared__ __align__(16) uint8_t stage[4][2][34 * kChunkB];
+    __shared__ uint32_t ambQ[4][kAmbQ];
+    __shared__ int ambN[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) ambN[warp] = 0;
+    __syncwarp();
     const int yBeg = (blockIdx.y * 4 + warp) * kHRows, img = blockIdx.z;
     const int yEnd = min(yBeg + kHRows, p.h);
     if (yBeg >= p.h) return;  // warp-uniform; no block barrier below
@@ -233,17 +335,7 @@ __global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
             float2 acc[kTile / 2][3];
             blur_taps_fp32<R, 32, 8>(raw, p.kernel32, acc);
             uint32_t out[kTile];
-            uint32_t ambMask = 0;
-#pragma unroll
-            for (int j = 0; j < kTile; j++) {
-                bool a0, a1, a2;
-                const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
-                const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
-                const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
-                uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
-                out[j] = r | (g << 8) | (b << 16) | (raw[8 + j] & 0xFF000000u);  // alpha from the source (effects.go:189)
-                if (a0 | a1 | a2) ambMask |= 1u << j;
-            }
+            uint32_t ambMask = blur_round_pack(acc, lim, out, [&](int j) { return raw[8 + j]; });  // alpha from the source (effects.go:189)
             uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
             if (dvec && x0 + kTile <= p.w) {
 #pragma unroll
@@ -254,27 +346,15 @@ __global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
                 for (int j = 0; j < kTile; j++)
                     if (x0 + j < p.w) *reinterpret_cast<uint32_t *>(drow + j * 4) = out[j];
             }
-            // Ambiguous outputs: exact FP64 sequence from the staged bytes, overwriting the pixel just stored
-            // (same thread, program order).  Taps of output j start at stage pixel 16*lane + 16 + j - R.
-            const uint32_t *stw = reinterpret_cast<const uint32_t *>(st);
-            while (ambMask) {
-                const int j = __ffs(ambMask) - 1;
-                ambMask &= ambMask - 1;
-                if (x0 + j < p.w) {
-                    uint32_t taps[2 * R + 1];
-#pragma unroll
-                    for (int k = 0; k <= 2 * R; k++) {
-                        const int sp = 16 * lane + 16 + j - R + k;  // stage pixel index
-                        taps[k] = stw[(sp >> 4) * (kChunkB / 4) + (sp & 15)];
-                    }
-                    uint32_t e = blur_exact_taps(taps, 1, 2 * R + 1, p.kernel);
-                    uint32_t alpha = stw[((16 * lane + 16 + j) >> 4) * (kChunkB / 4) + ((16 * lane + 16 + j) & 15)] & 0xFF000000u;
-                    *reinterpret_cast<uint32_t *>(drow + j * 4) = e | alpha;
-                }
-            }
+            if (x0 + kTile > p.w) ambMask &= (1u << (p.w - x0)) - 1u;
+            amb_push(ambMask, x0, y, 1, 0, ambQ[warp], &ambN[warp]);  // exact FP64 path deferred (see amb_drain)
         }
-        __syncwarp();  // every lane is done with `st` before it is restaged two rows later
+        __syncwarp();  // every lane is done with `st` before it is restaged two rows later; queue pushes are visible
+        amb_drain<false>(false, lane, ambQ[warp], &ambN[warp], simg, p.srcRowStride, p.dst + (long long)img * p.dstImgStride,
+                         p.dstRowStride, p.w, p.h, R, p.kernel);
     }
+    amb_drain<false>(true, lane, ambQ[warp], &ambN[warp], simg, p.srcRowStride, p.dst + (long long)img * p.dstImgStride,
+                     p.dstRowStride, p.w, p.h, R, p.kernel);
 }
 
 // Vertical pass: a thread owns one column and walks down a segment of kVSeg rows in chunks of kTile
@@ -286,15 +366,22 @@ __global__ void __launch_bounds__(128) blur_h_fast_kernel(const BlurParams p) {
 constexpr int kVSeg = 240;  // rows per thread segment (2160 = 9 * 240; halo 12/240)
 
 template <int R>
-__global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
+__global__ void __launch_bounds__(128, 4) blur_v_fast_kernel(const BlurParams p) {
     constexpr int NIN = kTile + 2 * R;
-    __shared__ uint32_t dump[128 * (NIN + 1)];  // per-thread tap dump for the exact path (+1: bank spread)
+    __shared__ uint32_t ambQ[4][kAmbQ];
+    __shared__ int ambN[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) ambN[warp] = 0;
+    __syncwarp();
     const int x = blockIdx.x * 128 + threadIdx.x, img = blockIdx.z;
     const int ys = blockIdx.y * kVSeg;
     const int yEnd = min(ys + kVSeg, p.h);
-    if (x >= p.w) return;
-    const uint8_t *scol = p.src + (long long)img * p.srcImgStride + (long long)x * 4;
-    uint8_t *dcol = p.dst + (long long)img * p.dstImgStride + (long long)x * 4;
+    const bool active = x < p.w;   // inactive lanes still take part in the warp's queue drains
+    const int xc = active ? x : p.w - 1;
+    const uint8_t *simg = p.src + (long long)img * p.srcImgStride;
+    uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
+    const uint8_t *scol = simg + (long long)xc * 4;
+    uint8_t *dcol = dimg + (long long)xc * 4;
     const float lim = 0.5f - p.eps;
     auto ld_row = [&](int y) -> uint32_t {
         const int sy = min(max(y, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
@@ -307,40 +394,37 @@ __global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
     for (int y0 = ys; y0 < yEnd; y0 += kTile) {
         const bool more = y0 + kTile < yEnd;
         if (more) {
+            const int yn = y0 + kTile + R;  // first row of the next chunk's new rows
+            if (yn + kTile <= p.h) {       // no clamping: one running pointer
+                const uint8_t *np = scol + (long long)yn * p.srcRowStride;
 #pragma unroll
-            for (int i = 0; i < kTile; i++) nxt[i] = ld_row(y0 + kTile + R + i);
+                for (int i = 0; i < kTile; i++, np += p.srcRowStride) nxt[i] = __ldg(reinterpret_cast<const uint32_t *>(np));
+            } else {
+#pragma unroll
+                for (int i = 0; i < kTile; i++) nxt[i] = ld_row(yn + i);
+            }
         }
         float2 acc[kTile / 2][3];
         blur_taps_fp32<R, NIN, R>(raw, p.kernel32, acc);
-        uint32_t ambMask = 0;
+        uint32_t out[kTile];
+        uint32_t ambMask = blur_round_pack(acc, lim, out, [&](int j) { return raw[R + j]; });  // alpha rides in tmp (effects.go:189,215)
+        {
+            uint8_t *dp = dcol + (long long)y0 * p.dstRowStride;
+            if (!active) {
+                ambMask = 0;
+            } else if (y0 + kTile <= yEnd) {
 #pragma unroll
-        for (int j = 0; j < kTile; j++) {
-            const int y = y0 + j;
-            if (y < yEnd) {
-                bool a0, a1, a2;
-                const float v0 = (j & 1) ? acc[j / 2][0].y : acc[j / 2][0].x;
-                const float v1 = (j & 1) ? acc[j / 2][1].y : acc[j / 2][1].x;
-                const float v2 = (j & 1) ? acc[j / 2][2].y : acc[j / 2][2].x;
-                uint32_t r = round_flag(v0, lim, a0), g = round_flag(v1, lim, a1), b = round_flag(v2, lim, a2);
-                if (a0 | a1 | a2) ambMask |= 1u << j;
-                *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) =
-                    r | (g << 8) | (b << 16) | (raw[R + j] & 0xFF000000u);
+                for (int j = 0; j < kTile; j++, dp += p.dstRowStride) *reinterpret_cast<uint32_t *>(dp) = out[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < kTile; j++, dp += p.dstRowStride)
+                    if (y0 + j < yEnd) *reinterpret_cast<uint32_t *>(dp) = out[j];
+                ambMask &= (1u << (yEnd - y0)) - 1u;
             }
         }
-        if (ambMask) {  // rare: dump this thread's taps to shared memory and redo the flagged outputs exactly
-            uint32_t *mine = dump + threadIdx.x * (NIN + 1);
-#pragma unroll
-            for (int i = 0; i < NIN; i++) mine[i] = raw[i];
-            while (ambMask) {
-                const int j = __ffs(ambMask) - 1;
-                ambMask &= ambMask - 1;
-                const int y = y0 + j;
-                if (y < yEnd) {
-                    uint32_t e = blur_exact_taps(mine + j, 1, 2 * R + 1, p.kernel);
-                    *reinterpret_cast<uint32_t *>(dcol + (long long)y * p.dstRowStride) = e | (mine[R + j] & 0xFF000000u);
-                }
-            }
-        }
+        if (active) amb_push(ambMask, x, y0, 0, 1, ambQ[warp], &ambN[warp]);  // exact FP64 path deferred (see amb_drain)
+        __syncwarp();
+        amb_drain<true>(false, lane, ambQ[warp], &ambN[warp], simg, p.srcRowStride, dimg, p.dstRowStride, p.w, p.h, R, p.kernel);
         if (more) {
 #pragma unroll
             for (int i = 0; i < 2 * R; i++) raw[i] = raw[i + kTile];
@@ -348,6 +432,8 @@ __global__ void __launch_bounds__(128) blur_v_fast_kernel(const BlurParams p) {
             for (int i = 0; i < kTile; i++) raw[2 * R + i] = nxt[i];
         }
     }
+    __syncwarp();
+    amb_drain<true>(true, lane, ambQ[warp], &ambN[warp], simg, p.srcRowStride, dimg, p.dstRowStride, p.w, p.h, R, p.kernel);
 }
 
 template <int R>
@@ -701,7 +787,7 @@ int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long 
     p.src = src; p.srcImgStride = imgStride; p.srcRowStride = rowStride;
     p.alpha = src; p.alphaImgStride = imgStride; p.alphaRowStride = rowStride;
     p.dst = tmp; p.dstImgStride = tmpImgStride; p.dstRowStride = tmpRowStride;
-    const bool fastOK = !p.exactOnly && getenv("FB_BLUR_GENERIC") == nullptr;
+    const bool fastOK = !p.exactOnly && getenv("FB_BLUR_GENERIC") == nullptr && w <= 65535 && h <= 65535;  // the exact queue packs (x, y) in 16+16 bits
     if (!(fastOK && launch_blur_fast_any(s, p, n, false))) blur_pass_kernel<false><<<grid, 256, 0, s>>>(p);
     // vertical: tmp → dst, alpha from the original
     p.src = tmp; p.srcImgStride = tmpImgStride; p.srcRowStride = tmpRowStride;
