@@ -115,3 +115,67 @@ func gpuShard(nItems, nShards, shard int) (begin, end int, ok bool) {
 	st := C.fb_batch_shard(C.int(nItems), C.int(nShards), C.int(shard), &b, &e)
 	return int(b), int(e), st == C.FB_OK
 }
+
+// ---- SURVEY §8(f1): the step before SSIMFast in the quality search (compress.go:53-62) ----------------
+
+// gpuConvertToNRGBA replaces convertToNRGBA's pixel loop (convert.go:38-63) for the two concrete types
+// jpeg.Decode returns with Rect.Min == (0,0); anything else keeps the pure-Go loop.
+func gpuConvertToNRGBA(img image.Image, dst *image.NRGBA) bool {
+	switch s := img.(type) {
+	case *image.YCbCr:
+		if s.Rect.Min != (image.Point{}) || len(s.Y) == 0 {
+			return false
+		}
+		st := C.fb_ycbcr_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Y[0])), C.int(s.YStride),
+			(*C.uint8_t)(unsafe.Pointer(&s.Cb[0])), (*C.uint8_t)(unsafe.Pointer(&s.Cr[0])), C.int(s.CStride),
+			C.int(s.Rect.Dx()), C.int(s.Rect.Dy()), C.int(s.SubsampleRatio), pix(dst), C.int(dst.Stride))
+		return st == C.FB_OK
+	case *image.Gray:
+		if s.Rect.Min != (image.Point{}) || len(s.Pix) == 0 {
+			return false
+		}
+		st := C.fb_gray_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Pix[0])), C.int(s.Stride),
+			C.int(s.Rect.Dx()), C.int(s.Rect.Dy()), pix(dst), C.int(dst.Stride))
+		return st == C.FB_OK
+	}
+	return false
+}
+
+// ssimSession keeps `src` (its SSIMFast thumbnail) on the device for the whole binary search of
+// compressJPEG (compress.go:45-74).  Create it before the loop, Close it after; inside the loop
+//
+//	decoded, _ := jpeg.Decode(...)
+//	ssim, ok := sess.score(decoded)          // instead of toNRGBARef(decoded) + SSIMFast(src, ·)
+//	if !ok { ssim = SSIMFast(src, toNRGBARef(decoded)) }
+//
+// A session is bound to the OS thread's device; use it from one goroutine (runtime.LockOSThread).
+type ssimSession struct{ h *C.fb_ssim_ref }
+
+func newSSIMSession(src *image.NRGBA) (*ssimSession, bool) {
+	var h *C.fb_ssim_ref
+	st := C.fb_ssim_ref_create(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()), &h)
+	if st != C.FB_OK {
+		return nil, false
+	}
+	return &ssimSession{h}, true
+}
+
+func (s *ssimSession) score(decoded image.Image) (float64, bool) {
+	var out C.double
+	switch d := decoded.(type) {
+	case *image.YCbCr:
+		if d.Rect.Min != (image.Point{}) {
+			return 0, false
+		}
+		st := C.fb_ssim_ref_score_ycbcr(s.h, (*C.uint8_t)(unsafe.Pointer(&d.Y[0])), C.int(d.YStride),
+			(*C.uint8_t)(unsafe.Pointer(&d.Cb[0])), (*C.uint8_t)(unsafe.Pointer(&d.Cr[0])), C.int(d.CStride),
+			C.int(d.SubsampleRatio), &out)
+		return float64(out), st == C.FB_OK
+	case *image.NRGBA:
+		st := C.fb_ssim_ref_score_nrgba(s.h, pix(d), C.int(d.Stride), &out)
+		return float64(out), st == C.FB_OK
+	}
+	return 0, false
+}
+
+func (s *ssimSession) Close() { C.fb_ssim_ref_destroy(s.h); s.h = nil }
