@@ -660,6 +660,22 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
                 // gaussianBlur3x3 (effects.go:124-136): (sum + 8) >> 4 on each 16-bit lane
                 const uint32_t brb = ((hPrevRB[i] + 2 * hCurRB[i] + hNextRB[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
                 const uint32_t bga = ((hPrevGA[i] + 2 * hCurGA[i] + hNextGA[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+                if (MODE == 1 && INTK >= 0) {
+                    // Integer unsharp on packed 16-bit lanes (R|B and G|A): per lane
+                    //   T = orig*(A + 2^k) - blur*A + half + bias,   bias = 1024 << k  (lanes stay in [0, 32767])
+                    //   out = relu(min((T >> k) - 1024, 255))        one DPX instruction (VIADDMNMX.S16x2.RELU)
+                    // == min(max(((orig << k) + A*(orig - blur) + half) >> k, 0), 255), the exact form of effects.go:37-38
+                    // for dyadic amounts (checked for every (orig, blur) pair and every (A, k) the launcher can pick).
+                    const uint32_t cst = (uint32_t)((1024 << INTK) + p.half) * 0x00010001u;
+                    const uint32_t msk = (uint32_t)(0xFFFF >> INTK) * 0x00010001u;
+                    const uint32_t orb = c & 0x00FF00FFu, oga = (c >> 8) & 0x00FF00FFu;
+                    const uint32_t trb = ((orb * (uint32_t)(p.A + (1 << INTK)) + cst - brb * (uint32_t)p.A) >> INTK) & msk;
+                    const uint32_t tga = ((oga * (uint32_t)(p.A + (1 << INTK)) + cst - bga * (uint32_t)p.A) >> INTK) & msk;
+                    const uint32_t rrb = __viaddmin_s16x2_relu(trb, 0xFC00FC00u, 0x00FF00FFu);   // + (-1024) per lane
+                    const uint32_t rga = __viaddmin_s16x2_relu(tga, 0xFC00FC00u, 0x00FF00FFu);
+                    out[i] = ((rrb | (rga << 8)) & 0x00FFFFFFu) | (c & 0xFF000000u);
+                    continue;
+                }
                 const int bl[3] = {(int)(brb & 0xFF), (int)(bga & 0xFF), (int)(brb >> 16)};
                 if (MODE == 0) {
                     res = (uint32_t)bl[0] | ((uint32_t)bl[1] << 8) | ((uint32_t)bl[2] << 16) | (c & 0xFF000000u);

@@ -62,6 +62,51 @@ __global__ void __launch_bounds__(128) ycbcr_to_nrgba_kernel(const YccParams p) 
     }
 }
 
+// 4:2:0 fast path: one thread = 8 pixels x 2 rows = one 4-sample chroma group: two 64-bit Y loads, one 32-bit
+// load per chroma plane, four 128-bit stores (the generic kernel above issues 9 loads per 4 pixels).
+__global__ void __launch_bounds__(128) ycbcr420_to_nrgba_kernel(const YccParams p) {
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    const int y0 = blockIdx.y * 2, img = blockIdx.z;
+    if (x0 >= p.w) return;
+    const uint8_t *yrow = p.y + (long long)img * p.yImgStride + (long long)y0 * p.yStride;
+    const long long coff = (long long)img * p.cImgStride + (long long)blockIdx.y * p.cStride;
+    const uint8_t *cbrow = p.cb + coff, *crrow = p.cr + coff;
+    uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y0 * p.dstRowStride + (long long)x0 * 4;
+    const bool two = y0 + 1 < p.h;
+    if (x0 + 8 <= p.w) {
+        const uint32_t cb4 = __ldg(reinterpret_cast<const uint32_t *>(cbrow + (x0 >> 1)));
+        const uint32_t cr4 = __ldg(reinterpret_cast<const uint32_t *>(crrow + (x0 >> 1)));
+        const uint2 ya = __ldg(reinterpret_cast<const uint2 *>(yrow + x0));
+        const uint2 yb = two ? __ldg(reinterpret_cast<const uint2 *>(yrow + p.yStride + x0)) : make_uint2(0u, 0u);
+        uint32_t oa[8], ob[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int cb = (int)((cb4 >> (8 * (i >> 1))) & 0xFF), cr = (int)((cr4 >> (8 * (i >> 1))) & 0xFF);
+            const int cb1 = cb - 128, cr1 = cr - 128;
+            const int dr = 91881 * cr1, dg = -22554 * cb1 - 46802 * cr1, db = 116130 * cb1;   // shared by the two rows
+            const int Ya = (int)(((i < 4 ? ya.x : ya.y) >> (8 * (i & 3))) & 0xFF) * 0x10101;
+            const int Yb = (int)(((i < 4 ? yb.x : yb.y) >> (8 * (i & 3))) & 0xFF) * 0x10101;
+            oa[i] = (uint32_t)min(max((Ya + dr) >> 16, 0), 255) | ((uint32_t)min(max((Ya + dg) >> 16, 0), 255) << 8) |
+                    ((uint32_t)min(max((Ya + db) >> 16, 0), 255) << 16) | 0xFF000000u;
+            ob[i] = (uint32_t)min(max((Yb + dr) >> 16, 0), 255) | ((uint32_t)min(max((Yb + dg) >> 16, 0), 255) << 8) |
+                    ((uint32_t)min(max((Yb + db) >> 16, 0), 255) << 16) | 0xFF000000u;
+        }
+        *reinterpret_cast<uint4 *>(drow) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<uint4 *>(drow + 16) = make_uint4(oa[4], oa[5], oa[6], oa[7]);
+        if (two) {
+            *reinterpret_cast<uint4 *>(drow + p.dstRowStride) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+            *reinterpret_cast<uint4 *>(drow + p.dstRowStride + 16) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+        }
+    } else {  // right edge: per pixel
+        for (int r = 0; r < (two ? 2 : 1); r++)
+            for (int i = 0; x0 + i < p.w; i++) {
+                const int cx = (x0 + i) >> 1;
+                *reinterpret_cast<uint32_t *>(drow + (long long)r * p.dstRowStride + 4 * i) =
+                    ycc_px((int)__ldg(yrow + (long long)r * p.yStride + x0 + i), (int)__ldg(cbrow + cx), (int)__ldg(crrow + cx));
+            }
+    }
+}
+
 __global__ void __launch_bounds__(128) gray_to_nrgba_kernel(const uint8_t *g, long long gImgStride, int gStride, uint8_t *dst,
                                                             long long dstImgStride, int dstRowStride, int w, int h, int vecOK) {
     const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
@@ -104,8 +149,16 @@ int launch_ycbcr_to_nrgba(cudaStream_t s, const uint8_t *y, long long yImgStride
     p.w = w; p.h = h;
     p.vecOK = ((((uintptr_t)y | (uintptr_t)yImgStride | (uintptr_t)yStride) & 3) == 0) &&
               ((((uintptr_t)dst | (uintptr_t)dstImgStride | (uintptr_t)dstRowStride) & 15) == 0);
-    dim3 grid(((w + 3) / 4 + 127) / 128, h, n);
-    ycbcr_to_nrgba_kernel<<<grid, 128, 0, s>>>(p);
+    const bool fast420 = ratio == 2 && ((((uintptr_t)y | (uintptr_t)yImgStride | (uintptr_t)yStride) & 7) == 0) &&
+                         ((((uintptr_t)cb | (uintptr_t)cr | (uintptr_t)cImgStride | (uintptr_t)cStride) & 3) == 0) &&
+                         ((((uintptr_t)dst | (uintptr_t)dstImgStride | (uintptr_t)dstRowStride) & 15) == 0);
+    if (fast420) {
+        dim3 grid(((w + 7) / 8 + 127) / 128, (h + 1) / 2, n);
+        ycbcr420_to_nrgba_kernel<<<grid, 128, 0, s>>>(p);
+    } else {
+        dim3 grid(((w + 3) / 4 + 127) / 128, h, n);
+        ycbcr_to_nrgba_kernel<<<grid, 128, 0, s>>>(p);
+    }
     FB_LAUNCHED(1);
     FB_CUDA(cudaGetLastError());
     return FB_OK;
