@@ -24,6 +24,14 @@ class FbWeights(C.Structure):
     _fields_ = [("n", C.c_int), ("start", ip), ("index", ip), ("weight", dp)]
 
 
+class FbImageStats(C.Structure):
+    """struct fb_image_stats — the fields of fennec.ImageStats (analyze.go:9-22)."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("has_alpha", C.c_int), ("is_grayscale", C.c_int),
+                ("unique_colors", C.c_int), ("entropy", C.c_double), ("edge_density", C.c_double),
+                ("mean_brightness", C.c_double), ("contrast", C.c_double), ("recommended_format", C.c_int),
+                ("recommended_quality", C.c_int), ("estimated_compression", C.c_double)]
+
+
 _IMG = [u8p, C.c_int]
 _PAIR = _IMG + _IMG + [C.c_int, C.c_int, dp]
 _BATCH_SCORE = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -62,6 +70,10 @@ PROTOTYPES = {
     "fb_ycbcr_to_nrgba_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                               C.c_int]),
+    "fb_analyze": (C.c_int, _IMG + [C.c_int, C.c_int, C.POINTER(FbImageStats)]),
+    "fb_analyze_raw_bytes": (C.c_size_t, []),
+    "fb_analyze_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fb_analyze_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FbImageStats)]),
     "fb_ssim_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_ssim_fast_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_msssim_batch_dev": (C.c_int, _BATCH_SCORE),

@@ -298,3 +298,24 @@ class SSIMReference:
             self.close()
         except Exception:
             pass
+
+
+# ---- analyze.go:26-176 -----------------------------------------------------------------------------
+
+FORMAT_JPEG, FORMAT_PNG = 1, 2                                  # types.go:36-42
+QUALITY_BALANCED, QUALITY_HIGH, QUALITY_AGGRESSIVE = 0, 3, 4    # types.go:59-70
+
+
+def _stats_dict(st: "_lib.FbImageStats") -> dict:
+    return {k: getattr(st, k) for k, _ in _lib.FbImageStats._fields_}
+
+
+def Analyze(img: np.ndarray) -> dict:
+    """fennec.Analyze (analyze.go:26-113) → the ImageStats fields as a dict (snake_case keys)."""
+    st = _lib.FbImageStats()
+    if img.size == 0:
+        check(_lib.load().fb_analyze(None, 0, img.shape[1] if img.ndim == 3 else 0, img.shape[0] if img.ndim == 3 else 0, C.byref(st)))
+    else:
+        p, stride, w, h = _img(img)
+        check(_lib.load().fb_analyze(p, stride, w, h, C.byref(st)))
+    return _stats_dict(st)

@@ -101,6 +101,29 @@ def ycbcr_to_nrgba_batch(y: torch.Tensor, cb: torch.Tensor, cr: torch.Tensor, ra
     return out
 
 
+def analyze_batch(imgs: torch.Tensor) -> List[dict]:
+    """fennec.Analyze (analyze.go:26-176) for n device-resident images: the scans run on the device, the raw records
+    (histogram, integer sums, counts) come back in one copy and are finished with host arithmetic."""
+    p, i_s, rs, w, h, n = _batch(imgs)
+    L = _lib.load()
+    rec = int(L.fb_analyze_raw_bytes())
+    raw = torch.empty(n * rec, dtype=torch.uint8, device=imgs.device)
+    check(L.fb_analyze_batch_dev(_dev(imgs), _stream(imgs), p, i_s, rs, w, h, n, raw.data_ptr()))
+    host = raw.cpu().numpy()
+    out = []
+    for i in range(n):
+        st = _lib.FbImageStats()
+        check(L.fb_analyze_finish(host[i * rec:(i + 1) * rec].ctypes.data, w, h, C.byref(st)))
+        out.append({k: getattr(st, k) for k, _ in _lib.FbImageStats._fields_})
+    return out
+
+
+def analyze_scan_batch(imgs: torch.Tensor, raw: torch.Tensor) -> None:
+    """Enqueue only (what tools/bench_ops.py times): raw must hold n * fb_analyze_raw_bytes() bytes on the device."""
+    p, i_s, rs, w, h, n = _batch(imgs)
+    check(_lib.load().fb_analyze_batch_dev(_dev(imgs), _stream(imgs), p, i_s, rs, w, h, n, raw.data_ptr()))
+
+
 def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Tensor] = None,
                         kernel: Optional[np.ndarray] = None) -> torch.Tensor:
     """fennec.GaussianBlur per image (effects.go:146-220); sigma <= 0 returns `src` itself."""

@@ -1298,3 +1298,116 @@ int fb_ssim_ref_score_ycbcr(const fb_ssim_ref *ref, const uint8_t *y, int yStrid
 }
 
 }  // extern "C"
+
+// ---- Analyze (analyze.go:26-176) ----------------------------------------------------------------
+
+namespace fb {
+
+// math.Log2 as Go defines it (Frexp; 0.5 -> exp-1; else Log(frac)*(1/Ln2) + exp), with libm's log.
+static double go_log2(double x) {
+    int e;
+    double frac = frexp(x, &e);
+    if (frac == 0.5) return (double)(e - 1);
+    return log(frac) * (1.0 / 0.693147180559945309417232121458176568) + (double)e;
+}
+
+static void analyze_finish_host(const AnalyzeRaw &r, int w, int h, fb_image_stats *st) {
+    memset(st, 0, sizeof *st);
+    st->width = w;
+    st->height = h;
+    if (w <= 0 || h <= 0) return;   // analyze.go:36-38
+    AnalyzeSteps sp;
+    analyze_steps(w, h, &sp);
+    const double n = (double)((long long)w * h);
+    st->has_alpha = r.hasAlpha != 0;
+    st->is_grayscale = r.hasColour == 0;
+    st->unique_colors = (int)(r.uniqueSampled < 1024u ? r.uniqueSampled : 1024u);   // the map stops growing at 1024
+    st->mean_brightness = (double)r.sumL / 1000.0 / n;
+    const long long samples = (long long)sp.contrastNx * sp.contrastNy;
+    if (samples > 0) st->contrast = sqrt(r.varSum / (double)samples);
+    double entropy = 0.0;           // computeEntropy analyze.go:116-128, bins in ascending order
+    for (int i = 0; i < 256; i++)
+        if (r.hist[i] > 0) {
+            double p = (double)r.hist[i] / n;
+            entropy -= p * go_log2(p);
+        }
+    st->entropy = entropy;
+    const long long total = (long long)sp.edgeNx * sp.edgeNy;
+    st->edge_density = total > 0 ? (double)r.edges / (double)total : 0.0;
+    // recommendFormat / recommendQuality / estimateCompression, analyze.go:183-232
+    const int JPEG = 1, PNG = 2, Balanced = 0, High = 3, Aggressive = 4;
+    if (st->has_alpha) st->recommended_format = PNG;
+    else if (st->unique_colors <= 256) st->recommended_format = PNG;
+    else if (st->edge_density > 0.3 && st->unique_colors < 1000) st->recommended_format = PNG;
+    else st->recommended_format = JPEG;
+    if (st->entropy > 6 && st->edge_density < 0.15) st->recommended_quality = Balanced;
+    else if (st->entropy < 4) st->recommended_quality = Aggressive;
+    else if (st->edge_density > 0.25) st->recommended_quality = High;
+    else st->recommended_quality = Balanced;
+    if (st->recommended_format == PNG) {
+        if (st->unique_colors <= 256) st->estimated_compression = 5.0 + (256 - (double)st->unique_colors) / 50;
+        else if (st->is_grayscale) st->estimated_compression = 3.0;
+        else st->estimated_compression = 2.0;
+    } else {
+        double base = 10.0;
+        if (st->entropy > 7) base = 5.0;
+        else if (st->entropy > 5) base = 8.0;
+        if (st->edge_density > 0.2) base *= 0.7;
+        st->estimated_compression = base;
+    }
+}
+
+}  // namespace fb
+
+extern "C" {
+
+size_t fb_analyze_raw_bytes(void) { return sizeof(AnalyzeRaw); }
+
+int fb_analyze_finish(const void *raw_host, int w, int h, fb_image_stats *out) {
+    if (!raw_host || !out) { set_error("fb_analyze_finish: null argument"); return FB_E_INVALID; }
+    AnalyzeRaw r;
+    memcpy(&r, raw_host, sizeof r);
+    analyze_finish_host(r, w, h, out);
+    return FB_OK;
+}
+
+int fb_analyze_batch_dev(int device, void *stream, const uint8_t *imgs, int64_t imgStride, int rowStride, int w, int h,
+                         int n, void *raw) {
+    FB_TRY(check_batch("fb_analyze_batch_dev", imgs, imgStride, rowStride, w, h, n));
+    if (!raw) { set_error("fb_analyze_batch_dev: null output"); return FB_E_INVALID; }
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_analyze_batch_dev", device, &c));
+    FB_TRY(reserve(c, analyze_scratch_bytes(w, h, n), 256));
+    void *scratch = c->ws.take(analyze_scratch_bytes(w, h, n) - 512);
+    if (!scratch) { set_error("internal: workspace under-reserved (analyze)"); return FB_E_INVALID; }
+    return launch_analyze((cudaStream_t)stream, imgs, imgStride, rowStride, w, h, n, (AnalyzeRaw *)raw, scratch);
+}
+
+int fb_analyze(const uint8_t *pix, int stride, int w, int h, fb_image_stats *out) {
+    if (!out) { set_error("fb_analyze: null output"); return FB_E_INVALID; }
+    FB_TRY(check_img("fb_analyze", pix, stride, w, h));
+    if (w == 0 || h == 0) {          // analyze.go:36-38: only the dimensions are filled in
+        memset(out, 0, sizeof *out);
+        out->width = w;
+        out->height = h;
+        return FB_OK;
+    }
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h + analyze_scratch_bytes(w, h, 1) + sizeof(AnalyzeRaw) + 4096, sizeof(AnalyzeRaw) + 256));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(upload(c, pix, stride, w, h, &d, &pitch));
+    AnalyzeRaw *draw = (AnalyzeRaw *)c->ws.take(sizeof(AnalyzeRaw));
+    void *scratch = c->ws.take(analyze_scratch_bytes(w, h, 1) - 512);
+    AnalyzeRaw *pin = (AnalyzeRaw *)c->pin.take(sizeof(AnalyzeRaw));
+    if (!draw || !scratch || !pin) { set_error("internal: workspace under-reserved (analyze)"); return FB_E_INVALID; }
+    FB_TRY(launch_analyze(c->stream, d, 0, pitch, w, h, 1, draw, scratch));
+    FB_CUDA(cudaMemcpyAsync(pin, draw, sizeof(AnalyzeRaw), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    analyze_finish_host(*pin, w, h, out);
+    return FB_OK;
+}
+
+}  // extern "C"

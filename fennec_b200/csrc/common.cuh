@@ -111,6 +111,25 @@ int launch_ycbcr_to_nrgba(cudaStream_t s, const uint8_t *y, long long yImgStride
 int launch_gray_to_nrgba(cudaStream_t s, const uint8_t *g, long long gImgStride, int gStride, int w, int h, uint8_t *dst,
                          long long dstImgStride, int dstRowStride, int n);
 
+// analyze.cu — SURVEY §8(f2): the scans behind Analyze (analyze.go:26-176)
+constexpr int kAnalyzeTableSlots = 1 << 18;   // 64-bit slots of the sampled-colour table (<= 100 001 samples)
+struct AnalyzeRaw {                            // what the device produces per image; finished on the host
+    unsigned int hist[256];                    // luminance histogram, bins int(lum + 0.5)
+    unsigned long long sumL;                   // sum of 299R + 587G + 114B over all pixels (exact)
+    double varSum;                             // sum((lum - mean)^2) over the contrast grid
+    unsigned int hasAlpha, hasColour, uniqueSampled, edges;
+};
+struct AnalyzeSteps {
+    int contrastX, contrastY, contrastNx, contrastNy;
+    int edgeX, edgeY, edgeNx, edgeNy;
+    long long sampleStep;
+    int nSamples;
+};
+void analyze_steps(int w, int h, AnalyzeSteps *s);
+size_t analyze_scratch_bytes(int w, int h, int n);
+int launch_analyze(cudaStream_t s, const uint8_t *imgs, long long imgStride, int rowStride, int w, int h, int n,
+                   AnalyzeRaw *raw, void *scratch);
+
 // resize.cu
 // When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.
 struct IntRatioInfo {

@@ -286,26 +286,31 @@ __global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p)
     const bool vecOK = ((((uintptr_t)p.src | (uintptr_t)p.srcImgStride | (uintptr_t)p.srcRowStride) & 15) == 0);
     const bool dvec = ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0);
     // stage chunks -1..32 (34 chunks of 16 px) of row y with clamp-to-edge (effects.go:173-178)
+    // Block-uniform: the whole staged span lies inside the row, so every quad is one aligned 16-byte cp.async
+    // (kept separate from the clamped path — if-converted together they cost ~250 address/clamp instructions
+    // per warp-row, 18 % of the kernel).
+    const bool interiorSpan = vecOK && xs >= kTile && xs + 33 * kTile <= p.w;
     auto stage_row = [&](int y, uint8_t *st) {
         const uint8_t *srow = simg + (long long)y * p.srcRowStride;
+        if (interiorSpan) {
+            const uint8_t *g0 = srow + (long long)(xs - kTile) * 4 + lane * 16;   // quad v = lane + 32k ↔ 16 bytes at 16*v
+            uint8_t *s0 = st + (lane >> 2) * kChunkB + (lane & 3) * 16;
 #pragma unroll
-        for (int k = 0; k < (34 * 4 + 31) / 32; k++) {
-            const int v = lane + 32 * k;
-            if (v < 34 * 4) {
+            for (int k = 0; k < (34 * 4 + 31) / 32; k++)
+                if (k < 4 || lane < 34 * 4 - 128) cp_async16(s0 + k * 8 * kChunkB, g0 + k * 512);
+        } else {
+#pragma unroll 1
+            for (int v = lane; v < 34 * 4; v += 32) {
                 const int chunk = v >> 2, quad = v & 3;
                 const int px0 = xs + (chunk - 1) * kTile + quad * 4;
                 uint8_t *dstp = st + chunk * kChunkB + quad * 16;
-                if (vecOK && px0 >= 0 && px0 + 3 < p.w) {
-                    cp_async16(dstp, srow + (long long)px0 * 4);
-                } else {
-                    uint32_t t[4];
+                uint32_t t[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        int sx = min(max(px0 + i, 0), p.w - 1);
-                        t[i] = ld_nc_u32(srow + (long long)sx * 4);
-                    }
-                    *reinterpret_cast<uint4 *>(dstp) = make_uint4(t[0], t[1], t[2], t[3]);
+                for (int i = 0; i < 4; i++) {
+                    int sx = min(max(px0 + i, 0), p.w - 1);
+                    t[i] = ld_nc_u32(srow + (long long)sx * 4);
                 }
+                *reinterpret_cast<uint4 *>(dstp) = make_uint4(t[0], t[1], t[2], t[3]);
             }
         }
         cp_async_commit_group();
@@ -637,7 +642,9 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
     hsum(pPrev, hPrevRB, hPrevGA);
     hsum(pCur, hCurRB, hCurGA);
     if (MODE == 2) { lumas(pPrev, lPrev); lumas(pCur, lCur); }
-#pragma unroll 1
+    // MODE 0/1: fully unrolled so the three-row window is renamed instead of rotated with ~28 MOVs per row
+    // (the MODE 2 body is too large to replicate eight times).
+#pragma unroll (MODE == 2 ? 1 : kFxRows)
     for (int r = 0; r < kFxRows; r++) {
         const int y = yb + r;
         if (y >= p.h) break;

@@ -143,6 +143,29 @@ FB_API int fb_ssim_ref_score_ycbcr(const fb_ssim_ref *ref, const uint8_t *y, int
 FB_API int fb_ssim_ref_score_nrgba(const fb_ssim_ref *ref, const uint8_t *img, int stride, double *score);
 FB_API void fb_ssim_ref_destroy(fb_ssim_ref *ref);
 
+/* ---- Analyze — analyze.go:26-176 ---------------------------------------------- */
+
+/* The fields of fennec.ImageStats. recommended_format / recommended_quality carry Go's numeric values
+ * (types.go:36-42: JPEG = 1, PNG = 2; types.go:59-70: Balanced = 0, High = 3, Aggressive = 4). */
+typedef struct fb_image_stats {
+    int width, height;
+    int has_alpha, is_grayscale, unique_colors;
+    double entropy, edge_density, mean_brightness, contrast;
+    int recommended_format, recommended_quality;
+    double estimated_compression;
+} fb_image_stats;
+
+/* Analyze on a host NRGBA buffer. Integer fields and EdgeDensity are exact; MeanBrightness, Contrast and
+ * Entropy agree with the reference's sequential float64 sums to ~1e-12 relative (summation order, log2). */
+FB_API int fb_analyze(const uint8_t *pix, int stride, int w, int h, fb_image_stats *out);
+/* Device-resident batch: writes n raw records (fb_analyze_raw_bytes() each) to device memory `raw`;
+ * copy them to the host and turn each into ImageStats with fb_analyze_finish (host arithmetic only:
+ * entropy from the histogram, sqrt, ratios, the recommendation rules of analyze.go:183-232). */
+FB_API size_t fb_analyze_raw_bytes(void);
+FB_API int fb_analyze_batch_dev(int device, void *stream, const uint8_t *imgs, int64_t imgStride, int rowStride,
+                         int w, int h, int n, void *raw);
+FB_API int fb_analyze_finish(const void *raw_host, int w, int h, fb_image_stats *out);
+
 /* ---- device-resident batch entry points (configs 3-5 and the headline metric) ------------- */
 /* n images (or pairs) of identical dims; image i starts at base + i*imgStride bytes. All pointers
  * are device pointers on `device`; `stream` is a cudaStream_t. Scores land in device memory. */

@@ -871,3 +871,131 @@ void fo_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst,
             o[3] = 0xff;
         }
 }
+
+/* ---- §8(f2): Analyze (analyze.go:26-176) — the measured part: one full scan + two sampled scans ------------
+ * Sequential, source order, binary64 unfused — exactly as the Go loops.  math.Log2 is Go's own
+ * (Frexp; frac == 0.5 -> exp-1; else Log(frac)*(1/Ln2) + exp), restated with libm's log: entropy may differ from Go
+ * in the last bits (both logs are < 1 ulp), which is why the GPU parity bar on Entropy is a tolerance.
+ * The recommendations (analyze.go:183-232) are host logic on these numbers and are restated too. */
+
+static double fo_go_log2(double x) {
+    int e;
+    double frac = frexp(x, &e);
+    if (frac == 0.5) return (double)(e - 1);
+    return log(frac) * (1.0 / 0.693147180559945309417232121458176568) + (double)e;
+}
+
+static double fo_lum_at(const uint8_t *pix, int stride, int x, int y) {   /* analyze.go:178-181 */
+    const uint8_t *p = pix + (size_t)y * stride + (size_t)x * 4;
+    return 0.299 * (double)p[0] + 0.587 * (double)p[1] + 0.114 * (double)p[2];
+}
+
+static int fo_cmp_u32(const void *a, const void *b) {
+    uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* Numeric values are Go's (types.go:36-42, 59-70): Format Auto=0 JPEG=1 PNG=2; Quality Balanced=0 Lossless=1 Ultra=2 High=3 Aggressive=4 */
+#define FO_JPEG 1
+#define FO_PNG 2
+#define FO_BALANCED 0
+#define FO_HIGH 3
+#define FO_AGGRESSIVE 4
+void fo_recommend(fo_image_stats *st) {
+    /* recommendFormat analyze.go:183-194 */
+    if (st->has_alpha) st->recommended_format = FO_PNG;
+    else if (st->unique_colors <= 256) st->recommended_format = FO_PNG;
+    else if (st->edge_density > 0.3 && st->unique_colors < 1000) st->recommended_format = FO_PNG;
+    else st->recommended_format = FO_JPEG;
+    /* recommendQuality analyze.go:196-207 */
+    if (st->entropy > 6 && st->edge_density < 0.15) st->recommended_quality = FO_BALANCED;
+    else if (st->entropy < 4) st->recommended_quality = FO_AGGRESSIVE;
+    else if (st->edge_density > 0.25) st->recommended_quality = FO_HIGH;
+    else st->recommended_quality = FO_BALANCED;
+    /* estimateCompression analyze.go:209-232 */
+    if (st->recommended_format == FO_PNG) {
+        if (st->unique_colors <= 256) st->estimated_compression = 5.0 + (256 - (double)st->unique_colors) / 50;
+        else if (st->is_grayscale) st->estimated_compression = 3.0;
+        else st->estimated_compression = 2.0;
+    } else {
+        double base = 10.0;
+        if (st->entropy > 7) base = 5.0;
+        else if (st->entropy > 5) base = 8.0;
+        if (st->edge_density > 0.2) base *= 0.7;
+        st->estimated_compression = base;
+    }
+}
+
+void fo_analyze(const uint8_t *pix, int stride, int w, int h, fo_image_stats *st) {
+    memset(st, 0, sizeof *st);
+    st->width = w;
+    st->height = h;
+    if (w == 0 || h == 0) return;                       /* analyze.go:36-38 */
+    double bright = 0.0;
+    const int max_sample = 50000;
+    long long step = 1;
+    if ((long long)w * h > max_sample) step = (long long)w * h / max_sample;
+    /* the map[uint32]struct{} capped at 1024 entries: collect the sampled keys in scan order, stop at 1024 distinct */
+    uint32_t *keys = (uint32_t *)malloc(sizeof(uint32_t) * 1024);
+    int nkeys = 0;
+    int all_gray = 1, has_alpha = 0;
+    long long idx = 0;
+    for (int y = 0; y < h; y++) {
+        const uint8_t *row = pix + (size_t)y * stride;
+        for (int x = 0; x < w; x++) {
+            uint8_t r = row[4 * x], g = row[4 * x + 1], b = row[4 * x + 2], a = row[4 * x + 3];
+            double lum = 0.299 * (double)r + 0.587 * (double)g + 0.114 * (double)b;
+            bright += lum;
+            st->histogram[(int)(lum + 0.5)] += 1.0;
+            if (a < 255) has_alpha = 1;
+            if (r != g || g != b) all_gray = 0;
+            if (idx % step == 0 && nkeys < 1024) {
+                uint32_t key = (uint32_t)r << 24 | (uint32_t)g << 16 | (uint32_t)b << 8 | (uint32_t)a;
+                int found = 0;
+                for (int k = 0; k < nkeys; k++) if (keys[k] == key) { found = 1; break; }
+                if (!found) keys[nkeys++] = key;
+            }
+            idx++;
+        }
+    }
+    (void)fo_cmp_u32;
+    free(keys);
+    double n = (double)((long long)w * h);
+    st->has_alpha = has_alpha;
+    st->is_grayscale = all_gray;
+    st->unique_colors = nkeys;
+    st->mean_brightness = bright / n;
+    int step_y = (int)fmax(1, ceil((double)h / 100));
+    int step_x = (int)fmax(1, ceil((double)w / 100));
+    double var_sum = 0.0, mean = st->mean_brightness;
+    int samples = 0;
+    for (int y = 0; y < h; y += step_y)
+        for (int x = 0; x < w; x += step_x) {
+            double d = fo_lum_at(pix, stride, x, y) - mean;
+            var_sum += d * d;
+            samples++;
+        }
+    if (samples > 0) st->contrast = sqrt(var_sum / (double)samples);
+    double entropy = 0.0;                                /* computeEntropy analyze.go:116-128 */
+    for (int i = 0; i < 256; i++)
+        if (st->histogram[i] > 0) {
+            double p = st->histogram[i] / n;
+            entropy -= p * fo_go_log2(p);
+        }
+    st->entropy = entropy;
+    if (w >= 3 && h >= 3) {                              /* computeEdgeDensity analyze.go:131-176 */
+        int sx = (int)fmax(1, (double)w / 200), sy = (int)fmax(1, (double)h / 200);
+        int edges = 0, total = 0;
+        for (int y = 1; y < h - 1; y += sy)
+            for (int x = 1; x < w - 1; x += sx) {
+#define L(xx, yy) fo_lum_at(pix, stride, (xx), (yy))
+                double gx = L(x + 1, y - 1) - L(x - 1, y - 1) + 2 * L(x + 1, y) - 2 * L(x - 1, y) + L(x + 1, y + 1) - L(x - 1, y + 1);
+                double gy = L(x - 1, y + 1) - L(x - 1, y - 1) + 2 * L(x, y + 1) - 2 * L(x, y - 1) + L(x + 1, y + 1) - L(x + 1, y - 1);
+#undef L
+                if (sqrt(gx * gx + gy * gy) > 30.0) edges++;
+                total++;
+            }
+        if (total > 0) st->edge_density = (double)edges / (double)total;
+    }
+    fo_recommend(st);
+}

@@ -109,6 +109,19 @@ int fo_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const ui
                       int w, int h, int ratio, uint8_t *dst, int dstStride);
 void fo_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride);
 
+/* Analyze (analyze.go:26-176) and the recommendation rules (analyze.go:183-232). */
+typedef struct {
+    int width, height;
+    int has_alpha, is_grayscale, unique_colors;
+    double entropy, edge_density, mean_brightness, contrast;
+    int recommended_format;   /* Go's Format value: 1 = JPEG, 2 = PNG (types.go:36-42) */
+    int recommended_quality;  /* Go's Quality value: 0 = Balanced, 3 = High, 4 = Aggressive (types.go:59-70) */
+    double estimated_compression;
+    double histogram[256];    /* luminance histogram, bins int(lum + 0.5) */
+} fo_image_stats;
+void fo_analyze(const uint8_t *pix, int stride, int w, int h, fo_image_stats *st);
+void fo_recommend(fo_image_stats *st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -431,3 +431,58 @@ def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
     out[..., 0] = out[..., 1] = out[..., 2] = g
     out[..., 3] = 255
     return out
+
+
+# ---- §8(f2): Analyze (analyze.go:26-176) --------------------------------------------------------------------
+# Independent restatement: vectorised per-pixel float64 luminance, np.cumsum for the SEQUENTIAL sums (cumsum adds in
+# order, unlike np.sum's pairwise reduction), a dict-free distinct count for the capped colour set.
+
+def _lum(img: np.ndarray) -> np.ndarray:
+    p = img.astype(np.float64)
+    return (0.299 * p[..., 0] + 0.587 * p[..., 1]) + 0.114 * p[..., 2]
+
+
+def _go_log2(x: float) -> float:
+    frac, e = math.frexp(x)
+    if frac == 0.5:
+        return float(e - 1)
+    return math.log(frac) * (1.0 / math.log(2.0)) + float(e)
+
+
+def analyze(img: np.ndarray) -> dict:
+    h, w = img.shape[:2]
+    st = dict(width=w, height=h, has_alpha=0, is_grayscale=0, unique_colors=0, entropy=0.0, edge_density=0.0,
+              mean_brightness=0.0, contrast=0.0)
+    if w == 0 or h == 0:
+        return st
+    lum = _lum(img)
+    n = float(w * h)
+    st["mean_brightness"] = float(np.cumsum(lum.ravel())[-1]) / n
+    hist = np.bincount((lum + 0.5).astype(np.int64).ravel(), minlength=256).astype(np.float64)
+    st["histogram"] = hist
+    st["has_alpha"] = int((img[..., 3] < 255).any())
+    st["is_grayscale"] = int(((img[..., 0] == img[..., 1]) & (img[..., 1] == img[..., 2])).all())
+    step = (w * h) // 50000 if w * h > 50000 else 1
+    flat = img.reshape(-1, 4)[::step].astype(np.uint32)
+    keys = flat[:, 0] << 24 | flat[:, 1] << 16 | flat[:, 2] << 8 | flat[:, 3]
+    # the map stops growing at 1024 entries: the count is min(distinct among the sampled keys, 1024)
+    st["unique_colors"] = int(min(len(np.unique(keys)), 1024))
+    sy, sx = int(max(1, math.ceil(h / 100))), int(max(1, math.ceil(w / 100)))
+    d = lum[::sy, ::sx] - st["mean_brightness"]
+    dd = (d * d).ravel()
+    st["contrast"] = math.sqrt(float(np.cumsum(dd)[-1]) / float(dd.size))
+    ent = 0.0
+    for c in hist:
+        if c > 0:
+            p = c / n
+            ent -= p * _go_log2(p)
+    st["entropy"] = ent
+    if w >= 3 and h >= 3:
+        ex, ey = int(max(1, w / 200)), int(max(1, h / 200))
+        ys, xs = np.arange(1, h - 1, ey), np.arange(1, w - 1, ex)
+        L = lambda dx, dy: lum[np.ix_(ys + dy, xs + dx)]  # noqa: E731
+        gx = ((((L(1, -1) - L(-1, -1)) + 2 * L(1, 0)) - 2 * L(-1, 0)) + L(1, 1)) - L(-1, 1)
+        gy = ((((L(-1, 1) - L(-1, -1)) + 2 * L(0, 1)) - 2 * L(0, -1)) + L(1, 1)) - L(1, -1)
+        mag = np.sqrt(gx * gx + gy * gy)
+        st["edge_density"] = float((mag > 30.0).sum()) / float(mag.size)
+    return st

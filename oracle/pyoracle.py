@@ -26,6 +26,13 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+class FoImageStats(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("has_alpha", C.c_int), ("is_grayscale", C.c_int),
+                ("unique_colors", C.c_int), ("entropy", C.c_double), ("edge_density", C.c_double),
+                ("mean_brightness", C.c_double), ("contrast", C.c_double), ("recommended_format", C.c_int),
+                ("recommended_quality", C.c_int), ("estimated_compression", C.c_double), ("histogram", C.c_double * 256)]
+
+
 _lib = None
 _u8p = C.POINTER(C.c_uint8)
 _dp = C.POINTER(C.c_double)
@@ -67,6 +74,8 @@ def lib():
         L.fo_resize_v.argtypes = img + [C.c_int, C.c_int] + img + [C.c_int]
         L.fo_lanczos_resize.argtypes = img + [C.c_int, C.c_int] + img + [C.c_int, C.c_int]
         L.fo_smart_resize_dims.argtypes = [C.c_int] * 4 + [_ip, _ip]
+        L.fo_analyze.argtypes = img + [C.c_int, C.c_int, C.POINTER(FoImageStats)]
+        L.fo_analyze.restype = None
         L.fo_ycbcr_to_nrgba.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.fo_gray_to_nrgba.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         _lib = L
@@ -273,3 +282,16 @@ def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
     pd, sd = _img(dst)
     lib().fo_gray_to_nrgba(pg, sg, w, h, pd, sd)
     return dst
+
+
+def analyze(img: np.ndarray) -> dict:
+    """Analyze (analyze.go:26-176) → dict of the ImageStats fields (+ the luminance histogram)."""
+    st = FoImageStats()
+    if img.size == 0:
+        lib().fo_analyze(None, 0, img.shape[1] if img.ndim == 3 else 0, 0, C.byref(st))
+    else:
+        p, s = _img(img)
+        lib().fo_analyze(p, s, img.shape[1], img.shape[0], C.byref(st))
+    d = {k: getattr(st, k) for k, _ in FoImageStats._fields_ if k != "histogram"}
+    d["histogram"] = np.array(st.histogram[:], dtype=np.float64)
+    return d

@@ -90,6 +90,13 @@ if want("ycbcr"):
     print(json.dumps({"op": "search iteration e2e 4032x3024 (config 2), pageable host buffers", "ms_fb_ssim_fast_both_nrgba": round(ms_ref, 3),
                       "ms_session_ycbcr420": round(ms_ses, 3), "ms_session_nrgba": round(ms_ses_n, 3),
                       "h2d_bytes": {"fb_ssim_fast": 2 * 4032 * 3024 * 4, "session_ycbcr420": int(4032 * 3024 * 1.5), "session_nrgba": 4032 * 3024 * 4}}), flush=True)
+if want("analyze"):
+    # the scans behind Analyze, device-resident (4 B/px read once + sampled reads)
+    x = noise(16, 2160, 3840, 12)
+    from fennec_b200 import _lib
+    raw = torch.empty(16 * int(_lib.load().fb_analyze_raw_bytes()), dtype=torch.uint8, device="cuda")
+    report("Analyze scans 3840x2160 (f2)", timeit(lambda: batch.analyze_scan_batch(x, raw), 20), 16, 8.2944, 3840 * 2160 * 4)
+    del x, raw
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
     report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)

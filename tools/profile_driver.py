@@ -36,6 +36,9 @@ for _ in range(args.iters):
         r = batch.sharpen_batch(a, 0.5)
     elif args.op == "adaptive":
         r = batch.adaptive_sharpen_batch(a, 0.5)
+    elif args.op == "analyze":
+        r = torch.empty(args.pairs * 2048, dtype=torch.uint8, device="cuda")
+        batch.analyze_scan_batch(a, r)
     elif args.op == "lanczos":
         r = batch.lanczos_resize_batch(a, args.w // 4, args.h // 4)
     elif args.op == "box":
