@@ -64,12 +64,22 @@ __global__ void __launch_bounds__(kScanThreads) analyze_scan_kernel(const uint8_
     for (int y = y0; y < y1; y++) {
         const uint8_t *row = base + (long long)y * rowStride;
         if (vecOK) {
-            for (int x = threadIdx.x * 4; x < w; x += kScanThreads * 4) {
-                if (x + 4 <= w) {
-                    const uint4 q = ld_nc_u128(row + (long long)x * 4);
-                    px1(q.x); px1(q.y); px1(q.z); px1(q.w);
-                } else {
-                    for (int i = 0; x + i < w; i++) px1(ld_nc_u32(row + (long long)(x + i) * 4));
+            // four independent 128-bit loads in flight per thread (one 4096-pixel sweep of the row per iteration)
+            for (int xb = threadIdx.x * 4; xb < w; xb += kScanThreads * 16) {
+                uint4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int x = xb + u * kScanThreads * 4;
+                    q[u] = (x + 4 <= w) ? ld_nc_u128(row + (long long)x * 4) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int x = xb + u * kScanThreads * 4;
+                    if (x + 4 <= w) {
+                        px1(q[u].x); px1(q[u].y); px1(q[u].z); px1(q[u].w);
+                    } else {
+                        for (int i = 0; x + i < w; i++) px1(ld_nc_u32(row + (long long)(x + i) * 4));
+                    }
                 }
             }
         } else {

@@ -179,3 +179,24 @@ func (s *ssimSession) score(decoded image.Image) (float64, bool) {
 }
 
 func (s *ssimSession) Close() { C.fb_ssim_ref_destroy(s.h); s.h = nil }
+
+// ---- SURVEY §8(f2): Analyze (analyze.go:26-113) ---------------------------------------------------------
+
+// gpuAnalyze replaces the three scans of Analyze; ok=false → run the pure-Go body.  The recommendation rules
+// (analyze.go:183-232) are evaluated inside the library with the same thresholds, and the Go-typed values are
+// rebuilt here from their numeric constants.
+func gpuAnalyze(src *image.NRGBA) (ImageStats, bool) {
+	var st C.fb_image_stats
+	rc := C.fb_analyze(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()), &st)
+	if rc != C.FB_OK {
+		return ImageStats{}, false
+	}
+	return ImageStats{
+		Width: int(st.width), Height: int(st.height),
+		HasAlpha: st.has_alpha != 0, IsGrayscale: st.is_grayscale != 0, UniqueColors: int(st.unique_colors),
+		Entropy: float64(st.entropy), EdgeDensity: float64(st.edge_density),
+		MeanBrightness: float64(st.mean_brightness), Contrast: float64(st.contrast),
+		RecommendedFormat: Format(st.recommended_format), RecommendedQuality: Quality(st.recommended_quality),
+		EstimatedCompression: float64(st.estimated_compression),
+	}, true
+}
