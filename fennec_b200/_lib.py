@@ -74,6 +74,10 @@ PROTOTYPES = {
     "fb_analyze_raw_bytes": (C.c_size_t, []),
     "fb_analyze_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fb_analyze_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FbImageStats)]),
+    "fb_orientation_dims": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
+    "fb_apply_orientation": (C.c_int, _IMG + [C.c_int, C.c_int, C.c_int] + _IMG),
+    "fb_apply_orientation_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     "fb_ssim_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_ssim_fast_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_msssim_batch_dev": (C.c_int, _BATCH_SCORE),

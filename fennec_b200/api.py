@@ -319,3 +319,21 @@ def Analyze(img: np.ndarray) -> dict:
         p, stride, w, h = _img(img)
         check(_lib.load().fb_analyze(p, stride, w, h, C.byref(st)))
     return _stats_dict(st)
+
+
+# ---- exif.go:176-203 ---------------------------------------------------------------------------------
+
+ORIENT_NORMAL, ORIENT_FLIP_H, ORIENT_ROTATE_180, ORIENT_FLIP_V = 1, 2, 3, 4          # exif.go:12-21
+ORIENT_TRANSPOSE, ORIENT_ROTATE_90CW, ORIENT_TRANSVERSE, ORIENT_ROTATE_270CW = 5, 6, 7, 8
+
+
+def ApplyOrientation(img: np.ndarray, orient: int) -> np.ndarray:
+    """fennec.ApplyOrientation (exif.go:176-203); orientations 1, 0 and unknown values return `img` itself."""
+    p, stride, w, h = _img(img)
+    dw, dh = C.c_int(), C.c_int()
+    if check(_lib.load().fb_orientation_dims(orient, w, h, C.byref(dw), C.byref(dh))) == FB_IDENTITY:
+        return img
+    dst = _new(dh.value, dw.value)
+    pd, sd, _, _ = _img(dst)
+    check(_lib.load().fb_apply_orientation(p, stride, w, h, orient, pd, sd if dst.size else dw.value * 4))
+    return dst

@@ -124,6 +124,19 @@ def analyze_scan_batch(imgs: torch.Tensor, raw: torch.Tensor) -> None:
     check(_lib.load().fb_analyze_batch_dev(_dev(imgs), _stream(imgs), p, i_s, rs, w, h, n, raw.data_ptr()))
 
 
+def apply_orientation_batch(src: torch.Tensor, orient: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fennec.ApplyOrientation (exif.go:176-203) per image; identity orientations return `src` itself."""
+    ps, i_s, rs, w, h, n = _batch(src)
+    if orient < 2 or orient > 8:
+        return src
+    dw, dh = (h, w) if orient >= 5 else (w, h)
+    if out is None:
+        out = torch.empty((n, dh, dw, 4), dtype=torch.uint8, device=src.device)
+    pd, i_d, rd, _, _, _ = _batch(out)
+    check(_lib.load().fb_apply_orientation_batch_dev(_dev(src), _stream(src), ps, i_s, rs, w, h, orient, pd, i_d, rd, n))
+    return out
+
+
 def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Tensor] = None,
                         kernel: Optional[np.ndarray] = None) -> torch.Tensor:
     """fennec.GaussianBlur per image (effects.go:146-220); sigma <= 0 returns `src` itself."""

@@ -1411,3 +1411,49 @@ int fb_analyze(const uint8_t *pix, int stride, int w, int h, fb_image_stats *out
 }
 
 }  // extern "C"
+
+// ---- ApplyOrientation (exif.go:176-203) --------------------------------------------------------
+
+extern "C" {
+
+int fb_orientation_dims(int orient, int w, int h, int *dstW, int *dstH) {
+    if (!dstW || !dstH) { set_error("fb_orientation_dims: null output"); return FB_E_INVALID; }
+    *dstW = w;
+    *dstH = h;
+    return orient_dims(orient, w, h, dstW, dstH) ? FB_OK : FB_IDENTITY;
+}
+
+int fb_apply_orientation(const uint8_t *src, int srcStride, int w, int h, int orient, uint8_t *dst, int dstStride) {
+    int dw, dh;
+    if (!orient_dims(orient, w, h, &dw, &dh)) return FB_IDENTITY;
+    FB_TRY(check_img("fb_apply_orientation", src, srcStride, w, h));
+    FB_TRY(check_img("fb_apply_orientation", dst, dstStride, dw, dh));
+    if (w == 0 || h == 0) return FB_OK;
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h + (size_t)dev_pitch(dw) * dh + 4096, 256));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(upload(c, src, srcStride, w, h, &d, &pitch));
+    const int opitch = dev_pitch(dw);
+    uint8_t *o = (uint8_t *)c->ws.take((size_t)opitch * dh + 16);
+    if (!o) { set_error("internal: workspace under-reserved (orientation)"); return FB_E_INVALID; }
+    FB_TRY(launch_orient(c->stream, d, 0, pitch, w, h, orient, o, 0, opitch, 1));
+    FB_TRY(download(c, o, opitch, dst, dstStride, dw, dh));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_apply_orientation_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride, int srcRowStride,
+                                   int w, int h, int orient, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int n) {
+    int dw, dh;
+    if (!orient_dims(orient, w, h, &dw, &dh)) return FB_IDENTITY;
+    FB_TRY(check_batch("fb_apply_orientation_batch_dev", src, srcImgStride, srcRowStride, w, h, n));
+    FB_TRY(check_batch("fb_apply_orientation_batch_dev", dst, dstImgStride, dstRowStride, dw, dh, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_apply_orientation_batch_dev", device, &c));
+    return launch_orient((cudaStream_t)stream, src, srcImgStride, srcRowStride, w, h, orient, dst, dstImgStride, dstRowStride, n);
+}
+
+}  // extern "C"

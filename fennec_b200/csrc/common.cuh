@@ -130,6 +130,11 @@ size_t analyze_scratch_bytes(int w, int h, int n);
 int launch_analyze(cudaStream_t s, const uint8_t *imgs, long long imgStride, int rowStride, int w, int h, int n,
                    AnalyzeRaw *raw, void *scratch);
 
+// orient.cu — SURVEY §8(f4): ApplyOrientation (exif.go:176-203, convert.go:186-256)
+bool orient_dims(int orient, int w, int h, int *dw, int *dh);
+int launch_orient(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int w, int h, int orient,
+                  uint8_t *dst, long long dstImgStride, int dstRowStride, int n);
+
 // resize.cu
 // When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.
 struct IntRatioInfo {

@@ -166,6 +166,17 @@ FB_API int fb_analyze_batch_dev(int device, void *stream, const uint8_t *imgs, i
                          int w, int h, int n, void *raw);
 FB_API int fb_analyze_finish(const void *raw_host, int w, int h, fb_image_stats *out);
 
+/* ---- ApplyOrientation — exif.go:176-203 (rotate / flip loops convert.go:186-256) ---- */
+
+/* `orient` is the EXIF orientation value (exif.go:12-21: 2 FlipH, 3 Rotate180, 4 FlipV, 5 Transpose,
+ * 6 Rotate90CW, 7 Transverse, 8 Rotate270CW). FB_IDENTITY for 1, 0 and unknown values (the reference returns
+ * its input). dst must be dstW x dstH as reported by fb_orientation_dims (axes swap for 5-8). */
+FB_API int fb_orientation_dims(int orient, int w, int h, int *dstW, int *dstH);
+FB_API int fb_apply_orientation(const uint8_t *src, int srcStride, int w, int h, int orient, uint8_t *dst, int dstStride);
+FB_API int fb_apply_orientation_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride,
+                                   int srcRowStride, int w, int h, int orient, uint8_t *dst, int64_t dstImgStride,
+                                   int dstRowStride, int n);
+
 /* ---- device-resident batch entry points (configs 3-5 and the headline metric) ------------- */
 /* n images (or pairs) of identical dims; image i starts at base + i*imgStride bytes. All pointers
  * are device pointers on `device`; `stream` is a cudaStream_t. Scores land in device memory. */

@@ -999,3 +999,39 @@ void fo_analyze(const uint8_t *pix, int stride, int w, int h, fo_image_stats *st
     }
     fo_recommend(st);
 }
+
+/* ---- §8(f4): ApplyOrientation (exif.go:176-203) through the loops of convert.go:186-256 -------------------------
+ * dst must hold the oriented image (w x h, or h x w for orientations 5-8).  Returns 1 when the reference returns
+ * its input (orientations 1, 0, unknown), dst untouched. */
+static void fo_perm(const uint8_t *src, int ss, int w, int h, uint8_t *dst, int ds, int kind) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t so = (size_t)y * ss + (size_t)x * 4, d;
+            switch (kind) {
+                case 0: d = (size_t)x * ds + (size_t)(h - 1 - y) * 4; break;           /* rotate90CW  convert.go:186-198 */
+                case 1: d = (size_t)(h - 1 - y) * ds + (size_t)(w - 1 - x) * 4; break; /* rotate180    :201-213 */
+                case 2: d = (size_t)(w - 1 - x) * ds + (size_t)y * 4; break;           /* rotate270CW  :216-226 */
+                case 3: d = (size_t)y * ds + (size_t)(w - 1 - x) * 4; break;           /* flipH        :229-241 */
+                default: d = (size_t)(h - 1 - y) * ds + (size_t)x * 4; break;          /* flipV        :244-255 */
+            }
+            memcpy(dst + d, src + so, 4);
+        }
+}
+
+int fo_apply_orientation(const uint8_t *src, int ss, int w, int h, int orient, uint8_t *dst, int ds) {
+    switch (orient) {
+        case 2: fo_perm(src, ss, w, h, dst, ds, 3); return 0;
+        case 3: fo_perm(src, ss, w, h, dst, ds, 1); return 0;
+        case 4: fo_perm(src, ss, w, h, dst, ds, 4); return 0;
+        case 6: fo_perm(src, ss, w, h, dst, ds, 0); return 0;
+        case 8: fo_perm(src, ss, w, h, dst, ds, 2); return 0;
+        case 5: case 7: {   /* rotate, then flipH of the rotated (h x w) image: exif.go:187-196 */
+            uint8_t *tmp = (uint8_t *)malloc((size_t)h * 4 * (size_t)w + 4);
+            fo_perm(src, ss, w, h, tmp, h * 4, orient == 5 ? 2 : 0);
+            fo_perm(tmp, h * 4, h, w, dst, ds, 3);
+            free(tmp);
+            return 0;
+        }
+        default: return 1;
+    }
+}

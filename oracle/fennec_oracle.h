@@ -122,6 +122,9 @@ typedef struct {
 void fo_analyze(const uint8_t *pix, int stride, int w, int h, fo_image_stats *st);
 void fo_recommend(fo_image_stats *st);
 
+/* ApplyOrientation (exif.go:176-203); returns 1 for the identity orientations. */
+int fo_apply_orientation(const uint8_t *src, int srcStride, int w, int h, int orient, uint8_t *dst, int dstStride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -486,3 +486,16 @@ def analyze(img: np.ndarray) -> dict:
         mag = np.sqrt(gx * gx + gy * gy)
         st["edge_density"] = float((mag > 30.0).sum()) / float(mag.size)
     return st
+
+
+# ---- §8(f4): ApplyOrientation (exif.go:176-203) with array operations instead of the reference's index loops ----
+
+def apply_orientation(img: np.ndarray, orient: int) -> np.ndarray:
+    rot90cw = lambda a: np.rot90(a, k=-1)      # noqa: E731  convert.go:186-198
+    rot270cw = lambda a: np.rot90(a, k=1)      # noqa: E731  convert.go:216-226
+    fliph = lambda a: a[:, ::-1]               # noqa: E731  convert.go:229-241
+    ops = {2: fliph, 3: lambda a: a[::-1, ::-1], 4: lambda a: a[::-1], 5: lambda a: fliph(rot270cw(a)), 6: rot90cw,
+           7: lambda a: fliph(rot90cw(a)), 8: rot270cw}
+    if orient not in ops:
+        return img
+    return np.ascontiguousarray(ops[orient](img))

@@ -76,6 +76,7 @@ def lib():
         L.fo_smart_resize_dims.argtypes = [C.c_int] * 4 + [_ip, _ip]
         L.fo_analyze.argtypes = img + [C.c_int, C.c_int, C.POINTER(FoImageStats)]
         L.fo_analyze.restype = None
+        L.fo_apply_orientation.argtypes = img + [C.c_int, C.c_int, C.c_int] + img
         L.fo_ycbcr_to_nrgba.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.fo_gray_to_nrgba.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         _lib = L
@@ -295,3 +296,15 @@ def analyze(img: np.ndarray) -> dict:
     d = {k: getattr(st, k) for k, _ in FoImageStats._fields_ if k != "histogram"}
     d["histogram"] = np.array(st.histogram[:], dtype=np.float64)
     return d
+
+
+def apply_orientation(src: np.ndarray, orient: int) -> np.ndarray:
+    """ApplyOrientation (exif.go:176-203); identity orientations return `src` itself."""
+    h, w = src.shape[:2]
+    if orient < 2 or orient > 8:
+        return src
+    dst = _new(w, h) if orient >= 5 else _new(h, w)
+    ps, ss = _img(src)
+    pd, sd = _img(dst)
+    assert lib().fo_apply_orientation(ps, ss, w, h, orient, pd, sd) == 0
+    return dst

@@ -97,6 +97,13 @@ if want("analyze"):
     raw = torch.empty(16 * int(_lib.load().fb_analyze_raw_bytes()), dtype=torch.uint8, device="cuda")
     report("Analyze scans 3840x2160 (f2)", timeit(lambda: batch.analyze_scan_batch(x, raw), 20), 16, 8.2944, 3840 * 2160 * 4)
     del x, raw
+if want("orient"):
+    x = noise(16, 2160, 3840, 13)
+    y = torch.empty((16, 3840, 2160, 4), dtype=torch.uint8, device="cuda")
+    z = torch.empty_like(x)
+    report("ApplyOrientation Rotate90CW 3840x2160 (f4)", timeit(lambda: batch.apply_orientation_batch(x, 6, out=y), 20), 16, 8.2944, 2 * 3840 * 2160 * 4)
+    report("ApplyOrientation FlipH 3840x2160 (f4)", timeit(lambda: batch.apply_orientation_batch(x, 2, out=z), 20), 16, 8.2944, 2 * 3840 * 2160 * 4)
+    del x, y, z
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
     report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)
