@@ -78,6 +78,9 @@ PROTOTYPES = {
     "fb_apply_orientation": (C.c_int, _IMG + [C.c_int, C.c_int, C.c_int] + _IMG),
     "fb_apply_orientation_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p, C.c_int64, C.c_int, C.c_int]),
+    "fb_apply_palette": (C.c_int, _IMG + [C.c_int, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]),
+    "fb_apply_palette_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     "fb_ssim_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_ssim_fast_batch_dev": (C.c_int, _BATCH_SCORE),
     "fb_msssim_batch_dev": (C.c_int, _BATCH_SCORE),

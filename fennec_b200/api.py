@@ -337,3 +337,19 @@ def ApplyOrientation(img: np.ndarray, orient: int) -> np.ndarray:
     pd, sd, _, _ = _img(dst)
     check(_lib.load().fb_apply_orientation(p, stride, w, h, orient, pd, sd if dst.size else dw.value * 4))
     return dst
+
+
+# ---- targetsize.go:479-545 ---------------------------------------------------------------------------
+
+def apply_palette(src: np.ndarray, palette: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """applyPalette + palettedToNRGBA (targetsize.go:479-545): (indices (h, w) uint8, reconstruction (h, w, 4)).
+    `palette` is (ncolors, 4) uint8 NRGBA with alpha 255 — what medianCut returns."""
+    pal = np.ascontiguousarray(palette, dtype=np.uint8)
+    if pal.ndim != 2 or pal.shape[1] != 4:
+        raise TypeError("palette must have shape (ncolors, 4)")
+    p, stride, w, h = _img(src)
+    idx = np.zeros((h, w), dtype=np.uint8)
+    dst = _new(h, w)
+    pd, sd, _, _ = _img(dst)
+    check(_lib.load().fb_apply_palette(p, stride, w, h, pal.ctypes.data_as(u8p), pal.shape[0], idx.ctypes.data_as(u8p), w, pd, sd))
+    return idx, dst

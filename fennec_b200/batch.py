@@ -137,6 +137,19 @@ def apply_orientation_batch(src: torch.Tensor, orient: int, out: Optional[torch.
     return out
 
 
+def apply_palette_batch(src: torch.Tensor, palettes: torch.Tensor, ncolors: int):
+    """applyPalette + palettedToNRGBA per image; palettes: (n, 256, 4) uint8 on the device → (indices (n,h,w), NRGBA)."""
+    ps, i_s, rs, w, h, n = _batch(src)
+    if not (palettes.is_cuda and palettes.dtype == torch.uint8 and tuple(palettes.shape) == (n, 256, 4) and palettes.is_contiguous()):
+        raise TypeError("palettes must be a contiguous CUDA uint8 tensor of shape (n, 256, 4)")
+    idx = torch.empty((n, h, w), dtype=torch.uint8, device=src.device)
+    out = torch.empty_like(src)
+    po, i_o, ro, _, _, _ = _batch(out)
+    check(_lib.load().fb_apply_palette_batch_dev(_dev(src), _stream(src), ps, i_s, rs, w, h, n, palettes.data_ptr(), ncolors,
+                                                 idx.data_ptr(), int(idx.stride(0)), int(idx.stride(1)), po, i_o, ro))
+    return idx, out
+
+
 def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Tensor] = None,
                         kernel: Optional[np.ndarray] = None) -> torch.Tensor:
     """fennec.GaussianBlur per image (effects.go:146-220); sigma <= 0 returns `src` itself."""

@@ -1457,3 +1457,60 @@ int fb_apply_orientation_batch_dev(int device, void *stream, const uint8_t *src,
 }
 
 }  // extern "C"
+
+// ---- applyPalette + palettedToNRGBA (targetsize.go:479-545) ------------------------------------
+
+extern "C" {
+
+static int check_palette(const char *fn, const uint8_t *palette, int ncolors, bool host) {
+    if (!palette || ncolors < 1 || ncolors > 256) { set_error("%s: palette must hold 1..256 entries", fn); return FB_E_INVALID; }
+    if (host)
+        for (int i = 0; i < ncolors; i++)
+            if (palette[4 * i + 3] != 255) { set_error("%s: palette entry %d has alpha %d (medianCut produces 255)", fn, i, palette[4 * i + 3]); return FB_E_INVALID; }
+    return FB_OK;
+}
+
+int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint8_t *palette, int ncolors,
+                     uint8_t *indices, int idxStride, uint8_t *dst, int dstStride) {
+    FB_TRY(check_palette("fb_apply_palette", palette, ncolors, true));
+    FB_TRY(check_img("fb_apply_palette", src, srcStride, w, h));
+    if (dst) FB_TRY(check_img("fb_apply_palette", dst, dstStride, w, h));
+    if (indices && idxStride < w) { set_error("fb_apply_palette: index stride %d < w", idxStride); return FB_E_INVALID; }
+    if (w == 0 || h == 0) return FB_OK;
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    const int ipitch = (int)align_up((size_t)w, 16);
+    FB_TRY(reserve(c, 2 * ((size_t)dev_pitch(w) * h + 512) + (size_t)ipitch * h + 4096, 2048));
+    uint8_t *d;
+    int pitch;
+    FB_TRY(upload(c, src, srcStride, w, h, &d, &pitch));
+    uint8_t *dpal = (uint8_t *)c->ws.take(1024);
+    uint8_t *ppin = (uint8_t *)c->pin.take(1024);
+    uint8_t *didx = indices ? (uint8_t *)c->ws.take((size_t)ipitch * h) : nullptr;
+    uint8_t *dout = dst ? (uint8_t *)c->ws.take((size_t)pitch * h + 16) : nullptr;
+    if (!dpal || !ppin || (indices && !didx) || (dst && !dout)) { set_error("internal: workspace under-reserved (palette)"); return FB_E_INVALID; }
+    memset(ppin, 0, 1024);
+    memcpy(ppin, palette, (size_t)ncolors * 4);
+    FB_CUDA(cudaMemcpyAsync(dpal, ppin, 1024, cudaMemcpyHostToDevice, c->stream));
+    FB_TRY(launch_apply_palette(c->stream, d, 0, pitch, w, h, dpal, ncolors, didx, 0, ipitch, dout, 0, pitch, 1));
+    if (indices) FB_CUDA(cudaMemcpy2DAsync(indices, idxStride, didx, ipitch, (size_t)w, h, cudaMemcpyDeviceToHost, c->stream));
+    if (dst) FB_TRY(download(c, dout, pitch, dst, dstStride, w, h));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FB_OK;
+}
+
+int fb_apply_palette_batch_dev(int device, void *stream, const uint8_t *src, int64_t imgStride, int rowStride, int w, int h,
+                               int n, const uint8_t *palettes, int ncolors, uint8_t *indices, int64_t idxImgStride,
+                               int idxRowStride, uint8_t *dst, int64_t dstImgStride, int dstRowStride) {
+    FB_TRY(check_palette("fb_apply_palette_batch_dev", palettes, ncolors, false));
+    FB_TRY(check_batch("fb_apply_palette_batch_dev", src, imgStride, rowStride, w, h, n));
+    if (dst) FB_TRY(check_batch("fb_apply_palette_batch_dev", dst, dstImgStride, dstRowStride, w, h, n));
+    if (indices && idxRowStride < w) { set_error("fb_apply_palette_batch_dev: index stride %d < w", idxRowStride); return FB_E_INVALID; }
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_apply_palette_batch_dev", device, &c));
+    return launch_apply_palette((cudaStream_t)stream, src, imgStride, rowStride, w, h, palettes, ncolors, indices, idxImgStride,
+                                idxRowStride, dst, dstImgStride, dstRowStride, n);
+}
+
+}  // extern "C"

@@ -135,6 +135,11 @@ bool orient_dims(int orient, int w, int h, int *dw, int *dh);
 int launch_orient(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int w, int h, int orient,
                   uint8_t *dst, long long dstImgStride, int dstRowStride, int n);
 
+// palette.cu — SURVEY §8(f3): applyPalette + palettedToNRGBA (targetsize.go:479-545)
+int launch_apply_palette(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int w, int h,
+                         const uint8_t *palettes_dev, int ncolors, uint8_t *idx, long long idxImgStride, int idxRowStride,
+                         uint8_t *out, long long outImgStride, int outRowStride, int n);
+
 // resize.cu
 // When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.
 struct IntRatioInfo {

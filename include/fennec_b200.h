@@ -177,6 +177,19 @@ FB_API int fb_apply_orientation_batch_dev(int device, void *stream, const uint8_
                                    int srcRowStride, int w, int h, int orient, uint8_t *dst, int64_t dstImgStride,
                                    int dstRowStride, int n);
 
+/* ---- applyPalette + palettedToNRGBA — targetsize.go:479-545 ------------------------ */
+
+/* `palette` holds ncolors (1..256) NRGBA entries with A == 255 (what medianCut returns, targetsize.go:400-413).
+ * `indices` receives image.Paletted.Pix (first nearest entry by squared RGB distance, targetsize.go:499-510),
+ * `dst` the palettedToNRGBA reconstruction; either may be NULL. */
+FB_API int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint8_t *palette, int ncolors,
+                     uint8_t *indices, int idxStride, uint8_t *dst, int dstStride);
+/* n device-resident images, one 256-entry palette slot (1024 bytes, device memory) per image. */
+FB_API int fb_apply_palette_batch_dev(int device, void *stream, const uint8_t *src, int64_t imgStride, int rowStride,
+                               int w, int h, int n, const uint8_t *palettes, int ncolors, uint8_t *indices,
+                               int64_t idxImgStride, int idxRowStride, uint8_t *dst, int64_t dstImgStride,
+                               int dstRowStride);
+
 /* ---- device-resident batch entry points (configs 3-5 and the headline metric) ------------- */
 /* n images (or pairs) of identical dims; image i starts at base + i*imgStride bytes. All pointers
  * are device pointers on `device`; `stream` is a cudaStream_t. Scores land in device memory. */

@@ -1035,3 +1035,22 @@ int fo_apply_orientation(const uint8_t *src, int ss, int w, int h, int orient, u
         default: return 1;
     }
 }
+
+/* ---- §8(f3): applyPalette + palettedToNRGBA (targetsize.go:479-545) ----------------------------------------------
+ * palette: ncolors NRGBA entries (A = 255 as medianCut produces them, so c.RGBA()>>8 is the 8-bit channel).
+ * The reference's map is a memo of the same search and is omitted.  idx / out may be NULL. */
+void fo_apply_palette(const uint8_t *src, int ss, int w, int h, const uint8_t *palette, int ncolors,
+                      uint8_t *idx, int idxStride, uint8_t *out, int outStride) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t *p = src + (size_t)y * ss + (size_t)x * 4;
+            int bestIdx = 0, bestDist = 2147483647;                    /* math.MaxInt32 */
+            for (int i = 0; i < ncolors; i++) {
+                int dr = (int)p[0] - (int)palette[4 * i], dg = (int)p[1] - (int)palette[4 * i + 1], db = (int)p[2] - (int)palette[4 * i + 2];
+                int dist = dr * dr + dg * dg + db * db;
+                if (dist < bestDist) { bestDist = dist; bestIdx = i; }
+            }
+            if (idx) idx[(size_t)y * idxStride + x] = (uint8_t)bestIdx;
+            if (out) memcpy(out + (size_t)y * outStride + (size_t)x * 4, palette + 4 * bestIdx, 4);   /* targetsize.go:529-538, A = 255 */
+        }
+}

@@ -125,6 +125,10 @@ void fo_recommend(fo_image_stats *st);
 /* ApplyOrientation (exif.go:176-203); returns 1 for the identity orientations. */
 int fo_apply_orientation(const uint8_t *src, int srcStride, int w, int h, int orient, uint8_t *dst, int dstStride);
 
+/* applyPalette + palettedToNRGBA (targetsize.go:479-545). */
+void fo_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint8_t *palette, int ncolors,
+                      uint8_t *idx, int idxStride, uint8_t *out, int outStride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -499,3 +499,16 @@ def apply_orientation(img: np.ndarray, orient: int) -> np.ndarray:
     if orient not in ops:
         return img
     return np.ascontiguousarray(ops[orient](img))
+
+
+# ---- §8(f3): applyPalette + palettedToNRGBA (targetsize.go:479-545): distance matrix + argmin (first minimum) ----
+
+def apply_palette(img: np.ndarray, palette: np.ndarray):
+    pal = np.asarray(palette, dtype=np.int64)[:, :3]
+    h, w = img.shape[:2]
+    idx = np.empty((h, w), np.uint8)
+    for y0 in range(0, h, 64):                      # row blocks keep the (rows, w, ncolors) tensor small
+        px = img[y0:y0 + 64, :, :3].astype(np.int64)
+        d = ((px[:, :, None, :] - pal[None, None, :, :]) ** 2).sum(-1)
+        idx[y0:y0 + 64] = np.argmin(d, axis=-1).astype(np.uint8)
+    return idx, np.asarray(palette, dtype=np.uint8)[idx]

@@ -77,6 +77,8 @@ def lib():
         L.fo_analyze.argtypes = img + [C.c_int, C.c_int, C.POINTER(FoImageStats)]
         L.fo_analyze.restype = None
         L.fo_apply_orientation.argtypes = img + [C.c_int, C.c_int, C.c_int] + img
+        L.fo_apply_palette.argtypes = img + [C.c_int, C.c_int, _u8p, C.c_int, _u8p, C.c_int] + img
+        L.fo_apply_palette.restype = None
         L.fo_ycbcr_to_nrgba.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.fo_gray_to_nrgba.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         _lib = L
@@ -308,3 +310,15 @@ def apply_orientation(src: np.ndarray, orient: int) -> np.ndarray:
     pd, sd = _img(dst)
     assert lib().fo_apply_orientation(ps, ss, w, h, orient, pd, sd) == 0
     return dst
+
+
+def apply_palette(src: np.ndarray, palette: np.ndarray):
+    """applyPalette + palettedToNRGBA (targetsize.go:479-545) → (indices (h, w), reconstruction (h, w, 4))."""
+    h, w = src.shape[:2]
+    pal = np.ascontiguousarray(palette, dtype=np.uint8)
+    idx = np.zeros((h, w), np.uint8)
+    out = _new(h, w)
+    ps, ss = _img(src)
+    po, so = _img(out)
+    lib().fo_apply_palette(ps, ss, w, h, pal.ctypes.data_as(_u8p), pal.shape[0], idx.ctypes.data_as(_u8p), w, po, so)
+    return idx, out

@@ -104,6 +104,13 @@ if want("orient"):
     report("ApplyOrientation Rotate90CW 3840x2160 (f4)", timeit(lambda: batch.apply_orientation_batch(x, 6, out=y), 20), 16, 8.2944, 2 * 3840 * 2160 * 4)
     report("ApplyOrientation FlipH 3840x2160 (f4)", timeit(lambda: batch.apply_orientation_batch(x, 2, out=z), 20), 16, 8.2944, 2 * 3840 * 2160 * 4)
     del x, y, z
+if want("palette"):
+    x = noise(4, 3024, 4032, 14)
+    pal = torch.randint(0, 256, (4, 256, 4), dtype=torch.uint8, device="cuda")
+    pal[..., 3] = 255
+    report("applyPalette 256 colours 4032x3024 (f3; integer-pipe bound, not HBM)", timeit(lambda: batch.apply_palette_batch(x, pal, 256), 5), 4, 12.192768,
+           4032 * 3024 * 9)
+    del x, pal
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
     report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)
