@@ -18,6 +18,7 @@ import "C"
 
 import (
 	"image"
+	"image/color"
 	"unsafe"
 )
 
@@ -199,4 +200,45 @@ func gpuAnalyze(src *image.NRGBA) (ImageStats, bool) {
 		RecommendedFormat: Format(st.recommended_format), RecommendedQuality: Quality(st.recommended_quality),
 		EstimatedCompression: float64(st.estimated_compression),
 	}, true
+}
+
+// ---- SURVEY §8(f3, f4) ------------------------------------------------------------------------------------
+
+// gpuApplyPalette replaces the pixel loops of applyPalette and palettedToNRGBA (targetsize.go:479-545).
+// indexed.Palette must be what medianCut returned (color.NRGBA entries with A == 255).
+func gpuApplyPalette(src *image.NRGBA, indexed *image.Paletted, recon *image.NRGBA) bool {
+	n := len(indexed.Palette)
+	if n == 0 || n > 256 {
+		return false
+	}
+	pal := make([]byte, 4*n)
+	for i, c := range indexed.Palette {
+		v, ok := c.(color.NRGBA)
+		if !ok || v.A != 255 {
+			return false
+		}
+		pal[4*i], pal[4*i+1], pal[4*i+2], pal[4*i+3] = v.R, v.G, v.B, v.A
+	}
+	var dst *C.uint8_t
+	dstStride := 0
+	if recon != nil {
+		dst, dstStride = pix(recon), recon.Stride
+	}
+	st := C.fb_apply_palette(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
+		(*C.uint8_t)(unsafe.Pointer(&pal[0])), C.int(n), (*C.uint8_t)(unsafe.Pointer(&indexed.Pix[0])), C.int(indexed.Stride),
+		dst, C.int(dstStride))
+	return st == C.FB_OK
+}
+
+// gpuApplyOrientation replaces the rotate / flip loops behind ApplyOrientation (exif.go:176-203).
+// The identity orientations never reach it (the switch returns img first).
+func gpuApplyOrientation(img *image.NRGBA, orient Orientation) (*image.NRGBA, bool) {
+	var dw, dh C.int
+	if C.fb_orientation_dims(C.int(orient), C.int(img.Bounds().Dx()), C.int(img.Bounds().Dy()), &dw, &dh) != C.FB_OK {
+		return nil, false
+	}
+	dst := image.NewNRGBA(image.Rect(0, 0, int(dw), int(dh)))
+	st := C.fb_apply_orientation(pix(img), C.int(img.Stride), C.int(img.Bounds().Dx()), C.int(img.Bounds().Dy()),
+		C.int(orient), pix(dst), C.int(dst.Stride))
+	return dst, st == C.FB_OK
 }
