@@ -278,7 +278,172 @@ __device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
     return dsum;
 }
 
-template <int CPL>
+// ------------------------------------------------------------------------------------------------
+// Software-pipelined row walk (aligned inputs, CPL = 4).  walk_strip above runs, per row, a strictly serial chain:
+// pixel LDS -> planes -> vertical taps -> STS -> __syncwarp -> neighbour LDS -> horizontal taps -> formula, and with
+// two warps per scheduler the two shared-memory round trips are exposed.  Here the work of row r+1 that does not
+// depend on the exchange is slotted into the waits of row r:
+//     1. STS V(r); __syncwarp; issue the 7 neighbour LDS of V(r)
+//     2. planes(r+1) from pixels fetched one step earlier          <- covers the neighbour-LDS latency
+//     3. horizontal taps + formula of row r
+//     4. cp.async.wait + pixel LDS of row r+2                       <- covered by step 5
+//     5. vertical taps of row r+1 -> V(r+1)
+// Register peak is unchanged (planes need no long-lived temporaries), the arithmetic is identical.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double walk_strip_pipe(const StripCtx<4> &q) {
+    constexpr int CPL = 4;
+    const uint8_t *pa = q.pa, *pb = q.pb;
+    const int nIn = q.nIn, lane = q.lane;
+    const float c = q.c;
+    const float2 s2 = make_float2(kLumaScale, kLumaScale);
+    const float2 K2 = make_float2(q.K, q.K);
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
+    const float kTh = fmaf(c, c, 0.5f * kC1f);
+    const float2 qpInit = make_float2(kC2f, 0.5f * kC2f);
+    float2 rab[8][CPL], rqp[8][CPL];
+    constexpr uint32_t kRowBuf = 32 * CPL * 4;
+    const uint32_t myRing = smem_u32(q.ring) + lane * (CPL * 4);
+    const uint8_t *myRingP = q.ring + lane * (CPL * 4);
+#pragma unroll
+    for (int row = 0; row < kStages; row++) {  // rows 0..3 exist (nIn >= 8)
+        cp_async<16>(myRing + (2 * row) * kRowBuf, pa);
+        cp_async<16>(myRing + (2 * row + 1) * kRowBuf, pb);
+        cp_async_commit();
+        pa += q.rowStrideA;
+        pb += q.rowStrideB;
+    }
+    uint4 pxa, pxb;   // pixels of the next row to convert
+#define PIPE_FETCH(R)                                                                           \
+    {                                                                                           \
+        cp_async_wait<kStages - 1>();                                                           \
+        const uint8_t *rb_ = myRingP + (2 * ((R) & (kStages - 1))) * kRowBuf;                   \
+        pxa = *reinterpret_cast<const uint4 *>(rb_);                                            \
+        pxb = *reinterpret_cast<const uint4 *>(rb_ + kRowBuf);                                  \
+    }
+    // planes of the fetched row into ring slot S, then start the copy of row R + kStages into the freed stage
+#define PIPE_PLANES(S, R)                                                                       \
+    {                                                                                           \
+        const uint32_t xa_[4] = {pxa.x, pxa.y, pxa.z, pxa.w}, xb_[4] = {pxb.x, pxb.y, pxb.z, pxb.w}; \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
+            float2 t = __ffma2_rn(f, s2, K2);                                                   \
+            float2 sq = __fmul2_rn(t, t);                                                       \
+            rab[S][i] = t;                                                                      \
+            rqp[S][i] = make_float2(sq.x + sq.y, t.x * t.y);                                    \
+        }                                                                                       \
+        if ((R) + kStages < nIn) {                                                              \
+            cp_async<16>(myRing + (2 * ((R) & (kStages - 1))) * kRowBuf, pa);                   \
+            cp_async<16>(myRing + (2 * ((R) & (kStages - 1)) + 1) * kRowBuf, pb);               \
+            pa += q.rowStrideA;                                                                 \
+            pb += q.rowStrideB;                                                                 \
+        }                                                                                       \
+        cp_async_commit();                                                                      \
+    }
+    // vertical taps for the row whose planes sit in slot S: rows r-7..r live in slots (S+1+j)&7
+#define PIPE_VTAPS(S)                                                                           \
+    _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                           \
+        float2 vab = __fmul2_rn(rab[(S + 1) & 7][i], g2[0]);                                    \
+        float2 vqp = __fmul2_rn(rqp[(S + 1) & 7][i], g2[0]);                                    \
+        _Pragma("unroll") for (int j = 1; j < 8; j++) {                                         \
+            vab = __ffma2_rn(rab[(S + 1 + j) & 7][i], g2[j], vab);                              \
+            vqp = __ffma2_rn(rqp[(S + 1 + j) & 7][i], g2[j], vqp);                              \
+        }                                                                                       \
+        it[i] = make_float4(vab.x, vab.y, vqp.x, vqp.y);                                        \
+    }
+
+    float4 it[CPL + 7];
+    // warm-up: rows 0..7 into slots 0..7, V(7), pixels of row 8
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        PIPE_FETCH(r)
+        PIPE_PLANES(r, r)
+    }
+    PIPE_VTAPS(7)
+    if (8 < nIn) PIPE_FETCH(8)
+
+    const float2 one_two = make_float2(1.f, 2.f), neg2 = make_float2(-1.f, -1.f);
+    float fs[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) fs[i] = 0.f;
+    constexpr int kVLanes = 36;
+    constexpr int kVBuf = CPL * kVLanes;
+    float4 *myV = q.vb0 + lane + ((7 & 1) ? kVBuf : 0);
+
+#pragma unroll 1
+    for (int r = 7; r < nIn; r++) {
+        // 1. exchange V(r)
+        float4 *vb = myV;
+        myV = (r & 1) ? myV - kVBuf : myV + kVBuf;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) vb[i * kVLanes] = it[i];
+        __syncwarp();
+#pragma unroll
+        for (int k = CPL; k < CPL + 7; k++) it[k] = vb[(k % CPL) * kVLanes + k / CPL];
+        // 2. planes of row r+1 (pixels fetched in step 4 of the previous iteration)
+        const int rn = r + 1;
+        if (rn < nIn) {
+            switch (rn & 7) {
+                case 0: PIPE_PLANES(0, rn) break;
+                case 1: PIPE_PLANES(1, rn) break;
+                case 2: PIPE_PLANES(2, rn) break;
+                case 3: PIPE_PLANES(3, rn) break;
+                case 4: PIPE_PLANES(4, rn) break;
+                case 5: PIPE_PLANES(5, rn) break;
+                case 6: PIPE_PLANES(6, rn) break;
+                default: PIPE_PLANES(7, rn) break;
+            }
+        }
+        // 3. horizontal 8-tap + SSIM of row r
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+            float2 mab = __fmul2_rn(make_float2(it[i].x, it[i].y), g2[0]);
+            float2 mqp = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], qpInit);
+#pragma unroll
+            for (int t = 1; t < 8; t++) {
+                mab = __ffma2_rn(make_float2(it[i + t].x, it[i + t].y), g2[t], mab);
+                mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
+            }
+            const float2 sq = __fmul2_rn(mab, mab);
+            const float2 mn = make_float2(mab.x * mab.y, sq.x + sq.y);
+            const float th = fmaf(c, mab.x + mab.y, kTh);
+            const float2 AB1 = __ffma2_rn(make_float2(th, th), one_two, mn);
+            const float2 AB2 = __ffma2_rn(mn, neg2, make_float2(mqp.y, mqp.x));
+            const float2 nd = __fmul2_rn(AB1, AB2);
+            float ssim4 = __fdividef(nd.x, nd.y);
+            fs[i] += q.valid[i] ? ssim4 : 0.f;
+        }
+        // 4. pixels of row r+2
+        if (r + 2 < nIn) PIPE_FETCH(r + 2)
+        // 5. vertical taps of row r+1
+        if (rn < nIn) {
+            switch (rn & 7) {
+                case 0: PIPE_VTAPS(0) break;
+                case 1: PIPE_VTAPS(1) break;
+                case 2: PIPE_VTAPS(2) break;
+                case 3: PIPE_VTAPS(3) break;
+                case 4: PIPE_VTAPS(4) break;
+                case 5: PIPE_VTAPS(5) break;
+                case 6: PIPE_VTAPS(6) break;
+                default: PIPE_VTAPS(7) break;
+            }
+        }
+    }
+#undef PIPE_FETCH
+#undef PIPE_PLANES
+#undef PIPE_VTAPS
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    return dsum;
+}
+
+#ifndef FB_SSIM_PIPE_DEFAULT
+#define FB_SSIM_PIPE_DEFAULT 0
+#endif
+
+template <int CPL, bool PIPE = false>
 __global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_strip_kernel(const SsimParams p) {
     constexpr int WARPS = 4;
     constexpr int INC = 32 * CPL;    // input columns per strip
@@ -338,7 +503,9 @@ __global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_stri
     q.pb = ib + (long long)Y0 * p.rowStrideB + (long long)xld * 4;
     if (fast && q.nvalid == 0) q.nvalid = CPL;
 
-    double dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
+    double dsum;
+    if (PIPE && CPL == 4) dsum = fast ? walk_strip_pipe(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
+    else dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if (lane == 0) p.partials[seg] = dsum * 4.0;
@@ -725,7 +892,11 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
             attrSet = true;
         }
         ssim_ws_kernel<<<(unsigned)blocks, 256, sizeof(WsSmem), s>>>(p);
-    } else if (g.cpl == 4) ssim_strip_kernel<4><<<(unsigned)blocks, 128, 0, s>>>(p);
+    } else if (g.cpl == 4) {
+        static const bool usePipe = [] { const char *e = getenv("FB_SSIM_PIPE"); return e ? e[0] == '1' : (FB_SSIM_PIPE_DEFAULT != 0); }();
+        if (usePipe) ssim_strip_kernel<4, true><<<(unsigned)blocks, 128, 0, s>>>(p);
+        else ssim_strip_kernel<4, false><<<(unsigned)blocks, 128, 0, s>>>(p);
+    }
     else ssim_strip_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(p);
     FB_CUDA(cudaGetLastError());
     ssim_finalize_kernel<<<n, 32, 0, s>>>(p.partials, g.nsx * g.nsy, (long long)(w - 8) * (h - 8), scores,
