@@ -1,7 +1,7 @@
 """Tiny driver for `ncu --set full` captures: runs one op of the hot path a few times on device-resident
 synthetic data and nothing else (keeps the replayed launch count small).
 
-    python tools/profile_driver.py ssim|ssim_fast|msssim|blur|sharpen|adaptive|lanczos|box [--pairs P] [--iters I]
+    python tools/profile_driver.py ssim|ssim_fast|msssim|blur|sharpen|adaptive|lanczos|box|ycbcr|analyze|orient|palette [--pairs P] [--iters I]
 """
 import argparse
 import os
@@ -39,6 +39,15 @@ for _ in range(args.iters):
     elif args.op == "analyze":
         r = torch.empty(args.pairs * 2048, dtype=torch.uint8, device="cuda")
         batch.analyze_scan_batch(a, r)
+    elif args.op == "ycbcr":
+        y = a[..., 0].contiguous(); cb = b[:, ::2, ::2, 1].contiguous(); cr = b[:, ::2, ::2, 2].contiguous()
+        r = batch.ycbcr_to_nrgba_batch(y, cb, cr, 2)
+    elif args.op == "orient":
+        r = batch.apply_orientation_batch(a, 6)
+        r = batch.apply_orientation_batch(a, 2)
+    elif args.op == "palette":
+        pal = b[:, 0, :256, :].contiguous(); pal[..., 3] = 255
+        r = batch.apply_palette_batch(a, pal, 256)[1]
     elif args.op == "lanczos":
         r = batch.lanczos_resize_batch(a, args.w // 4, args.h // 4)
     elif args.op == "box":
