@@ -128,26 +128,27 @@ __device__ __forceinline__ uint32_t pack_rgba_low_bytes(float tr, float tg, floa
 }
 
 template <typename AlphaFn>
-__device__ __forceinline__ uint32_t blur_round_pack(const float2 (&acc)[kTile / 2][3], float lim, uint32_t (&out)[kTile],
-                                                    AlphaFn alphaWord) {
+__device__ __forceinline__ uint32_t blur_round_pack(const float2 (&accRG)[kTile], const float2 (&accB)[kTile / 2], float lim,
+                                                    uint32_t (&out)[kTile], AlphaFn alphaWord) {
     const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
     const float2 neg1 = make_float2(-1.0f, -1.0f);
     uint32_t ambMask = 0;
 #pragma unroll
     for (int m = 0; m < kTile / 2; m++) {
-        float2 t[3], d[3];
+        float2 t[3], d[3];   // (R,G) of output 2m, (R,G) of output 2m+1, (B, B) of both
+        const float2 v[3] = {accRG[2 * m], accRG[2 * m + 1], accB[m]};
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            t[c] = __fadd2_rn(acc[m][c], magic);
+            t[c] = __fadd2_rn(v[c], magic);
             const float2 r = __fadd2_rn(t[c], nmagic);
-            d[c] = __ffma2_rn(r, neg1, acc[m][c]);   // v - r, exact product
+            d[c] = __ffma2_rn(r, neg1, v[c]);   // v - r, exact product
         }
-        const float mx = fmaxf(fmaxf(fabsf(d[0].x), fabsf(d[1].x)), fabsf(d[2].x));
-        const float my = fmaxf(fmaxf(fabsf(d[0].y), fabsf(d[1].y)), fabsf(d[2].y));
+        const float mx = fmaxf(fmaxf(fabsf(d[0].x), fabsf(d[0].y)), fabsf(d[2].x));
+        const float my = fmaxf(fmaxf(fabsf(d[1].x), fabsf(d[1].y)), fabsf(d[2].y));
         if (mx >= lim) ambMask |= 1u << (2 * m);
         if (my >= lim) ambMask |= 1u << (2 * m + 1);
-        out[2 * m] = pack_rgba_low_bytes(t[0].x, t[1].x, t[2].x, alphaWord(2 * m));
-        out[2 * m + 1] = pack_rgba_low_bytes(t[0].y, t[1].y, t[2].y, alphaWord(2 * m + 1));
+        out[2 * m] = pack_rgba_low_bytes(t[0].x, t[0].y, t[2].x, alphaWord(2 * m));
+        out[2 * m + 1] = pack_rgba_low_bytes(t[1].x, t[1].y, t[2].y, alphaWord(2 * m + 1));
     }
     return ambMask;
 }
@@ -230,29 +231,34 @@ __device__ __forceinline__ uint32_t blur_exact_taps(const uint32_t *px, int stri
     return clampf_dev(r) | (clampf_dev(g) << 8) | (clampf_dev(b) << 16);
 }
 
-// acc pairs: outputs (2m, 2m+1) of one channel share an FFMA2; input i feeds output j with tap
-// k = i - off - j, so the pair uses weights (w[k], w[k-1]) — kept as register pairs wp[k], k = 0..2R+1,
-// with w[-1] = w[2R+1] = 0.  Halves the issue slots of the tap loop (the pipe time is unchanged).
+// Accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar; B of outputs (2m, 2m+1)
+// sits in the two halves of accB[m] and takes scalar FFMAs.  [The first version paired two OUTPUTS of one channel
+// per FFMA2, which needs the weight pairs (w[k], w[k-1]) as aligned register pairs: ptxas rebuilt them with one
+// IMAD.MOV per FFMA2 — 28 % of the executed instructions, on the same pipe as the FMAs (profiles/r1d).]
 template <int R, int NIN, int OFF>
 __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const float *kernel32,
-                                               float2 (&acc)[kTile / 2][3]) {
-    float2 wp[2 * R + 2];
+                                               float2 (&accRG)[kTile], float2 (&accB)[kTile / 2]) {
+    float wt[2 * R + 1];
 #pragma unroll
-    for (int k = 0; k <= 2 * R + 1; k++)
-        wp[k] = make_float2(k <= 2 * R ? __ldg(kernel32 + k) : 0.f, k >= 1 ? __ldg(kernel32 + k - 1) : 0.f);
+    for (int k = 0; k <= 2 * R; k++) wt[k] = __ldg(kernel32 + k);
 #pragma unroll
-    for (int m = 0; m < kTile / 2; m++) acc[m][0] = acc[m][1] = acc[m][2] = make_float2(0.f, 0.f);
+    for (int j = 0; j < kTile; j++) accRG[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < kTile / 2; m++) accB[m] = make_float2(0.f, 0.f);
+    const float2 nmagic = make_float2(-8388608.0f, -8388608.0f);
 #pragma unroll
     for (int i = OFF - R; i < OFF + kTile + R; i++) {
-        const float f0 = byte_to_float(raw[i], 0), f1 = byte_to_float(raw[i], 1), f2 = byte_to_float(raw[i], 2);
-        const float2 f00 = make_float2(f0, f0), f11 = make_float2(f1, f1), f22 = make_float2(f2, f2);
+        // [byte k, 0, 0, 0x4B] = bits of 2^23 + byte; one FADD2 converts R and G, one FADD converts B
+        const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
+                                                 __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), nmagic);
+        const float bl = byte_to_float(raw[i], 2);
 #pragma unroll
-        for (int m = 0; m < kTile / 2; m++) {
-            const int k = i - OFF - 2 * m + R;  // tap of input i for output 2m (output 2m+1 uses k-1)
-            if (k >= 0 && k <= 2 * R + 1) {
-                acc[m][0] = __ffma2_rn(f00, wp[k], acc[m][0]);
-                acc[m][1] = __ffma2_rn(f11, wp[k], acc[m][1]);
-                acc[m][2] = __ffma2_rn(f22, wp[k], acc[m][2]);
+        for (int j = 0; j < kTile; j++) {
+            const int k = i - OFF - j + R;  // tap of input i for output j
+            if (k >= 0 && k <= 2 * R) {
+                accRG[j] = __ffma2_rn(rg, make_float2(wt[k], wt[k]), accRG[j]);
+                if (j & 1) accB[j / 2].y = fmaf(bl, wt[k], accB[j / 2].y);
+                else accB[j / 2].x = fmaf(bl, wt[k], accB[j / 2].x);
             }
         }
     }
@@ -337,10 +343,10 @@ __global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p)
                 uint4 q = *reinterpret_cast<const uint4 *>(st + (lane + i0 / kTile) * kChunkB + (i0 % kTile) * 4);
                 raw[v * 4 + 0] = q.x; raw[v * 4 + 1] = q.y; raw[v * 4 + 2] = q.z; raw[v * 4 + 3] = q.w;
             }
-            float2 acc[kTile / 2][3];
-            blur_taps_fp32<R, 32, 8>(raw, p.kernel32, acc);
+            float2 accRG[kTile], accB[kTile / 2];
+            blur_taps_fp32<R, 32, 8>(raw, p.kernel32, accRG, accB);
             uint32_t out[kTile];
-            uint32_t ambMask = blur_round_pack(acc, lim, out, [&](int j) { return raw[8 + j]; });  // alpha from the source (effects.go:189)
+            uint32_t ambMask = blur_round_pack(accRG, accB, lim, out, [&](int j) { return raw[8 + j]; });  // alpha from the source (effects.go:189)
             uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
             if (dvec && x0 + kTile <= p.w) {
 #pragma unroll
@@ -409,10 +415,10 @@ __global__ void __launch_bounds__(128, 4) blur_v_fast_kernel(const BlurParams p)
                 for (int i = 0; i < kTile; i++) nxt[i] = ld_row(yn + i);
             }
         }
-        float2 acc[kTile / 2][3];
-        blur_taps_fp32<R, NIN, R>(raw, p.kernel32, acc);
+        float2 accRG[kTile], accB[kTile / 2];
+        blur_taps_fp32<R, NIN, R>(raw, p.kernel32, accRG, accB);
         uint32_t out[kTile];
-        uint32_t ambMask = blur_round_pack(acc, lim, out, [&](int j) { return raw[R + j]; });  // alpha rides in tmp (effects.go:189,215)
+        uint32_t ambMask = blur_round_pack(accRG, accB, lim, out, [&](int j) { return raw[R + j]; });  // alpha rides in tmp (effects.go:189,215)
         {
             uint8_t *dp = dcol + (long long)y0 * p.dstRowStride;
             if (!active) {
