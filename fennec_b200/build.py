@@ -19,7 +19,8 @@ OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libfennec_b200.so")
 SOURCES = ["api.cu", "ssim.cu", "box.cu", "effects.cu", "resize.cu", "ycbcr.cu", "analyze.cu", "orient.cu", "palette.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+EXTRA = os.environ.get("FB_EXTRA_NVCC", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 

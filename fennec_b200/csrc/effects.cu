@@ -198,7 +198,9 @@ __device__ __forceinline__ void amb_push(uint32_t mask, int x0, int y0, int dx, 
 template <bool VERTICAL>
 __device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *cnt, const uint8_t *taps, int tapsRs,
                                           uint8_t *dst, int dstRs, int w, int h, int radius, const double *kernel) {
-    int n = *cnt;
+    // lane 0's view, broadcast: the decision must be warp-uniform even if a fast lane has already pushed entries of
+    // the next chunk (the shuffle is also the point no lane passes before all have pushed this chunk's entries)
+    int n = __shfl_sync(0xffffffffu, *cnt, 0);
     if (n < (all ? 1 : 32)) return;
     while (n >= (all ? 1 : 32)) {
         const int take = min(n, 32);
@@ -235,6 +237,9 @@ __device__ __forceinline__ uint32_t blur_exact_taps(const uint32_t *px, int stri
 // sits in the two halves of accB[m] and takes scalar FFMAs.  [The first version paired two OUTPUTS of one channel
 // per FFMA2, which needs the weight pairs (w[k], w[k-1]) as aligned register pairs: ptxas rebuilt them with one
 // IMAD.MOV per FFMA2 — 28 % of the executed instructions, on the same pipe as the FMAs (profiles/r1d).]
+#ifndef FB_BLUR_BA
+#define FB_BLUR_BA 0   // 1: B rides an FFMA2 together with the (discarded) alpha lane instead of a scalar FFMA
+#endif
 template <int R, int NIN, int OFF>
 __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const float *kernel32,
                                                float2 (&accRG)[kTile], float2 (&accB)[kTile / 2]) {
@@ -246,22 +251,40 @@ __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const
 #pragma unroll
     for (int m = 0; m < kTile / 2; m++) accB[m] = make_float2(0.f, 0.f);
     const float2 nmagic = make_float2(-8388608.0f, -8388608.0f);
+#if FB_BLUR_BA
+    float2 accBA[kTile];
+#pragma unroll
+    for (int j = 0; j < kTile; j++) accBA[j] = make_float2(0.f, 0.f);
+#endif
 #pragma unroll
     for (int i = OFF - R; i < OFF + kTile + R; i++) {
         // [byte k, 0, 0, 0x4B] = bits of 2^23 + byte; one FADD2 converts R and G, one FADD converts B
         const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
                                                  __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), nmagic);
+#if FB_BLUR_BA
+        const float2 ba = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7542u)),
+                                                 __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7543u))), nmagic);
+#else
         const float bl = byte_to_float(raw[i], 2);
+#endif
 #pragma unroll
         for (int j = 0; j < kTile; j++) {
             const int k = i - OFF - j + R;  // tap of input i for output j
             if (k >= 0 && k <= 2 * R) {
                 accRG[j] = __ffma2_rn(rg, make_float2(wt[k], wt[k]), accRG[j]);
+#if FB_BLUR_BA
+                accBA[j] = __ffma2_rn(ba, make_float2(wt[k], wt[k]), accBA[j]);
+#else
                 if (j & 1) accB[j / 2].y = fmaf(bl, wt[k], accB[j / 2].y);
                 else accB[j / 2].x = fmaf(bl, wt[k], accB[j / 2].x);
+#endif
             }
         }
     }
+#if FB_BLUR_BA
+#pragma unroll
+    for (int m = 0; m < kTile / 2; m++) accB[m] = make_float2(accBA[2 * m].x, accBA[2 * m + 1].x);
+#endif
 }
 
 constexpr int kHRows = 8;  // rows one warp walks in the horizontal pass (double-buffered staging)

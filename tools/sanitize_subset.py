@@ -33,4 +33,43 @@ assert np.array_equal(api.box_downsample(big, 512, 129), O.box_downsample(big, 5
 assert np.array_equal(api.lanczos_resize(big, 513, 130), O.lanczos_resize(big, 513, 130))
 assert np.array_equal(api.GaussianBlur(big, 2.0), O.gaussian_blur(big, 2.0))
 assert abs(api.SSIMFast(big, S.perturb(big, 1, 5)) - O.ssim_fast(big, S.perturb(big, 1, 5))) <= 1e-5
+# round-1b kernels: fused MS-SSIM level step, integer-ratio Lanczos (pipelined H pass + exact queue), tall blur segments,
+# YCbCr / Gray conversion, Analyze scans, orientation, palette
+import torch
+from fennec_b200 import batch
+for (w, h) in [(1028, 770), (1300, 700), (2048, 1152)]:
+    a = S.gradient_noise_image(w, h, w); b = S.perturb(a, 3, 8)
+    assert abs(api.MSSSIM(a, b) - O.msssim(a, b)) <= 1e-5
+    ok, tw, th = api.ssim_fast_dims(w, h)
+    ta, tb, ha, hb = batch.msssim_level_batch(torch.from_numpy(a[None]).cuda(), torch.from_numpy(b[None]).cuda(), tw, th)
+    assert np.array_equal(ta[0].cpu().numpy(), O.box_downsample(a, tw, th)) and np.array_equal(hb[0].cpu().numpy(), O.box_downsample(b, w // 2, h // 2))
+for (w, h, al) in [(1024, 64, "opaque"), (2052, 40, "random"), (516, 36, "ramp")]:
+    src = S.noise_image(w, h, w + 1, alpha=al)
+    assert np.array_equal(api.lanczos_resize(src, w // 4, h // 4), O.lanczos_resize(src, w // 4, h // 4))
+tall = S.noise_image(70, 500, 5, alpha="random")
+assert np.array_equal(api.GaussianBlur(tall, 2.0), O.gaussian_blur(tall, 2.0))
+for ratio in range(6):
+    for (w, h) in [(67, 45), (1, 1), (130, 3)]:
+        y, cb, cr = S.noise_planes(w, h, ratio, 10 + ratio)
+        assert np.array_equal(api.ycbcr_to_nrgba(y, cb, cr, ratio), O.ycbcr_to_nrgba(y, cb, cr, ratio))
+g = S.noise_image(37, 21, 5)[..., 0].copy()
+assert np.array_equal(api.gray_to_nrgba(g), O.gray_to_nrgba(g))
+src = S.gradient_noise_image(640, 480, 9)
+with api.SSIMReference(src) as ref:
+    y, cb, cr = S.ycbcr_planes_from_nrgba(src, 2, 1, 3)
+    assert abs(ref.score_ycbcr(y, cb, cr, 2) - O.ssim_fast(src, O.ycbcr_to_nrgba(y, cb, cr, 2))) <= 1e-5
+for img in (S.noise_image(301, 203, 6, alpha="random"), S.gradient_noise_image(640, 480, 7), S.noise_image(3, 3, 1)):
+    st, want = api.Analyze(img), O.analyze(img)
+    assert st["unique_colors"] == want["unique_colors"] and st["has_alpha"] == want["has_alpha"]
+    assert abs(st["edge_density"] - want["edge_density"]) <= 1e-12 and abs(st["entropy"] - want["entropy"]) <= 1e-9
+for o in range(2, 9):
+    for (w, h) in [(33, 65), (1, 7), (128, 64), (257, 31)]:
+        img = S.noise_image(w, h, w + o, alpha="random")
+        assert np.array_equal(api.ApplyOrientation(img, o), O.apply_orientation(img, o))
+rng = np.random.Generator(np.random.PCG64(3))
+pal = rng.integers(0, 256, (200, 4), dtype=np.uint8); pal[:, 3] = 255
+for (w, h) in [(97, 61), (4, 1), (130, 17)]:
+    img = S.noise_image(w, h, w, alpha="random")
+    gi, go = api.apply_palette(img, pal); oi, oo = O.apply_palette(img, pal)
+    assert np.array_equal(gi, oi) and np.array_equal(go, oo)
 print("sanitize subset ok")
