@@ -407,12 +407,25 @@ __global__ void __launch_bounds__(128) resize_h_int_ratio_kernel(const IntRatioP
                 if (k < NLD - 1 || u < SPAN + 1) cp_async8(buf + (u >> 4) * CHB + (u & 15) * 4, row + (long long)(sBase + u) * 4);
             }
         } else {
-            for (int u = threadIdx.x * 2; u < SPAN + 1; u += 256) {
-                const int sx = sBase + u;
-                uint2 v = make_uint2(0u, 0u);
-                if (sx >= 0 && sx < p.srcW) v.x = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)sx * 4));
-                if (sx + 1 >= 0 && sx + 1 < p.srcW) v.y = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(sx + 1) * 4));
-                *reinterpret_cast<uint2 *>(buf + (u >> 4) * CHB + (u & 15) * 4) = v;
+            // edge blocks (the first and the last of a row — half of all blocks at 7680 -> 1920): pairs that lie
+            // inside the row still go through cp.async; only the few pairs that straddle or leave the row are
+            // loaded by hand.  [A plain load -> store loop here cost 25 % of the kernel's stall samples.]
+            const bool al8 = (((uintptr_t)row + (long long)sBase * 4) & 7) == 0;
+#pragma unroll
+            for (int k = 0; k < NLD; k++) {
+                const int u = threadIdx.x * 2 + k * 256;
+                if (k < NLD - 1 || u < SPAN + 1) {
+                    const int sx = sBase + u;
+                    uint8_t *dstp = buf + (u >> 4) * CHB + (u & 15) * 4;
+                    if (al8 && sx >= 0 && sx + 1 < p.srcW) {
+                        cp_async8(dstp, row + (long long)sx * 4);
+                    } else {
+                        uint2 v = make_uint2(0u, 0u);
+                        if (sx >= 0 && sx < p.srcW) v.x = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)sx * 4));
+                        if (sx + 1 >= 0 && sx + 1 < p.srcW) v.y = __ldg(reinterpret_cast<const uint32_t *>(row + (long long)(sx + 1) * 4));
+                        *reinterpret_cast<uint2 *>(dstp) = v;
+                    }
+                }
             }
         }
         cp_async_commit_group();
