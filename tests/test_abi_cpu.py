@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from fennec_b200 import _lib, api, batch
+from fennec_b200 import synth as S
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -115,3 +116,68 @@ def test_workspace_bytes_is_host_logic(lib):
     assert lib.fb_workspace_bytes(b"ssim", 3840, 2160, 0, 0, 32) > 0
     assert lib.fb_workspace_bytes(b"msssim", 7680, 4320, 0, 0, 1) > 2 * 3840 * 2160 * 4
     assert lib.fb_workspace_bytes(b"nonsense", 1, 1, 1, 1, 1) == 0
+
+
+# ---- SURVEY §8(f1-f4) entry points: argument checking and host logic that run without a GPU ------------------------
+
+def test_new_entry_points_validate_before_touching_the_gpu(lib):
+    y = np.zeros((4, 8), np.uint8)
+    c = np.zeros((2, 4), np.uint8)
+    dst = np.zeros((4, 8, 4), np.uint8)
+    u8 = _lib.u8p
+    p = lambda a: a.ctypes.data_as(u8)  # noqa: E731
+    # unknown subsample ratio / plane stride too small / null planes
+    assert lib.fb_ycbcr_to_nrgba(p(y), 8, p(c), p(c), 4, 8, 4, 9, p(dst), 32) == _lib.FB_E_INVALID
+    assert b"ratio" in lib.fb_last_error()
+    assert lib.fb_ycbcr_to_nrgba(p(y), 7, p(c), p(c), 4, 8, 4, 2, p(dst), 32) == _lib.FB_E_INVALID
+    assert lib.fb_ycbcr_to_nrgba(None, 8, p(c), p(c), 4, 8, 4, 2, p(dst), 32) == _lib.FB_E_INVALID
+    # palette: 0 or > 256 entries, alpha != 255
+    pal = np.full((4, 4), 255, np.uint8)
+    idx = np.zeros((4, 8), np.uint8)
+    assert lib.fb_apply_palette(p(dst), 32, 8, 4, p(pal), 0, p(idx), 8, None, 0) == _lib.FB_E_INVALID
+    assert lib.fb_apply_palette(p(dst), 32, 8, 4, p(pal), 257, p(idx), 8, None, 0) == _lib.FB_E_INVALID
+    pal[2, 3] = 254
+    assert lib.fb_apply_palette(p(dst), 32, 8, 4, p(pal), 4, p(idx), 8, None, 0) == _lib.FB_E_INVALID
+    assert b"alpha" in lib.fb_last_error()
+    # session: null outputs
+    assert lib.fb_ssim_ref_create(p(dst), 32, 8, 4, None) == _lib.FB_E_INVALID
+    assert lib.fb_ssim_ref_score_nrgba(None, p(dst), 32, None) == _lib.FB_E_INVALID
+    lib.fb_ssim_ref_destroy(None)   # a no-op, like free(NULL)
+
+
+def test_orientation_dims_and_identity(lib):   # exif.go:176-203
+    dw, dh = C.c_int(), C.c_int()
+    for o in (2, 3, 4):
+        assert lib.fb_orientation_dims(o, 30, 20, C.byref(dw), C.byref(dh)) == _lib.FB_OK and (dw.value, dh.value) == (30, 20)
+    for o in (5, 6, 7, 8):
+        assert lib.fb_orientation_dims(o, 30, 20, C.byref(dw), C.byref(dh)) == _lib.FB_OK and (dw.value, dh.value) == (20, 30)
+    for o in (0, 1, 9, -3):   # the reference returns its input
+        assert lib.fb_orientation_dims(o, 30, 20, C.byref(dw), C.byref(dh)) == _lib.FB_IDENTITY
+        img = np.zeros((20, 30, 4), np.uint8)
+        assert api.ApplyOrientation(img, o) is img
+
+
+def test_analyze_finish_is_host_arithmetic(lib, oracle):
+    """fb_analyze_finish turns a raw record into ImageStats on the host: feed it a record assembled from the oracle's
+    own histogram and check entropy / mean / recommendations (analyze.go:86, 116-128, 183-232) without any GPU."""
+    img = S.gradient_noise_image(333, 217, 4)
+    want = oracle.analyze(img)
+    rec = np.zeros(int(lib.fb_analyze_raw_bytes()), np.uint8)
+    hist = rec[:1024].view(np.uint32)
+    hist[:] = want["histogram"].astype(np.uint32)
+    lum = 299 * img[..., 0].astype(np.int64) + 587 * img[..., 1].astype(np.int64) + 114 * img[..., 2].astype(np.int64)
+    rec[1024:1032].view(np.uint64)[0] = int(lum.sum())
+    sy, sx = int(np.ceil(217 / 100)), int(np.ceil(333 / 100))
+    n = len(range(0, 217, sy)) * len(range(0, 333, sx))
+    rec[1032:1040].view(np.float64)[0] = want["contrast"] ** 2 * n          # varSum
+    tail = rec[1040:1056].view(np.uint32)                                     # hasAlpha, hasColour, uniqueSampled, edges
+    ex, ey = max(1, 333 // 200), max(1, 217 // 200)
+    total = len(range(1, 216, ey)) * len(range(1, 332, ex))
+    tail[:] = [want["has_alpha"], 1 - want["is_grayscale"], want["unique_colors"], round(want["edge_density"] * total)]
+    st = _lib.FbImageStats()
+    assert lib.fb_analyze_finish(rec.ctypes.data, 333, 217, C.byref(st)) == _lib.FB_OK
+    assert (st.width, st.height, st.has_alpha, st.is_grayscale, st.unique_colors) == (333, 217, want["has_alpha"], want["is_grayscale"], want["unique_colors"])
+    assert abs(st.entropy - want["entropy"]) <= 1e-12 and abs(st.mean_brightness - want["mean_brightness"]) <= 1e-9
+    assert abs(st.contrast - want["contrast"]) <= 1e-9 and abs(st.edge_density - want["edge_density"]) <= 1e-12
+    assert (st.recommended_format, st.recommended_quality) == (want["recommended_format"], want["recommended_quality"])
+    assert abs(st.estimated_compression - want["estimated_compression"]) <= 1e-12
