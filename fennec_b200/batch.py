@@ -256,6 +256,11 @@ def gather_scores(local: torch.Tensor, n_items: int, world: int, rank: int) -> t
     per = (n_items + world - 1) // world
     padded = torch.zeros(per, dtype=local.dtype, device=local.device)
     padded[: local.numel()] = local
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded)
-    return torch.cat(parts)[:n_items]
+    out = torch.empty(per * world, dtype=local.dtype, device=local.device)
+    if hasattr(dist, "all_gather_into_tensor") and local.is_cuda:
+        dist.all_gather_into_tensor(out, padded)   # one ncclAllGather, no per-shard copies
+    else:
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded)
+        out = torch.cat(parts)
+    return out[:n_items]
