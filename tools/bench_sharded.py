@@ -95,6 +95,34 @@ out = torch.empty((n, 1080, 1920, 4), dtype=torch.uint8, device="cuda")
 c4 = lambda: batch.lanczos_resize_batch(x, 1920, 1080, out=out)  # noqa: E731
 line("4: Lanczos-3 7680x4320 -> 1920x1080", timed(c4, args.steps), timed(lambda: (c4(), gather_images(out)), args.steps),
      {"gather": "all_gather of NRGBA outputs (8.3 MB per item)"})
+# configs 3 and 4 with the gather FUSED into the producing kernel: the destination of rank r's batch is its slice of a
+# gathered buffer that lives on rank 0 (symmetric memory, mapped over NVLink; batch.PeerGather), so the kernel's own
+# stores are the transfer — no collective, no second pass over the outputs.
+if world > 1:
+    try:
+        pg = batch.PeerGather(total, (1080, 1920, 4), world, rank)
+        mine = pg.my_slice()
+        c4_fused = lambda: batch.lanczos_resize_batch(x, 1920, 1080, out=mine)  # noqa: E731
+        ms = timed(lambda: (c4_fused(), pg.handle.barrier()), args.steps)
+        c4(); ref_all = gather_images(out).clone()
+        c4_fused(); got = pg.finish()
+        ok = bool(torch.equal(got, ref_all)) if rank == 0 else True
+        line("4: Lanczos-3, gather fused into the kernel's stores (peer memory on rank 0)", timed(c4, args.steps), ms,
+             {"gather": "P2P stores over NVLink into rank 0's buffer; equals the all_gather result: %s" % ok})
+        del pg, mine, ref_all
+        x4k = noise(n, 2160, 3840, 1)
+        y4k = torch.empty_like(x4k)
+        pg3 = batch.PeerGather(total, (2160, 3840, 4), world, rank)
+        mine3 = pg3.my_slice()
+        def c3_fused():
+            batch.gaussian_blur_batch(x4k, 2.0, out=y4k); batch.sharpen_batch(y4k, 0.5, out=mine3)
+        ms3 = timed(lambda: (c3_fused(), pg3.handle.barrier()), args.steps)
+        line("3: blur + sharpen, gather fused into the sharpen kernel's stores", 0.0 + timed(lambda: (batch.gaussian_blur_batch(x4k, 2.0, out=y4k), batch.sharpen_batch(y4k, 0.5, out=x4k)), args.steps), ms3,
+             {"gather": "P2P stores over NVLink into rank 0's buffer (33.2 MB per item)"})
+        del pg3, mine3, x4k, y4k
+    except Exception as e:  # symmetric memory unavailable
+        if rank == 0:
+            print(json.dumps({"config": "fused gather", "unavailable": repr(e)[:300]}), flush=True)
 del out
 # config 5: MS-SSIM on 7680x4320 pairs
 b = noise(n, 4320, 7680, 3)
