@@ -172,6 +172,26 @@ def make_device_batch(torch, pairs: int, seed: int):
     return a, b
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process (and the pinned host buffers it allocates afterwards) to the CPUs NVML reports as local to
+    GPU `index`.  With 8 ranks the e2e leg is host-memory bound: buffers that land on the far socket halve the H2D
+    rate.  Returns the number of CPUs bound, or None if NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -180,6 +200,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -285,7 +306,8 @@ def run_ours(args):
                          },
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": E * BYTES_PER_PAIR,
                     "d2h_bytes_per_step": E * 8, "api": "fb_ssim (host buffers, pinned), 4 caller threads",
-                    "pairs_per_step": E, "steps": e2e_steps},
+                    "pairs_per_step": E, "steps": e2e_steps,
+                    "host_binding": (f"each rank bound to the {numa_cpus} CPUs NVML reports local to its GPU" if numa_cpus else "none")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
