@@ -100,6 +100,75 @@ inline Image fx(fx_fn fn, const Image &img, double strength) {
 inline Image Sharpen(const Image &img, double strength) { return detail::fx(fb_sharpen, img, strength); }                  // effects.go:10-45
 inline Image AdaptiveSharpen(const Image &img, double strength) { return detail::fx(fb_adaptive_sharpen, img, strength); }  // effects.go:49-90
 
+// ---- the callers / data formats either side of the path --------------------------------
+
+// image.YCbCr with Rect.Min == (0,0): what jpeg.Decode returns (image/ycbcr.go).
+struct YCbCr {
+    std::vector<uint8_t> Y, Cb, Cr;
+    int YStride = 0, CStride = 0, W = 0, H = 0;
+    int SubsampleRatio = 0;   // image.YCbCrSubsampleRatio: 0 = 444, 1 = 422, 2 = 420, 3 = 440, 4 = 411, 5 = 410
+};
+
+// convertToNRGBA — convert.go:34-64 — for a decoded *image.YCbCr
+inline Image convertToNRGBA(const YCbCr &img) {
+    Image dst = NewNRGBA(img.W, img.H);
+    if (img.W <= 0 || img.H <= 0) return dst;
+    check(fb_ycbcr_to_nrgba(img.Y.data(), img.YStride, img.Cb.data(), img.Cr.data(), img.CStride, img.W, img.H,
+                            img.SubsampleRatio, dst->data(), dst->Stride));
+    return dst;
+}
+
+// The `src` side of compress.go:45-74's binary search kept on the device: SSIMFast(src, candidate) per iteration.
+class SSIMSession {
+    fb_ssim_ref *h_ = nullptr;
+public:
+    explicit SSIMSession(const Image &src) { check(fb_ssim_ref_create(src->data(), src->Stride, src->W, src->H, &h_)); }
+    ~SSIMSession() { fb_ssim_ref_destroy(h_); }
+    SSIMSession(const SSIMSession &) = delete;
+    SSIMSession &operator=(const SSIMSession &) = delete;
+    double score(const YCbCr &d) const {
+        double out = 0.0;
+        check(fb_ssim_ref_score_ycbcr(h_, d.Y.data(), d.YStride, d.Cb.data(), d.Cr.data(), d.CStride, d.SubsampleRatio, &out));
+        return out;
+    }
+    double score(const Image &d) const {
+        double out = 0.0;
+        check(fb_ssim_ref_score_nrgba(h_, d->data(), d->Stride, &out));
+        return out;
+    }
+};
+
+// Analyze — analyze.go:26-113 (ImageStats as fb_image_stats; Format / Quality carry Go's numeric values)
+inline fb_image_stats Analyze(const Image &img) {
+    fb_image_stats st;
+    check(fb_analyze(img->data(), img->Stride, img->W, img->H, &st));
+    return st;
+}
+
+// ApplyOrientation — exif.go:176-203 (orientations 1, 0 and unknown values return the same pointer)
+inline Image ApplyOrientation(const Image &img, int orient) {
+    int dw = 0, dh = 0;
+    if (check(fb_orientation_dims(orient, img->W, img->H, &dw, &dh)) == FB_IDENTITY) return img;
+    Image dst = NewNRGBA(dw, dh);
+    check(fb_apply_orientation(img->data(), img->Stride, img->W, img->H, orient, dst->data(), dst->Stride));
+    return dst;
+}
+
+// applyPalette + palettedToNRGBA — targetsize.go:479-545. palette: NRGBA entries with A == 255 (medianCut's output).
+struct Paletted {
+    std::vector<uint8_t> Pix;   // one index per pixel, Stride == W
+    int W = 0, H = 0;
+};
+inline Paletted applyPalette(const Image &src, const std::vector<uint8_t> &palette, Image *recon = nullptr) {
+    Paletted out;
+    out.W = src->W; out.H = src->H;
+    out.Pix.assign((size_t)src->W * src->H, 0);
+    if (recon) *recon = NewNRGBA(src->W, src->H);
+    check(fb_apply_palette(src->data(), src->Stride, src->W, src->H, palette.data(), (int)(palette.size() / 4), out.Pix.data(), src->W,
+                           recon ? (*recon)->data() : nullptr, recon ? (*recon)->Stride : 0));
+    return out;
+}
+
 // The sharder part of CompressBatch (batch.go:58-128): items [begin, end) of shard `shard`.
 struct ShardRange { int begin, end; };
 inline ShardRange BatchShard(int nItems, int nShards, int shard) {

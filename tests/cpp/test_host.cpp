@@ -115,6 +115,64 @@ int main() {
         fo_box_downsample(src->data(), src->Stride, 200, 100, ref->data(), ref->Stride, 50, 25);
         EXPECT(bd->Pix == ref->Pix);
     }
+    // ---- SURVEY §8(f1-f4) through the C++ mirror -------------------------------------------------------
+    {   // TestAnalyze (fennec_test.go:564-610)
+        fb_image_stats a200 = Analyze(makeTestImage(200, 200));
+        EXPECT(a200.width == 200 && a200.height == 200 && !a200.has_alpha && a200.entropy >= 1);
+        fb_image_stats solid = Analyze(makeSolidImage(100, 100, 128, 128, 128, 255));
+        EXPECT(solid.is_grayscale && solid.entropy <= 0.01);
+        fo_image_stats want;
+        fo_analyze(src->data(), src->Stride, 200, 100, &want);
+        fb_image_stats got = Analyze(src);
+        EXPECT(got.unique_colors == want.unique_colors && got.has_alpha == want.has_alpha && got.is_grayscale == want.is_grayscale);
+        EXPECT(std::fabs(got.entropy - want.entropy) <= 1e-9 && std::fabs(got.edge_density - want.edge_density) <= 1e-12);
+        EXPECT(std::fabs(got.mean_brightness - want.mean_brightness) <= 1e-9 * want.mean_brightness);
+        EXPECT(got.recommended_format == want.recommended_format && got.recommended_quality == want.recommended_quality);
+    }
+    {   // TestApplyOrientation (fennec_test.go:802-825)
+        Image o = makeTestImage(100, 50);
+        EXPECT(ApplyOrientation(o, 1) == o);
+        Image r90 = ApplyOrientation(o, 6);
+        EXPECT(r90->W == 50 && r90->H == 100);
+        Image r180 = ApplyOrientation(o, 3);
+        EXPECT(r180->W == 100 && r180->H == 50);
+        for (int orient = 2; orient <= 8; orient++) {
+            Image g = ApplyOrientation(o, orient);
+            Image ref = NewNRGBA(g->W, g->H);
+            EXPECT(fo_apply_orientation(o->data(), o->Stride, 100, 50, orient, ref->data(), ref->Stride) == 0);
+            EXPECT(g->Pix == ref->Pix);
+        }
+    }
+    {   // convertToNRGBA on a 4:2:0 image + the search session (compress.go:45-74)
+        YCbCr yc;
+        yc.W = 200; yc.H = 100; yc.YStride = 200; yc.CStride = 100; yc.SubsampleRatio = 2;
+        yc.Y.resize(200 * 100); yc.Cb.resize(100 * 50); yc.Cr.resize(100 * 50);
+        for (int y = 0; y < 100; y++)
+            for (int x = 0; x < 200; x++) yc.Y[y * 200 + x] = (uint8_t)((0.299 * src->at(x, y)[0] + 0.587 * src->at(x, y)[1] + 0.114 * src->at(x, y)[2]) + 0.5);
+        for (int y = 0; y < 50; y++)
+            for (int x = 0; x < 100; x++) {
+                const uint8_t *p = src->at(2 * x, 2 * y);
+                yc.Cb[y * 100 + x] = (uint8_t)(128.0 - 0.168736 * p[0] - 0.331264 * p[1] + 0.5 * p[2] + 0.5);
+                yc.Cr[y * 100 + x] = (uint8_t)(128.0 + 0.5 * p[0] - 0.418688 * p[1] - 0.081312 * p[2] + 0.5);
+            }
+        Image conv = convertToNRGBA(yc);
+        Image ref = NewNRGBA(200, 100);
+        EXPECT(fo_ycbcr_to_nrgba(yc.Y.data(), 200, yc.Cb.data(), yc.Cr.data(), 100, 200, 100, 2, ref->data(), ref->Stride) == 0);
+        EXPECT(conv->Pix == ref->Pix);
+        SSIMSession sess(src);
+        double viaSession = sess.score(yc), direct = SSIMFast(src, conv);
+        EXPECT(std::fabs(viaSession - direct) <= 2e-7 && viaSession > 0.5 && std::fabs(sess.score(conv) - direct) <= 2e-7);
+    }
+    {   // applyPalette + palettedToNRGBA (targetsize.go:479-545)
+        std::vector<uint8_t> pal;
+        for (int i = 0; i < 27; i++) { pal.push_back((uint8_t)((i % 3) * 120)); pal.push_back((uint8_t)(((i / 3) % 3) * 120)); pal.push_back((uint8_t)((i / 9) * 120)); pal.push_back(255); }
+        Image recon;
+        Paletted idx = applyPalette(src, pal, &recon);
+        std::vector<uint8_t> wantIdx(200 * 100);
+        Image wantRecon = NewNRGBA(200, 100);
+        fo_apply_palette(src->data(), src->Stride, 200, 100, pal.data(), 27, wantIdx.data(), 200, wantRecon->data(), wantRecon->Stride);
+        EXPECT(idx.Pix == wantIdx && recon->Pix == wantRecon->Pix);
+    }
     // sharder keeps input order (batch.go:71,108)
     int covered = 0;
     for (int sh = 0; sh < 8; sh++) { ShardRange r = BatchShard(1024, 8, sh); EXPECT(r.begin == covered); covered = r.end; }
