@@ -820,6 +820,188 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// AdaptiveSharpen, second version.  fx_tile_kernel<2> (kept as FB_ADAPTIVE_OLD=1) spent 170 instructions per pixel:
+// four inlined copies of the FP64 reference sequence for the rare ambiguous pixels plus ~130 for the fast path
+// (IEEE sqrt, per-channel bounds, clamps on both sides of the rounding).  Here
+//   * ambiguous pixels are only QUEUED per warp ((x, y) in 16+16 bits) and the exact FP64 sequence of
+//     effects.go:49-112 runs 32 at a time, one pixel per lane, re-reading the 3x3 neighbourhood through L1/L2;
+//   * |grad| = g2 * rsqrt(g2) (MUFU, <= 2 ulp), one bound per pixel, v = fma(la, diff, orig) with a single rounding,
+//     clamp to [0, 255] BEFORE the magic-number rounding so the low byte of the bit pattern is the result.
+// Error bound (relative, first order): g2 2^-23 -> sqrt halves it; rsqrt 2^-22, product 2^-24  =>  mag 3.6e-7;
+// x fl(1/400000): 4.8e-7; x fl(amount): 6.0e-7 on la; |la*diff| <= 765; the fma rounds once (<= 1020 * 2^-24).
+// eps = la * 255 * 7.5e-7 + 8e-5 (25 % margin on the first term) is a bound for every channel of the pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAdQ = 128 + 32;   // a warp adds at most 128 entries per row to fewer than 32 leftovers
+
+__device__ __forceinline__ uint32_t adaptive_exact_at(const uint8_t *img, int rs, int x, int y, double amount0) {
+    uint32_t n[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) n[ky * 3 + kx] = ld_nc_u32(img + (long long)(y - 1 + ky) * rs + (long long)(x - 1 + kx) * 4);
+    uint32_t bl[3];
+    blur3_rgb(n, bl);
+    const double amount = __dmul_rn(amount0, edge_strength(n));   // effects.go:74
+    const uint32_t c = n[4];
+    uint32_t o[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        const int orig = (int)((c >> (8 * ch)) & 0xFF);
+        const double val = __dadd_rn(small_int_to_double(orig), __dmul_rn(amount, small_int_to_double(orig - (int)bl[ch])));
+        o[ch] = clampf_magic(val);   // effects.go:82-83
+    }
+    return o[0] | (o[1] << 8) | (o[2] << 16) | (c & 0xFF000000u);
+}
+
+__global__ void __launch_bounds__(128) adaptive_tile_kernel(const FxTileParams p) {
+    __shared__ uint32_t ambQ[4][kAdQ];
+    __shared__ int ambN[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) ambN[warp] = 0;
+    __syncwarp();
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int yb = blockIdx.y * kFxRows, img = blockIdx.z;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *d = p.dst + (long long)img * p.dstImgStride;
+    const bool active = x0 < p.w;                     // inactive lanes still take part in the queue drains
+    const int xa = active ? x0 : 0;
+    const bool full = p.vecOK && xa + 4 <= p.w;
+    const int xl = max(xa - 1, 0), xr = min(xa + 4, p.w - 1);
+    const bool dvec = full && ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0);
+
+    auto load_row = [&](int y, uint32_t (&px)[6]) {
+        const uint8_t *row = s + (long long)min(max(y, 0), p.h - 1) * p.srcRowStride;
+        if (full) {
+            uint4 q = *reinterpret_cast<const uint4 *>(row + (long long)xa * 4);
+            px[1] = q.x; px[2] = q.y; px[3] = q.z; px[4] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) px[1 + i] = ld_nc_u32(row + (long long)min(xa + i, p.w - 1) * 4);
+        }
+        px[0] = ld_nc_u32(row + (long long)xl * 4);
+        px[5] = ld_nc_u32(row + (long long)xr * 4);
+    };
+    auto hsum = [&](const uint32_t (&px)[6], uint32_t (&hrb)[4], uint32_t (&hga)[4]) {
+        uint32_t rb[6], ga[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { rb[i] = px[i] & 0x00FF00FFu; ga[i] = (px[i] >> 8) & 0x00FF00FFu; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            hrb[i] = rb[i] + 2 * rb[i + 1] + rb[i + 2];
+            hga[i] = ga[i] + 2 * ga[i + 1] + ga[i + 2];
+        }
+    };
+    // integer lumas x1000 and their horizontal 1-2-1 / difference combinations for the Sobel sums
+    auto lumas = [&](const uint32_t (&px)[6], int (&L)[6]) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) L[i] = (int)__dp2a_lo(299u | (587u << 16), px[i], __dp2a_hi(114u, px[i], 0u));
+    };
+    const float amountF = (float)p.amount;
+    const float kMagic = 12582912.0f;
+
+    uint32_t pPrev[6], pCur[6], pNext[6];
+    uint32_t hPrevRB[4], hPrevGA[4], hCurRB[4], hCurGA[4], hNextRB[4], hNextGA[4];
+    int lPrev[6], lCur[6], lNext[6];
+    load_row(yb - 1, pPrev);
+    load_row(yb, pCur);
+    hsum(pPrev, hPrevRB, hPrevGA);
+    hsum(pCur, hCurRB, hCurGA);
+    lumas(pPrev, lPrev);
+    lumas(pCur, lCur);
+#pragma unroll 1
+    for (int r = 0; r < kFxRows; r++) {
+        const int y = yb + r;
+        if (y >= p.h) break;   // warp-uniform
+        load_row(y + 1, pNext);
+        hsum(pNext, hNextRB, hNextGA);
+        lumas(pNext, lNext);
+        int colsum[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) colsum[i] = lPrev[i] + 2 * lCur[i] + lNext[i];
+        uint32_t out[4];
+        uint32_t ambMask = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = xa + i;
+            const uint32_t c = pCur[1 + i];
+            uint32_t res = c;
+            const bool interior = x >= 1 && x < p.w - 1 && y >= 1 && y < p.h - 1;
+            if (interior) {
+                const uint32_t brb = ((hPrevRB[i] + 2 * hCurRB[i] + hNextRB[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+                const uint32_t bga = ((hPrevGA[i] + 2 * hCurGA[i] + hNextGA[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+                const int GX = colsum[i + 2] - colsum[i];
+                const int GY = (lNext[i] + 2 * lNext[i + 1] + lNext[i + 2]) - (lPrev[i] + 2 * lPrev[i + 1] + lPrev[i + 2]);
+                const float gxf = __int_as_float(GX + 0x4B400000) - kMagic;
+                const float gyf = __int_as_float(GY + 0x4B400000) - kMagic;
+                const float g2 = fmaxf(fmaf(gxf, gxf, gyf * gyf), 1e-30f);
+                const float la = amountF * fminf(g2 * rsqrtf(g2) * 2.5e-6f, 1.0f);
+                const float lim = 0.5f - fmaf(la, 255.0f * 7.5e-7f, 8e-5f);
+                // channels as floats straight from the bytes: [byte, 0, 0x40, 0x4B] = bits of 1.5 * 2^23 + byte
+                const float oR = __uint_as_float(__byte_perm(c, 0x4B400000u, 0x7650u)) - kMagic;
+                const float oG = __uint_as_float(__byte_perm(c, 0x4B400000u, 0x7651u)) - kMagic;
+                const float oB = __uint_as_float(__byte_perm(c, 0x4B400000u, 0x7652u)) - kMagic;
+                const float bR = __uint_as_float(__byte_perm(brb, 0x4B400000u, 0x7650u)) - kMagic;
+                const float bG = __uint_as_float(__byte_perm(bga, 0x4B400000u, 0x7650u)) - kMagic;
+                const float bB = __uint_as_float(__byte_perm(brb, 0x4B400000u, 0x7652u)) - kMagic;
+                const float o3[3] = {oR, oG, oB}, b3[3] = {bR, bG, bB};
+                float t3[3];
+                float worst = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    float v = fmaf(la, o3[ch] - b3[ch], o3[ch]);   // orig - blur is an exact small integer
+                    v = fminf(fmaxf(v, 0.0f), 255.0f);             // ties at -0.5 / 255.5 cannot change the clamped result
+                    t3[ch] = v + kMagic;
+                    worst = fmaxf(worst, fabsf(v - (t3[ch] - kMagic)));
+                }
+                if (worst >= lim) ambMask |= 1u << i;
+                res = pack_rgba_low_bytes(t3[0], t3[1], t3[2], c);
+            }
+            out[i] = res;
+        }
+        if (active) {
+            uint8_t *drow = d + (long long)y * p.dstRowStride + (long long)xa * 4;
+            if (dvec) {
+                *reinterpret_cast<uint4 *>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (xa + i < p.w) *reinterpret_cast<uint32_t *>(drow + i * 4) = out[i];
+            }
+            if (xa + 4 > p.w) ambMask &= (1u << (p.w - xa)) - 1u;
+            amb_push(ambMask, xa, y, 1, 0, ambQ[warp], &ambN[warp]);
+        }
+        __syncwarp();
+        {   // drain 32 at a time (warp-uniform decision on lane 0's view, see amb_drain)
+            int n = __shfl_sync(0xffffffffu, ambN[warp], 0);
+            if (n >= 32) {
+                while (n >= 32) {
+                    n -= 32;
+                    const uint32_t code = ambQ[warp][n + lane];
+                    const int ex = (int)(code & 0xFFFFu), ey = (int)(code >> 16);
+                    *reinterpret_cast<uint32_t *>(d + (long long)ey * p.dstRowStride + (long long)ex * 4) = adaptive_exact_at(s, p.srcRowStride, ex, ey, p.amount);
+                }
+                __syncwarp();
+                if (lane == 0) ambN[warp] = n;
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { pPrev[i] = pCur[i]; pCur[i] = pNext[i]; lPrev[i] = lCur[i]; lCur[i] = lNext[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { hPrevRB[i] = hCurRB[i]; hPrevGA[i] = hCurGA[i]; hCurRB[i] = hNextRB[i]; hCurGA[i] = hNextGA[i]; }
+    }
+    __syncwarp();
+    {   // leftovers
+        const int n = __shfl_sync(0xffffffffu, ambN[warp], 0);
+        if (lane < n) {
+            const uint32_t code = ambQ[warp][lane];
+            const int ex = (int)(code & 0xFFFFu), ey = (int)(code >> 16);
+            *reinterpret_cast<uint32_t *>(d + (long long)ey * p.dstRowStride + (long long)ex * 4) = adaptive_exact_at(s, p.srcRowStride, ex, ey, p.amount);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
@@ -874,6 +1056,7 @@ static int launch_fx(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long
             }
         }
         if (mode == 0) fx_tile_kernel<0, -1><<<tgrid, 128, 0, s>>>(t);
+        else if (mode == 2 && w <= 65535 && h <= 65535 && getenv("FB_ADAPTIVE_OLD") == nullptr) adaptive_tile_kernel<<<tgrid, 128, 0, s>>>(t);
         else if (mode == 2) fx_tile_kernel<2, -1><<<tgrid, 128, 0, s>>>(t);
         else if (k == 0) fx_tile_kernel<1, 0><<<tgrid, 128, 0, s>>>(t);
         else if (k == 1) fx_tile_kernel<1, 1><<<tgrid, 128, 0, s>>>(t);
