@@ -326,3 +326,28 @@ def test_adaptive_sharpen_fast_path_bit_exact(kind, strength, lib, oracle):
     else:
         src = S.make_striped_image(640, 360, 7)
     assert np.array_equal(api.AdaptiveSharpen(src, strength), oracle.adaptive_sharpen(src, strength))
+
+
+# ---- adversarial inputs for the exact-path queues ---------------------------------------------------------------
+
+def test_blur_all_outputs_ambiguous(lib, oracle):
+    """Columns alternating 0 / 1: every horizontal tap sum is 0.5 +- ~1e-9 (the even and odd taps of a sigma = 2
+    Gaussian each add up to one half), so EVERY output lies inside the FP32 error bound and the reference's own
+    float64 sum decides each byte.  Fills the per-warp exact queues to capacity (32 x 16 entries per chunk)."""
+    w, h = 1100, 300
+    img = np.zeros((h, w, 4), np.uint8)
+    img[:, 1::2, :3] = 1
+    img[..., 3] = np.arange(w, dtype=np.uint8)[None, :]
+    assert np.array_equal(api.GaussianBlur(img, 2.0), oracle.gaussian_blur(img, 2.0))
+    imgT = np.ascontiguousarray(img.transpose(1, 0, 2))          # rows alternate: the vertical pass is the ambiguous one
+    assert np.array_equal(api.GaussianBlur(imgT, 2.0), oracle.gaussian_blur(imgT, 2.0))
+
+
+def test_lanczos_all_outputs_take_the_exact_queue(lib, oracle):
+    """alpha = 1 everywhere: the premultiplied sums are ~1, the FP32 bound on r/a exceeds 0.25 and every output of the
+    integer-ratio kernels is queued — the block queue of the pipelined horizontal pass must drain every other row."""
+    src = S.noise_image(2048, 96, 21)
+    src[..., 3] = 1
+    assert np.array_equal(api.lanczos_resize(src, 512, 24), oracle.lanczos_resize(src, 512, 24))
+    src[..., 3] = (np.arange(2048) % 3).astype(np.uint8)[None, :]   # alpha 0 / 1 / 2: the a > 0.5 gate itself is in play
+    assert np.array_equal(api.lanczos_resize(src, 512, 24), oracle.lanczos_resize(src, 512, 24))
