@@ -2,17 +2,17 @@
 //
 // The reference makes one full pass (luminance histogram, brightness sum, alpha / grayscale tests, a sampled
 // colour set capped at 1024 entries) and two sampled passes (contrast on a <= 100x100 grid, Sobel edge density on a
-// <= ~200x200 grid).  Here:
-//   K9a analyze_scan_kernel    the full pass: 4 B/px read once, HBM-bound.  Luminance x1000 is the exact integer
+// <= ~200x200 grid).  Here (K9a-c are block roles of ONE launch, analyze_all_kernel):
+//   K9a analyze_scan_role      the full pass: 4 B/px read once, HBM-bound.  Luminance x1000 is the exact integer
 //                              L = 299R + 587G + 114B (two IDP); the histogram bin int(lum + 0.5) is (L + 500) / 1000
 //                              except when (L + 500) % 1000 == 0, where the mathematically exact value sits ON the
 //                              bin edge and the reference's FP64 rounding decides — only then the FP64 expression
 //                              of analyze.go:63 is evaluated (1 pixel in 1000).  Per-warp shared-memory
 //                              histograms, integer sums: the result does not depend on the summation order.
-//   K9b analyze_sample_kernel  the colour set: sample k is pixel k*step in scan order (analyze.go:45-48, 73-76);
+//   K9b analyze_sample_role    the colour set: sample k is pixel k*step in scan order (analyze.go:45-48, 73-76);
 //                              keys go into an open-addressing table with 64-bit CAS, distinct insertions are counted
 //                              (the map stops growing at 1024, so UniqueColors = min(distinct, 1024)).
-//   K9c analyze_edge_kernel    Sobel on the sample grid in the reference's FP64 expression order (analyze.go:148-156);
+//   K9c analyze_edge_role      Sobel on the sample grid in the reference's FP64 expression order (analyze.go:148-156);
 //                              integer counts.
 //   K9d analyze_contrast_kernel  sum((lum - mean)^2) on the grid, one block, fixed reduction tree (deterministic).
 // MeanBrightness: the reference adds 8 M doubles sequentially; sum(L)/1000/n is the same quantity without the
