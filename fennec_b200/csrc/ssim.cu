@@ -100,7 +100,10 @@ struct StripCtx {
 #ifndef FB_SSIM_MINB4
 #define FB_SSIM_MINB4 2
 #endif
-constexpr int kStages = 4;  // rows in flight per warp (power of two: the stage is the ring slot & 3)
+#ifndef FB_SSIM_STAGES
+#define FB_SSIM_STAGES 4
+#endif
+constexpr int kStages = FB_SSIM_STAGES;  // rows in flight per warp (power of two: the stage is the ring slot & (kStages-1))
 
 // The row walk of one strip segment; returns this lane's sum of ssim/4 over its valid outputs.
 template <int CPL, bool FAST>
@@ -835,10 +838,16 @@ Geo geometry(int w, int h, int n) {
     g.outc = 32 * g.cpl - 8;
     int ow = w - 8, oh = h - 8;
     g.nsx = (ow + g.outc - 1) / g.outc;
-    // Aim for >= ~8 warps per SM over 148 SMs while keeping the 7-row warm-up overhead small.
-    long long want = 148LL * 16;
-    int rs = 128;  // 256 was measured slightly slower (tail effects outweigh the smaller 7-row warm-up)
-    while (rs > 16 && (long long)n * g.nsx * ((oh + rs - 1) / rs) < want) rs >>= 1;
+    // Rows per segment: every segment pays a 7-row warm-up (work ~ oh + 7*oh/rs per strip) and the last blocks of the
+    // grid straggle for about half a segment.  Measured on 16 4K pairs: rs 64 / 128 / 256 / 512 -> 0.546 / 0.542 /
+    // 0.574 / 0.612 ms; a closed-form optimum of that model (rs = 112 at 16 pairs, 160 at 32) was no better than a
+    // flat 128 (0.551 / 1.053 vs 0.542 / 1.050 ms), so: 128, halved while the grid would not fill the GPU, never
+    // below 32 (one 4K pair: 0.050 ms at 32 against 0.056 ms at 128).  FB_SSIM_RS overrides for experiments.
+    static const int rsForce = [] { const char *e = getenv("FB_SSIM_RS"); int v = e ? atoi(e) : 0; return (v >= 16 && v <= 4096) ? v : 0; }();
+    const long long want = 148LL * 16;
+    int rs = rsForce ? rsForce : 128;
+    if (!rsForce)
+        while (rs > 32 && (long long)n * g.nsx * ((oh + rs - 1) / rs) < want) rs >>= 1;
     g.rs = rs;
     g.nsy = (oh + rs - 1) / rs;
     return g;
