@@ -841,13 +841,14 @@ Geo geometry(int w, int h, int n) {
     // Rows per segment: every segment pays a 7-row warm-up (work ~ oh + 7*oh/rs per strip) and the last blocks of the
     // grid straggle for about half a segment.  Measured on 16 4K pairs: rs 64 / 128 / 256 / 512 -> 0.546 / 0.542 /
     // 0.574 / 0.612 ms; a closed-form optimum of that model (rs = 112 at 16 pairs, 160 at 32) was no better than a
-    // flat 128 (0.551 / 1.053 vs 0.542 / 1.050 ms), so: 128, halved while the grid would not fill the GPU, never
-    // below 32 (one 4K pair: 0.050 ms at 32 against 0.056 ms at 128).  FB_SSIM_RS overrides for experiments.
+    // flat 128 (0.551 / 1.053 vs 0.542 / 1.050 ms), so: 128, halved (down to 16) while the grid has fewer than 12
+    // warps per SM (one 4K pair: 32 rows, 0.050 ms against 0.056 ms at 128; 16 MS-SSIM thumbnails: 16 rows).
+    // FB_SSIM_RS overrides for experiments.
     static const int rsForce = [] { const char *e = getenv("FB_SSIM_RS"); int v = e ? atoi(e) : 0; return (v >= 16 && v <= 4096) ? v : 0; }();
-    const long long want = 148LL * 16;
+    const long long want = 148LL * 12;
     int rs = rsForce ? rsForce : 128;
     if (!rsForce)
-        while (rs > 32 && (long long)n * g.nsx * ((oh + rs - 1) / rs) < want) rs >>= 1;
+        while (rs > 16 && (long long)n * g.nsx * ((oh + rs - 1) / rs) < want) rs >>= 1;
     g.rs = rs;
     g.nsy = (oh + rs - 1) / rs;
     return g;
