@@ -186,23 +186,31 @@ __global__ void __launch_bounds__(kScanThreads) analyze_all_kernel(const Analyze
         analyze_edge_role(bx - a.scanBlocks - a.sampleBlocks, a.imgs, a.imgStride, a.rowStride, a.w, a.h, a.edgeX, a.edgeY, a.edgeNx, a.edgeNy, a.raw);
 }
 
-__global__ void __launch_bounds__(256) analyze_contrast_kernel(const uint8_t *imgs, long long imgStride, int rowStride, int w, int h,
-                                                               int sx, int sy, int nx, int ny, AnalyzeRaw *raw) {
-    __shared__ double part[256];
+constexpr int kContrastThreads = 1024;   // <= 10 000 grid samples per image: ~10 per thread, so the load latency is paid ~5 times, not 40
+__global__ void __launch_bounds__(kContrastThreads) analyze_contrast_kernel(const uint8_t *imgs, long long imgStride, int rowStride, int w, int h,
+                                                                            int sx, int sy, int nx, int ny, AnalyzeRaw *raw) {
+    __shared__ double part[kContrastThreads];
     const int img = blockIdx.x;
     AnalyzeRaw *r = raw + img;
     // MeanBrightness (analyze.go:86) from the exact integer sum
     const double mean = __ddiv_rn(__ddiv_rn((double)r->sumL, 1000.0), (double)((long long)w * h));
     const uint8_t *b = imgs + (long long)img * imgStride;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < nx * ny; i += 256) {
-        const int x = (i % nx) * sx, y = (i / nx) * sy;
-        const double d = __dadd_rn(lum_fp64(ld_nc_u32(b + (long long)y * rowStride + (long long)x * 4)), -mean);
-        acc = __dadd_rn(acc, __dmul_rn(d, d));
+    const int n = nx * ny;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 2 * kContrastThreads) {   // two independent loads in flight
+        const int i1 = i0 + kContrastThreads;
+        const uint32_t v0 = ld_nc_u32(b + (long long)((i0 / nx) * sy) * rowStride + (long long)((i0 % nx) * sx) * 4);
+        const uint32_t v1 = i1 < n ? ld_nc_u32(b + (long long)((i1 / nx) * sy) * rowStride + (long long)((i1 % nx) * sx) * 4) : 0u;
+        const double d0 = __dadd_rn(lum_fp64(v0), -mean);
+        acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+        if (i1 < n) {
+            const double d1 = __dadd_rn(lum_fp64(v1), -mean);
+            acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+        }
     }
     part[threadIdx.x] = acc;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = kContrastThreads / 2; o > 0; o >>= 1) {   // fixed tree: the result does not depend on scheduling
         if ((int)threadIdx.x < o) part[threadIdx.x] = __dadd_rn(part[threadIdx.x], part[threadIdx.x + o]);
         __syncthreads();
     }
@@ -256,7 +264,7 @@ int launch_analyze(cudaStream_t s, const uint8_t *imgs, long long imgStride, int
     const int edgeBlocks = (st.edgeNx * st.edgeNy + kScanThreads - 1) / kScanThreads;
     analyze_all_kernel<<<dim3(a.scanBlocks + a.sampleBlocks + edgeBlocks, n), kScanThreads, 0, s>>>(a);
     int launches = 1;
-    analyze_contrast_kernel<<<n, 256, 0, s>>>(imgs, imgStride, rowStride, w, h, st.contrastX, st.contrastY, st.contrastNx, st.contrastNy, raw);
+    analyze_contrast_kernel<<<n, kContrastThreads, 0, s>>>(imgs, imgStride, rowStride, w, h, st.contrastX, st.contrastY, st.contrastNx, st.contrastNy, raw);
     launches++;
     FB_LAUNCHED(launches);
     FB_CUDA(cudaGetLastError());
