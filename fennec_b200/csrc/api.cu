@@ -450,8 +450,7 @@ static int pipeline_ssim_fast(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b,
         uint8_t *da = (uint8_t *)c->ws.take((size_t)imgBytes * n);
         uint8_t *db = (uint8_t *)c->ws.take((size_t)imgBytes * n);
         if (!da || !db) { set_error("internal: workspace under-reserved (ssim_fast)"); return FB_E_INVALID; }
-        FB_TRY(launch_box(s, a.p, a.imgStride, a.rowStride, w, h, da, imgBytes, pitch, nw, nh, n, nullptr));
-        FB_TRY(launch_box(s, b.p, b.imgStride, b.rowStride, w, h, db, imgBytes, pitch, nw, nh, n, nullptr));
+        FB_TRY(launch_box_pair(s, a.p, a.imgStride, a.rowStride, b.p, b.imgStride, b.rowStride, w, h, da, db, imgBytes, pitch, nw, nh, n));
         a = ImgBatch{da, imgBytes, pitch};
         b = ImgBatch{db, imgBytes, pitch};
         w = nw;

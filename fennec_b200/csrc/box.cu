@@ -34,6 +34,11 @@ struct BoxParams {
     int dxChunk;   // output columns per CTA
     int dyPerCta;  // output rows per CTA (small boxes: amortise the CTA over more source rows)
     int vecOK;
+    // optional second batch in the same launch (SSIMFast downsamples both images of every pair): blockIdx.z >= nFirst
+    const uint8_t *src2;
+    uint8_t *dst2;
+    long long src2ImgStride;
+    int src2RowStride, nFirst;
 };
 
 // ssim.go:255-265 / 268-278
@@ -54,9 +59,14 @@ __device__ __forceinline__ uint32_t box_finish(uint32_t sr, uint32_t sg, uint32_
     return r | (g << 8) | (b << 16) | (a << 24);
 }
 
-__global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams p) {
+__global__ void __launch_bounds__(kThreads) box_rows_kernel(const BoxParams pIn) {
     __shared__ uint2 colsum[kSpanMax + 8];  // per source column: (R | B<<16, G | A<<16) 16-bit sums
-    const int img = blockIdx.z;
+    BoxParams p = pIn;
+    int img = blockIdx.z;
+    if (img >= p.nFirst) {   // second batch: same dims, its own base / strides
+        img -= p.nFirst;
+        p.src = p.src2; p.dst = p.dst2; p.srcImgStride = p.src2ImgStride; p.srcRowStride = p.src2RowStride;
+    }
     const int dx0 = blockIdx.x * p.dxChunk;
     const int dx1 = min(dx0 + p.dxChunk, p.dstW);
     const int dyEnd = min((int)(blockIdx.y + 1) * p.dyPerCta, p.dstH);
@@ -336,24 +346,52 @@ void box_edges_host(int src, int dst, int *lo, int *hi) {
     }
 }
 
+static int launch_box_impl(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
+                           int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
+                           const uint8_t *src2, long long src2ImgStride, int src2RowStride, uint8_t *dst2);
+
 int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
                const int *unused_edges) {
     (void)unused_edges;
+    return launch_box_impl(s, src, srcImgStride, srcRowStride, srcW, srcH, dst, dstImgStride, dstRowStride, dstW, dstH, n,
+                           nullptr, 0, 0, nullptr);
+}
+
+// Both images of every pair in one launch (same dims; the destinations share strides): one grid instead of two
+// half-sized ones, so the tail of the first does not idle the GPU.
+int launch_box_pair(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA, const uint8_t *srcB,
+                    long long srcImgStrideB, int srcRowStrideB, int srcW, int srcH, uint8_t *dstA, uint8_t *dstB,
+                    long long dstImgStride, int dstRowStride, int dstW, int dstH, int n) {
+    return launch_box_impl(s, srcA, srcImgStrideA, srcRowStrideA, srcW, srcH, dstA, dstImgStride, dstRowStride, dstW, dstH, n,
+                           srcB, srcImgStrideB, srcRowStrideB, dstB);
+}
+
+static int launch_box_impl(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
+                           int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
+                           const uint8_t *src2, long long src2ImgStride, int src2RowStride, uint8_t *dst2) {
     if (n <= 0) return FB_OK;
     BoxParams p;
+    p.src2 = src2; p.dst2 = dst2; p.src2ImgStride = src2ImgStride; p.src2RowStride = src2RowStride; p.nFirst = n;
     p.src = src; p.dst = dst;
     p.srcImgStride = srcImgStride; p.dstImgStride = dstImgStride;
     p.srcRowStride = srcRowStride; p.dstRowStride = dstRowStride;
     p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH;
     p.xRatio = (double)srcW / (double)dstW;   // ssim.go:251-252
     p.yRatio = (double)srcH / (double)dstH;
-    p.vecOK = (((uintptr_t)src | (uintptr_t)srcImgStride | (uintptr_t)srcRowStride) & 15) == 0;
+    p.vecOK = (((uintptr_t)src | (uintptr_t)srcImgStride | (uintptr_t)srcRowStride | (uintptr_t)src2 | (uintptr_t)src2ImgStride |
+                 (uintptr_t)src2RowStride) & 15) == 0;
     // Fast path needs: disjoint ascending boxes (ratio >= 1), <= 256 rows per box (16-bit sums),
     // and at least one output column per shared-memory span.
     int maxBoxW = (int)p.xRatio + 2, maxBoxH = (int)p.yRatio + 2;
     bool fast = p.xRatio >= 1.0 && p.yRatio >= 1.0 && maxBoxH <= 256 && maxBoxW <= kSpanMax / 2;
-    if (srcW == 2 * dstW && srcH == 2 * dstH) {  // every box is exactly 2x2
+    const bool exact2x = srcW == 2 * dstW && srcH == 2 * dstH;
+    if (src2 != nullptr && (exact2x || !fast)) {   // only box_rows_kernel understands the second batch
+        int rc = launch_box_impl(s, src, srcImgStride, srcRowStride, srcW, srcH, dst, dstImgStride, dstRowStride, dstW, dstH, n, nullptr, 0, 0, nullptr);
+        if (rc != FB_OK) return rc;
+        return launch_box_impl(s, src2, src2ImgStride, src2RowStride, srcW, srcH, dst2, dstImgStride, dstRowStride, dstW, dstH, n, nullptr, 0, 0, nullptr);
+    }
+    if (exact2x) {  // every box is exactly 2x2
         p.dxChunk = 0; p.dyPerCta = 1;
         dim3 grid(((srcW + 3) / 4 + kThreads - 1) / kThreads, dstH, n);
         box2x_kernel<<<grid, kThreads, 0, s>>>(p);
@@ -364,7 +402,7 @@ int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int s
         p.dxChunk = chunk;
         // ~32 source rows per CTA: one output row for 15x15 boxes, 16 output rows for the 2x cascade
         p.dyPerCta = maxBoxH >= 32 ? 1 : (32 / maxBoxH < 1 ? 1 : 32 / maxBoxH);
-        dim3 grid((dstW + chunk - 1) / chunk, (dstH + p.dyPerCta - 1) / p.dyPerCta, n);
+        dim3 grid((dstW + chunk - 1) / chunk, (dstH + p.dyPerCta - 1) / p.dyPerCta, src2 ? 2 * n : n);
         box_rows_kernel<<<grid, kThreads, 0, s>>>(p);
     } else {
         p.dxChunk = 0;

@@ -86,6 +86,9 @@ int launch_msssim_combine(cudaStream_t s, const double *levelScores, int nLevels
 int launch_box(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int dstH, int n,
                const int *reserved);
+int launch_box_pair(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA, const uint8_t *srcB,
+                    long long srcImgStrideB, int srcRowStrideB, int srcW, int srcH, uint8_t *dstA, uint8_t *dstB,
+                    long long dstImgStride, int dstRowStride, int dstW, int dstH, int n);
 void box_edges_host(int src, int dst, int *lo, int *hi);
 // MS-SSIM level step: thumbnail + half-resolution image of both batches from one read; returns 1 when not applicable.
 int launch_box_fused(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA,
