@@ -462,14 +462,37 @@ static int pipeline_ssim_fast(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b,
                        scoreStride, scratch);
 }
 
+// Level l can take the fused step (thumbnail + next level from one read) as far as dims go; *tw/*th = thumbnail dims.
+static bool msssim_level_fusable(const std::vector<MsLevel> &plan, int l, int *tw, int *th) {
+    const int L = (int)plan.size();
+    return l + 1 < L && ssim_fast_dims(plan[l].w, plan[l].h, tw, th) && plan[l + 1].w * 2 == plan[l].w && plan[l + 1].h * 2 == plan[l].h;
+}
+// Consecutive fusable levels from l on that share l's thumbnail dims: what one batched K1 launch can score.
+static int msssim_run_capacity(const std::vector<MsLevel> &plan, int l) {
+    int tw0, th0, tw, th, k = 0;
+    if (!msssim_level_fusable(plan, l, &tw0, &th0)) return 0;
+    while (l + k < (int)plan.size() && msssim_level_fusable(plan, l + k, &tw, &th) && tw == tw0 && th == th0) k++;
+    return k;
+}
+
 static size_t msssim_scratch(int w, int h, int n) {
     std::vector<MsLevel> plan = msssim_plan(w, h);
+    const size_t L = plan.size();
     size_t bytes = 0, fast = 0;
-    for (size_t l = 0; l < plan.size(); l++) {
+    for (size_t l = 0; l < L; l++) {
         if (l > 0) bytes += 2 * align_up((size_t)dev_pitch(plan[l].w) * plan[l].h * n, 256);
         fast = std::max(fast, ssim_fast_scratch(plan[l].w, plan[l].h, n));
     }
-    bytes += fast * plan.size();  // arena is bump-only within a call
+    // the arena is bump-only within a call.  A run of fused levels reserves its thumbnails when it opens and scores
+    // them with one batched K1 launch; if the fused kernel declines a level (unaligned caller buffers at level 0),
+    // the next level opens a new run, so every level's capacity is budgeted once.
+    bytes += fast * L;
+    for (size_t l = 0; l < L; l++) {
+        int tw, th;
+        const int cap = msssim_run_capacity(plan, (int)l);
+        if (cap > 0 && msssim_level_fusable(plan, (int)l, &tw, &th))
+            bytes += 2 * align_up((size_t)dev_pitch(tw) * th * n * cap, 256) + ssim_scratch_bytes(tw, th, n * cap) + 1024;
+    }
     bytes += align_up(sizeof(double) * (size_t)n * 5, 256) * 2 + 1024;
     return bytes;
 }
@@ -478,13 +501,26 @@ static size_t msssim_scratch(int w, int h, int n) {
 static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, int w, int h, int n, double *out) {
     std::vector<MsLevel> plan = msssim_plan(w, h);
     const int L = (int)plan.size();
-    double *levelScores = (double *)c->ws.take(sizeof(double) * (size_t)n * L);
+    double *levelScores = (double *)c->ws.take(sizeof(double) * (size_t)n * L);   // level-major: score(l, i) at [l*n + i]
     double *wdev = (double *)c->ws.take(sizeof(double) * 8);
     double *wpin = (double *)c->pin.take(sizeof(double) * 8);
     if (!levelScores || !wdev || !wpin) { set_error("internal: workspace under-reserved (msssim)"); return FB_E_INVALID; }
     for (int l = 0; l < L; l++) wpin[l] = plan[l].weight;
     FB_CUDA(cudaMemcpyAsync(wdev, wpin, sizeof(double) * L, cudaMemcpyHostToDevice, s));
     mark_pin_busy(c, s);
+    // Thumbnails of consecutive fused levels that share dims (8K: levels 0-3 are all 512x288) are kept side by side
+    // and scored by ONE K1 launch at the end of the run instead of one small launch per level.
+    struct Run { int l0 = 0, count = 0, tw = 0, th = 0, tpitch = 0; long long tBytes = 0; uint8_t *ta = nullptr, *tb = nullptr; } run;
+    auto flush_run = [&]() -> int {
+        if (run.count == 0) return FB_OK;
+        const int pairs = run.count * n;
+        void *scratch = c->ws.take(ssim_scratch_bytes(run.tw, run.th, pairs));
+        if (!scratch) { set_error("internal: workspace under-reserved (ssim batch)"); return FB_E_INVALID; }
+        int rc = launch_ssim(c, s, run.ta, run.tb, run.tBytes, run.tBytes, run.tpitch, run.tpitch, run.tw, run.th, pairs,
+                             levelScores + (size_t)run.l0 * n, 1, scratch);
+        run.count = 0;
+        return rc;
+    };
     ImgBatch ca = a, cb = b;
     for (int l = 0; l < L; l++) {
         const int lw = plan[l].w, lh = plan[l].h;
@@ -503,27 +539,28 @@ static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, in
         // image, one kernel reads it once and writes both (box.cu: box_fused_kernel).
         int tw, th;
         bool fused = false;
-        if (l + 1 < L && ssim_fast_dims(lw, lh, &tw, &th) && plan[l + 1].w * 2 == lw && plan[l + 1].h * 2 == lh) {
-            int tpitch = dev_pitch(tw);
-            long long tBytes = (long long)tpitch * th;
-            size_t mark = c->ws.off;
-            uint8_t *ta = (uint8_t *)c->ws.take((size_t)tBytes * n);
-            uint8_t *tb = (uint8_t *)c->ws.take((size_t)tBytes * n);
-            if (!ta || !tb) { set_error("internal: workspace under-reserved (msssim thumbs)"); return FB_E_INVALID; }
+        if (msssim_level_fusable(plan, l, &tw, &th)) {
+            if (run.count > 0 && (run.tw != tw || run.th != th)) FB_TRY(flush_run());
+            if (run.count == 0) {   // open a run: room for the thumbnails of the levels it can cover
+                const int cap = msssim_run_capacity(plan, l);
+                run.l0 = l; run.tw = tw; run.th = th; run.tpitch = dev_pitch(tw);
+                run.tBytes = (long long)run.tpitch * th;
+                run.ta = (uint8_t *)c->ws.take((size_t)run.tBytes * n * cap);
+                run.tb = (uint8_t *)c->ws.take((size_t)run.tBytes * n * cap);
+                if (!run.ta || !run.tb) { set_error("internal: workspace under-reserved (msssim thumbs)"); return FB_E_INVALID; }
+            }
+            uint8_t *ta = run.ta + (size_t)run.tBytes * n * run.count, *tb = run.tb + (size_t)run.tBytes * n * run.count;
             int rc = launch_box_fused(s, ca.p, ca.imgStride, ca.rowStride, cb.p, cb.imgStride, cb.rowStride, lw, lh, ta, tb,
-                                      tBytes, tpitch, tw, th, (uint8_t *)na.p, (uint8_t *)nb.p, na.imgStride, na.rowStride, n);
+                                      run.tBytes, run.tpitch, tw, th, (uint8_t *)na.p, (uint8_t *)nb.p, na.imgStride, na.rowStride, n);
             if (rc < 0) return rc;
             if (rc == FB_OK) {
-                void *scratch = c->ws.take(ssim_scratch_bytes(tw, th, n));
-                if (!scratch) { set_error("internal: workspace under-reserved (ssim)"); return FB_E_INVALID; }
-                FB_TRY(launch_ssim(c, s, ta, tb, tBytes, tBytes, tpitch, tpitch, tw, th, n, levelScores + l, L, scratch));
+                run.count++;
                 fused = true;
-            } else {
-                c->ws.off = mark;  // not applicable: give the thumbnails back, take the unfused path
             }
         }
         if (!fused) {
-            FB_TRY(pipeline_ssim_fast(c, s, ca, cb, lw, lh, n, levelScores + l, L));
+            FB_TRY(flush_run());
+            FB_TRY(pipeline_ssim_fast(c, s, ca, cb, lw, lh, n, levelScores + (size_t)l * n, 1));
             if (l + 1 < L) {
                 FB_TRY(launch_box(s, ca.p, ca.imgStride, ca.rowStride, lw, lh, (uint8_t *)na.p, na.imgStride, na.rowStride, plan[l + 1].w, plan[l + 1].h, n, nullptr));
                 FB_TRY(launch_box(s, cb.p, cb.imgStride, cb.rowStride, lw, lh, (uint8_t *)nb.p, nb.imgStride, nb.rowStride, plan[l + 1].w, plan[l + 1].h, n, nullptr));
@@ -532,6 +569,7 @@ static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, in
         ca = na;
         cb = nb;
     }
+    FB_TRY(flush_run());
     return launch_msssim_combine(s, levelScores, L, n, wdev, out);
 }
 

@@ -812,7 +812,7 @@ __global__ void msssim_combine_kernel(const double *levelScores, int nLevels, in
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double r = 0.0;
-    for (int l = 0; l < nLevels; l++) r += weights[l] * log(fmax(levelScores[(long long)i * nLevels + l], 1e-10));
+    for (int l = 0; l < nLevels; l++) r += weights[l] * log(fmax(levelScores[(long long)l * n + i], 1e-10));   // level-major
     out[i] = exp(r);
 }
 
