@@ -287,7 +287,10 @@ __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const
 #endif
 }
 
-constexpr int kHRows = 8;  // rows one warp walks in the horizontal pass (double-buffered staging)
+#ifndef FB_BLUR_HROWS
+#define FB_BLUR_HROWS 8
+#endif
+constexpr int kHRows = FB_BLUR_HROWS;  // rows one warp walks in the horizontal pass (double-buffered staging)
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -397,7 +400,10 @@ __global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p)
 // the loads are hidden behind ~300 FFMA2s and every tmp row is read 1 + 2R/kVSeg times instead of
 // 1 + 2R/kTile.  Alpha: the horizontal pass has already copied the source alpha into tmp (effects.go:189), so the
 // centre tap carries exactly the byte effects.go:215 copies — the original image is not read again.
-constexpr int kVSeg = 240;  // rows per thread segment (2160 = 9 * 240; halo 12/240)
+#ifndef FB_BLUR_VSEG
+#define FB_BLUR_VSEG 240
+#endif
+constexpr int kVSeg = FB_BLUR_VSEG;  // rows per thread segment (2160 = 9 * 240; halo 12/240)
 
 template <int R>
 __global__ void __launch_bounds__(128, 4) blur_v_fast_kernel(const BlurParams p) {

@@ -238,7 +238,10 @@ struct IntRatioParams {
     float w[28];    // the T shared weights (T <= 24 used)
 };
 
-constexpr int kRowsPerBlock = 8;  // horizontal pass: rows one block walks (double-buffered staging)
+#ifndef FB_LZ_ROWS
+#define FB_LZ_ROWS 8
+#endif
+constexpr int kRowsPerBlock = FB_LZ_ROWS;  // horizontal pass: rows one block walks (double-buffered staging); <= 8 (queue row code is 3 bits)
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
