@@ -224,7 +224,9 @@ FB_API int fb_adaptive_sharpen_batch_dev(int device, void *stream, const uint8_t
 FB_API int fb_lanczos_resize_batch_dev(int device, void *stream, const uint8_t *src, int64_t srcImgStride,
                                 int srcRowStride, int srcW, int srcH, uint8_t *dst, int64_t dstImgStride,
                                 int dstRowStride, int dstW, int dstH, int n);
-/* Bytes of scratch the _dev call above needs for these dims (the library keeps it per thread). */
+/* Bytes of scratch the _dev call above needs for these dims. The library keeps ONE grow-only scratch arena per
+ * calling thread and device and re-uses it from the start in every call: work enqueued by one thread must
+ * therefore go to one stream at a time (or be synchronised between streams); different threads never share. */
 FB_API size_t fb_workspace_bytes(const char *op, int w, int h, int dstW, int dstH, int n);
 
 /* ---- batch sharder (batch.go:58-128) ------------------------------------------------------ */
