@@ -5,7 +5,7 @@
 // converting here removes that loop and 63 % of the PCIe bytes of every search iteration.
 //
 // Arithmetic = Go's color.YCbCr.RGBA() followed by convert.go:48-53's `uint8(v >> 8)` (image/color/ycbcr.go, Go
-// 1.25.5 standard library — not under /root/reference; restated, see oracle/fennec_oracle.c):
+// 1.25.5 standard library — not under /root/reference; restated):
 //     yy1 = Y * 0x10101;  r = yy1 + 91881*cr1;  g = yy1 - 22554*cb1 - 46802*cr1;  b = yy1 + 116130*cb1
 //     channel = (v in [0, 2^24)) ? v >> 16 : (v < 0 ? 0 : 255)            ==  clamp(v >> 16, 0, 255)
 // (arithmetic shift; the equality is checked exhaustively over all 2^24 triples in tests/).  Chroma addressing is

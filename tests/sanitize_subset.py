@@ -2,7 +2,7 @@
 meant to run under `compute-sanitizer --tool memcheck`. Also checks results against the oracle."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 from fennec_b200 import api, synth as S
 from oracle import pyoracle as O
 
