@@ -97,6 +97,9 @@ struct StripCtx {
     uint8_t *ring;        // [kStages][2 images][32*CPL*4 bytes]
 };
 
+#ifndef FB_SSIM_F64FORMULA
+#define FB_SSIM_F64FORMULA 0
+#endif
 #ifndef FB_SSIM_MINB4
 #define FB_SSIM_MINB4 2
 #endif
@@ -262,6 +265,16 @@ __device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
             // mab = (mua', mub'); mqp = (E[a'^2+b'^2] + C2, E[a'b'] + C2/2).  Formula packed WITHIN the pixel
             // (pairs (m,nn), (A1h,B1), (A2h,B2), (num,den)): 10 FMA-pipe instructions instead of 13, no transposes.
             // (Packing across two pixels was measured slower: the pair transposes cost more MOVs than they save.)
+#if FB_SSIM_F64FORMULA
+            // Experiment: the 13-op formula on the otherwise idle FP64 pipe (the FP32 FMA pipe is the binding resource).
+            const double da = (double)mab.x, db = (double)mab.y;
+            const double dm = da * db, dnn = fma(da, da, db * db);
+            const double dth = fma((double)c, da + db, (double)kTh);
+            const double n1 = dth + dm, d1 = fma(2.0, dth, dnn);
+            const double n2 = (double)mqp.y - dm, d2 = (double)mqp.x - dnn;
+            float ssim4 = __fdividef((float)(n1 * n2), (float)(d1 * d2));
+            fs[i] += q.valid[i] ? ssim4 : 0.f;
+#else
             const float2 sq = __fmul2_rn(mab, mab);                       // (mua'^2, mub'^2)
             const float2 mn = make_float2(mab.x * mab.y, sq.x + sq.y);    // (m, nn)
             const float th = fmaf(c, mab.x + mab.y, kTh);
@@ -270,6 +283,7 @@ __device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
             const float2 nd = __fmul2_rn(AB1, AB2);                       // (num/4, den)
             float ssim4 = __fdividef(nd.x, nd.y);                         // ssim / 4
             fs[i] += q.valid[i] ? ssim4 : 0.f;
+#endif
         }
     }
 #undef FB_PLANES
