@@ -1134,6 +1134,7 @@ size_t fb_workspace_bytes(const char *op, int w, int h, int dstW, int dstH, int 
     if (!strcmp(op, "msssim")) return msssim_scratch(w, h, n);
     if (!strcmp(op, "gaussian_blur")) return (size_t)dev_pitch(w) * h * n;
     if (!strcmp(op, "lanczos_resize")) return (size_t)dev_pitch(dstW) * h * n;
+    if (!strcmp(op, "apply_palette")) return palette_scratch_bytes(w, h, n);
     (void)dstH;
     return 0;
 }
@@ -1517,7 +1518,7 @@ int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     const int ipitch = (int)align_up((size_t)w, 16);
-    FB_TRY(reserve(c, 2 * ((size_t)dev_pitch(w) * h + 512) + (size_t)ipitch * h + 4096, 2048));
+    FB_TRY(reserve(c, 2 * ((size_t)dev_pitch(w) * h + 512) + (size_t)ipitch * h + palette_scratch_bytes(w, h, 1) + 4096, 2048));
     uint8_t *d;
     int pitch;
     FB_TRY(upload(c, src, srcStride, w, h, &d, &pitch));
@@ -1525,11 +1526,13 @@ int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint
     uint8_t *ppin = (uint8_t *)c->pin.take(1024);
     uint8_t *didx = indices ? (uint8_t *)c->ws.take((size_t)ipitch * h) : nullptr;
     uint8_t *dout = dst ? (uint8_t *)c->ws.take((size_t)pitch * h + 16) : nullptr;
-    if (!dpal || !ppin || (indices && !didx) || (dst && !dout)) { set_error("internal: workspace under-reserved (palette)"); return FB_E_INVALID; }
+    const size_t cellBytes = palette_scratch_bytes(w, h, 1);
+    void *cells = cellBytes ? c->ws.take(cellBytes - 256) : nullptr;
+    if (!dpal || !ppin || (indices && !didx) || (dst && !dout) || (cellBytes && !cells)) { set_error("internal: workspace under-reserved (palette)"); return FB_E_INVALID; }
     memset(ppin, 0, 1024);
     memcpy(ppin, palette, (size_t)ncolors * 4);
     FB_CUDA(cudaMemcpyAsync(dpal, ppin, 1024, cudaMemcpyHostToDevice, c->stream));
-    FB_TRY(launch_apply_palette(c->stream, d, 0, pitch, w, h, dpal, ncolors, didx, 0, ipitch, dout, 0, pitch, 1));
+    FB_TRY(launch_apply_palette(c->stream, d, 0, pitch, w, h, dpal, ncolors, didx, 0, ipitch, dout, 0, pitch, 1, cells));
     if (indices) FB_CUDA(cudaMemcpy2DAsync(indices, idxStride, didx, ipitch, (size_t)w, h, cudaMemcpyDeviceToHost, c->stream));
     if (dst) FB_TRY(download(c, dout, pitch, dst, dstStride, w, h));
     FB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1546,8 +1549,15 @@ int fb_apply_palette_batch_dev(int device, void *stream, const uint8_t *src, int
     if (n == 0) return FB_OK;
     DevCtx *c;
     FB_TRY(dev_ctx_for("fb_apply_palette_batch_dev", device, &c));
+    const size_t cellBytes = palette_scratch_bytes(w, h, n);
+    void *cells = nullptr;
+    if (cellBytes) {
+        FB_TRY(reserve(c, cellBytes + 1024, 256));
+        cells = c->ws.take(cellBytes - 256);
+        if (!cells) { set_error("internal: workspace under-reserved (palette cells)"); return FB_E_INVALID; }
+    }
     return launch_apply_palette((cudaStream_t)stream, src, imgStride, rowStride, w, h, palettes, ncolors, indices, idxImgStride,
-                                idxRowStride, dst, dstImgStride, dstRowStride, n);
+                                idxRowStride, dst, dstImgStride, dstRowStride, n, cells);
 }
 
 }  // extern "C"

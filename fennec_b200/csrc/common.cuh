@@ -141,7 +141,8 @@ int launch_orient(cudaStream_t s, const uint8_t *src, long long srcImgStride, in
 // palette.cu — SURVEY §8(f3): applyPalette + palettedToNRGBA (targetsize.go:479-545)
 int launch_apply_palette(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int w, int h,
                          const uint8_t *palettes_dev, int ncolors, uint8_t *idx, long long idxImgStride, int idxRowStride,
-                         uint8_t *out, long long outImgStride, int outRowStride, int n);
+                         uint8_t *out, long long outImgStride, int outRowStride, int n, void *scratch);
+size_t palette_scratch_bytes(int w, int h, int n);
 
 // resize.cu
 // When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.

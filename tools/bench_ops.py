@@ -108,9 +108,22 @@ if want("palette"):
     x = noise(4, 3024, 4032, 14)
     pal = torch.randint(0, 256, (4, 256, 4), dtype=torch.uint8, device="cuda")
     pal[..., 3] = 255
-    report("applyPalette 256 colours 4032x3024 (f3; integer-pipe bound, not HBM)", timeit(lambda: batch.apply_palette_batch(x, pal, 256), 5), 4, 12.192768,
+    report("applyPalette 256 colours 4032x3024, noise image + random palette (f3)", timeit(lambda: batch.apply_palette_batch(x, pal, 256), 5), 4, 12.192768,
            4032 * 3024 * 9)
-    del x, pal
+    # photo-like: smooth gradients + noise sigma 6; palette = 256 colours sampled from the image (what median cut yields)
+    yy = torch.arange(3024, device="cuda").view(1, -1, 1, 1) / 3024.0
+    xx = torch.arange(4032, device="cuda").view(1, 1, -1, 1) / 4032.0
+    k = torch.tensor([[1.0, 0.2], [0.3, 0.9], [0.6, 0.6], [0.0, 0.0]], device="cuda")
+    base = 230.0 * (xx * k[:, 0].view(1, 1, 1, 4) + yy * k[:, 1].view(1, 1, 1, 4)) / (k.sum(1).view(1, 1, 1, 4) + 1e-6)
+    g = torch.Generator(device="cuda").manual_seed(15)
+    ph = (base + 6.0 * torch.randn((4, 3024, 4032, 4), device="cuda", generator=g)).clamp(0, 255).to(torch.uint8)
+    ph[..., 3] = 255
+    flat = ph.view(4, -1, 4)
+    pick = torch.randint(0, flat.shape[1], (256,), device="cuda", generator=g)
+    pal2 = flat[:, pick].contiguous()
+    report("applyPalette 256 colours 4032x3024, photo-like image + palette sampled from it (f3)", timeit(lambda: batch.apply_palette_batch(ph, pal2, 256), 5), 4,
+           12.192768, 4032 * 3024 * 9)
+    del x, pal, ph, pal2, flat, base
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
     report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)
