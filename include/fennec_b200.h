@@ -184,7 +184,9 @@ FB_API int fb_apply_orientation_batch_dev(int device, void *stream, const uint8_
  * `dst` the palettedToNRGBA reconstruction; either may be NULL. */
 FB_API int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint8_t *palette, int ncolors,
                      uint8_t *indices, int idxStride, uint8_t *dst, int dstStride);
-/* n device-resident images, one 256-entry palette slot (1024 bytes, device memory) per image. */
+/* n device-resident images, one 256-entry palette slot (1024 bytes, device memory) per image.  Images of 2^17
+ * pixels or more build per-palette cell lists (1 MiB each) in the calling thread's scratch arena —
+ * fb_workspace_bytes("apply_palette", w, h, 0, 0, n); the result is identical either way. */
 FB_API int fb_apply_palette_batch_dev(int device, void *stream, const uint8_t *src, int64_t imgStride, int rowStride,
                                int w, int h, int n, const uint8_t *palettes, int ncolors, uint8_t *indices,
                                int64_t idxImgStride, int idxRowStride, uint8_t *dst, int64_t dstImgStride,
