@@ -263,8 +263,10 @@ int launch_apply_palette(cudaStream_t s, const uint8_t *src, long long srcImgStr
         FB_LAUNCHED(1);
         p.cellList = (const uint4 *)scratch;
         apply_palette_kernel<true, rowsCells><<<gridCells, 256, 0, s>>>(p);
-    } else {
+    } else if (h <= 65535) {
         apply_palette_kernel<false, 1><<<grid, 256, 0, s>>>(p);
+    } else {                                      // gridDim.y limit: a very tall, narrow image
+        apply_palette_kernel<false, rowsCells><<<gridCells, 256, 0, s>>>(p);
     }
     FB_LAUNCHED(1);
     FB_CUDA(cudaGetLastError());

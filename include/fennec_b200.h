@@ -21,6 +21,8 @@
  *    compute entry point returns FB_E_NOGPU.  (The Go shim falls back to the pure-Go body.)
  *  - Thread safety: every entry point may be called concurrently (CompressBatch workers,
  *    batch.go:84-124); each calling thread gets its own stream and workspace per device.
+ *  - Size limits: the entries are written for images up to 65535 pixels per side (JPEG's own limit); some map
+ *    image rows to grid rows and return FB_E_CUDA beyond that instead of computing — never a wrong result.
  *  - Floating point: scores are binary64; SSIM/MS-SSIM agree with the reference to <= 1e-5 absolute
  *    (measured <= 2e-6); every uint8 output is bit-exact with the reference's FP64 arithmetic.
  */
