@@ -63,6 +63,9 @@ PROTOTYPES = {
     "fb_smart_resize_dims": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]),
     "fb_ycbcr_to_nrgba": (C.c_int, [u8p, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]),
     "fb_gray_to_nrgba": (C.c_int, [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]),
+    "fb_convert_to_nrgba": (C.c_int, [C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, u8p, C.c_int]),
+    "fb_convert_to_nrgba_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     "fb_ssim_ref_create": (C.c_int, _IMG + [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fb_ssim_ref_score_ycbcr": (C.c_int, [C.c_void_p, u8p, C.c_int, u8p, u8p, C.c_int, C.c_int, dp]),
     "fb_ssim_ref_score_nrgba": (C.c_int, [C.c_void_p] + _IMG + [dp]),

@@ -254,6 +254,37 @@ def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
     return dst
 
 
+FMT_RGBA, FMT_RGBA64, FMT_NRGBA64, FMT_GRAY16, FMT_CMYK, FMT_PALETTED = 1, 2, 3, 4, 5, 6
+_FMT_BPP = {FMT_RGBA: 4, FMT_RGBA64: 8, FMT_NRGBA64: 8, FMT_GRAY16: 2, FMT_CMYK: 4, FMT_PALETTED: 1}
+
+
+def convert_to_nrgba(fmt: int, pix: np.ndarray, palette16: Optional[np.ndarray] = None) -> np.ndarray:
+    """convertToNRGBA (convert.go:34-64) of a decoded *image.RGBA / RGBA64 / NRGBA64 / Gray16 / CMYK / Paletted:
+    `pix` is the Go image's Pix as (h, w, bytes-per-pixel) uint8 — (h, w) for Paletted, whose `palette16` holds
+    Palette[i].RGBA() as (n, 4) uint16.  Rows may be strided; pixels are packed within a row."""
+    if fmt not in _FMT_BPP:
+        raise ValueError(f"unknown pixel format {fmt}")
+    bpp = _FMT_BPP[fmt]
+    if pix.ndim == 2:
+        pix = pix[..., None]
+    if pix.dtype != np.uint8 or pix.ndim != 3 or pix.shape[2] != bpp:
+        raise TypeError(f"expected uint8 pixels of shape (h, w, {bpp})")
+    h, w = pix.shape[:2]
+    if (bpp > 1 and pix.strides[2] != 1) or (w > 1 and pix.strides[1] != bpp):
+        raise ValueError("pixels must be packed within a row")
+    dst = _new(h, w)
+    pd, sd, _, _ = _img(dst)
+    pp, n = None, 0
+    if palette16 is not None:
+        palette16 = np.ascontiguousarray(palette16, dtype=np.uint16)
+        if palette16.ndim != 2 or palette16.shape[1] != 4:
+            raise TypeError("palette16 must have shape (n, 4)")
+        pp, n = palette16.ctypes.data_as(C.POINTER(C.c_uint16)), len(palette16)
+    stride = int(pix.strides[0]) if h > 1 else w * bpp
+    check(_lib.load().fb_convert_to_nrgba(fmt, pix.ctypes.data_as(_lib.u8p), stride, w, h, pp, n, pd, sd))
+    return dst
+
+
 class SSIMReference:
     """The `src` side of compress.go:45-74's search, kept on the device: SSIMFast(src, candidate) per iteration
     with only the candidate crossing PCIe (as YCbCr planes or NRGBA)."""

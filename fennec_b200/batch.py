@@ -101,6 +101,31 @@ def ycbcr_to_nrgba_batch(y: torch.Tensor, cb: torch.Tensor, cr: torch.Tensor, ra
     return out
 
 
+def convert_to_nrgba_batch(fmt: int, pix: torch.Tensor, palettes16: Optional[torch.Tensor] = None, ncolors: int = 0,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """convertToNRGBA (convert.go:34-64) for n device-resident decoded images of one type (api.FMT_*): pix is
+    (n, h, w, bytes-per-pixel) uint8 — (n, h, w) for Paletted, with palettes16 (n, 256, 4) int16/uint16 bit patterns."""
+    if pix.dim() == 3:
+        pix = pix.unsqueeze(-1)
+    if not (pix.is_cuda and pix.dtype == torch.uint8 and pix.dim() == 4):
+        raise TypeError("expected a CUDA uint8 tensor of shape (n, h, w, bytes-per-pixel)")
+    n, h, w, bpp = pix.shape
+    if (bpp > 1 and pix.stride(3) != 1) or (w > 1 and pix.stride(2) != bpp):
+        raise ValueError("pixels must be packed within a row")
+    pal_ptr = 0
+    if palettes16 is not None:
+        if not (palettes16.is_cuda and palettes16.is_contiguous() and palettes16.element_size() == 2
+                and tuple(palettes16.shape) == (n, 256, 4)):
+            raise TypeError("palettes16 must be a contiguous CUDA 16-bit tensor of shape (n, 256, 4)")
+        pal_ptr = palettes16.data_ptr()
+    if out is None:
+        out = torch.empty((n, h, w, 4), dtype=torch.uint8, device=pix.device)
+    pd, i_d, rd, _, _, _ = _batch(out)
+    check(_lib.load().fb_convert_to_nrgba_batch_dev(_dev(pix), _stream(pix), fmt, pix.data_ptr(), int(pix.stride(0)),
+                                                    int(pix.stride(1)), w, h, n, pal_ptr, ncolors, pd, i_d, rd))
+    return out
+
+
 def analyze_batch(imgs: torch.Tensor) -> List[dict]:
     """fennec.Analyze (analyze.go:26-176) for n device-resident images: the scans run on the device, the raw records
     (histogram, integer sums, counts) come back in one copy and are finished with host arithmetic."""

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libfennec_b200.so")
-SOURCES = ["api.cu", "ssim.cu", "box.cu", "effects.cu", "resize.cu", "ycbcr.cu", "analyze.cu", "orient.cu", "palette.cu"]
+SOURCES = ["api.cu", "ssim.cu", "box.cu", "effects.cu", "resize.cu", "ycbcr.cu", "analyze.cu", "orient.cu", "palette.cu", "pixfmt.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("FB_EXTRA_NVCC", "").split()
 FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

@@ -1263,6 +1263,72 @@ int fb_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, 
     return FB_OK;
 }
 
+// convertToNRGBA (convert.go:34-64) for *image.RGBA / RGBA64 / NRGBA64 / Gray16 / CMYK / Paletted — pixfmt.cu
+static int check_pixfmt(const char *fn, int format, const void *pix, int stride, int w, int h, const void *palette16, int ncolors) {
+    const int bpp = pixfmt_bytes_per_pixel(format);
+    if (!bpp) { set_error("%s: unknown format %d (1 RGBA, 2 RGBA64, 3 NRGBA64, 4 Gray16, 5 CMYK, 6 Paletted)", fn, format); return FB_E_INVALID; }
+    if (w < 0 || h < 0) { set_error("%s: negative dimensions %dx%d", fn, w, h); return FB_E_INVALID; }
+    if (w > 0 && h > 0) {
+        if (!pix) { set_error("%s: null pixel pointer", fn); return FB_E_INVALID; }
+        if ((long long)stride < (long long)w * bpp) { set_error("%s: stride %d < %d bytes per row", fn, stride, w * bpp); return FB_E_INVALID; }
+    }
+    if (format == FB_FMT_PALETTED && (!palette16 || ncolors < 1 || ncolors > 256)) {
+        set_error("%s: a Paletted image needs 1..256 palette entries", fn);
+        return FB_E_INVALID;
+    }
+    return FB_OK;
+}
+
+int fb_convert_to_nrgba(int format, const uint8_t *pix, int stride, int w, int h, const uint16_t *palette16, int ncolors,
+                        uint8_t *dst, int dstStride) {
+    FB_TRY(check_pixfmt("fb_convert_to_nrgba", format, pix, stride, w, h, palette16, ncolors));
+    FB_TRY(check_img("fb_convert_to_nrgba", dst, dstStride, w, h));
+    if (w == 0 || h == 0) return FB_OK;
+    DevCtx *c = ctx(current_device());
+    if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
+    const int bpp = pixfmt_bytes_per_pixel(format);
+    const size_t sp = align_up((size_t)w * bpp, 256);
+    const int pitch = dev_pitch(w);
+    FB_TRY(reserve(c, sp * h + (size_t)pitch * h + 2048 + 256 + 4096, 2048 + 256));
+    uint8_t *ds = (uint8_t *)c->ws.take(sp * h);
+    uint8_t *d = (uint8_t *)c->ws.take((size_t)pitch * h + 16);
+    uint16_t *dpal = (uint16_t *)c->ws.take(2048);
+    unsigned int *dbad = (unsigned int *)c->ws.take(16);
+    uint16_t *ppal = (uint16_t *)c->pin.take(2048);
+    unsigned int *pbad = (unsigned int *)c->pin.take(16);
+    if (!ds || !d || !dpal || !dbad || !ppal || !pbad) { set_error("internal: workspace under-reserved (convert)"); return FB_E_INVALID; }
+    FB_CUDA(cudaMemcpy2DAsync(ds, sp, pix, stride, (size_t)w * bpp, h, cudaMemcpyHostToDevice, c->stream));
+    if (format == FB_FMT_PALETTED) {
+        memset(ppal, 0, 2048);
+        memcpy(ppal, palette16, (size_t)ncolors * 8);
+        FB_CUDA(cudaMemcpyAsync(dpal, ppal, 2048, cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(cudaMemsetAsync(dbad, 0, 4, c->stream));
+    }
+    FB_TRY(launch_pixfmt_to_nrgba(c->stream, format, ds, 0, (int)sp, w, h, dpal, ncolors, d, 0, pitch, 1, dbad));
+    FB_TRY(download(c, d, pitch, dst, dstStride, w, h));
+    if (format == FB_FMT_PALETTED) FB_CUDA(cudaMemcpyAsync(pbad, dbad, 4, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    if (format == FB_FMT_PALETTED && *pbad) {
+        set_error("fb_convert_to_nrgba: a pixel index is >= the palette length %d (Go panics here); those pixels were written as 0", ncolors);
+        return FB_E_INVALID;
+    }
+    return FB_OK;
+}
+
+int fb_convert_to_nrgba_batch_dev(int device, void *stream, int format, const uint8_t *pix, int64_t imgStride, int rowStride,
+                                  int w, int h, int n, const uint16_t *palettes16, int ncolors, uint8_t *dst,
+                                  int64_t dstImgStride, int dstRowStride) {
+    FB_TRY(check_pixfmt("fb_convert_to_nrgba_batch_dev", format, pix, rowStride, w, h, palettes16, ncolors));
+    if (n < 0) { set_error("fb_convert_to_nrgba_batch_dev: negative batch size"); return FB_E_INVALID; }
+    if (n > 1 && imgStride < (int64_t)rowStride * h) { set_error("fb_convert_to_nrgba_batch_dev: image stride smaller than an image"); return FB_E_INVALID; }
+    FB_TRY(check_batch("fb_convert_to_nrgba_batch_dev", dst, dstImgStride, dstRowStride, w, h, n));
+    if (n == 0 || w == 0 || h == 0) return FB_OK;
+    DevCtx *c;
+    FB_TRY(dev_ctx_for("fb_convert_to_nrgba_batch_dev", device, &c));
+    return launch_pixfmt_to_nrgba((cudaStream_t)stream, format, pix, imgStride, rowStride, w, h, palettes16, ncolors, dst,
+                                  dstImgStride, dstRowStride, n, nullptr);
+}
+
 int fb_ycbcr_to_nrgba_batch_dev(int device, void *stream, const uint8_t *y, int64_t yImgStride, int yStride,
                                 const uint8_t *cb, const uint8_t *cr, int64_t cImgStride, int cStride, int w, int h,
                                 int ratio, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int n) {

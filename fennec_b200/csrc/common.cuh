@@ -143,6 +143,10 @@ int launch_apply_palette(cudaStream_t s, const uint8_t *src, long long srcImgStr
                          const uint8_t *palettes_dev, int ncolors, uint8_t *idx, long long idxImgStride, int idxRowStride,
                          uint8_t *out, long long outImgStride, int outRowStride, int n, void *scratch);
 size_t palette_scratch_bytes(int w, int h, int n);
+int pixfmt_bytes_per_pixel(int fmt);
+int launch_pixfmt_to_nrgba(cudaStream_t s, int fmt, const uint8_t *src, long long srcImgStride, int srcRowStride, int w, int h,
+                           const uint16_t *pal16_dev, int ncolors, uint8_t *dst, long long dstImgStride, int dstRowStride, int n,
+                           unsigned int *badIndex_dev);
 
 // resize.cu
 // When srcSize == ratio * dstSize every interior destination shares one weight vector: see resize.cu.

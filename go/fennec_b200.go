@@ -119,8 +119,8 @@ func gpuShard(nItems, nShards, shard int) (begin, end int, ok bool) {
 
 // ---- SURVEY §8(f1): the step before SSIMFast in the quality search (compress.go:53-62) ----------------
 
-// gpuConvertToNRGBA replaces convertToNRGBA's pixel loop (convert.go:38-63) for the two concrete types
-// jpeg.Decode returns with Rect.Min == (0,0); anything else keeps the pure-Go loop.
+// gpuConvertToNRGBA replaces convertToNRGBA's pixel loop (convert.go:38-63) for the concrete types jpeg.Decode and
+// png.Decode return, with Rect.Min == (0,0); anything else keeps the pure-Go loop.
 func gpuConvertToNRGBA(img image.Image, dst *image.NRGBA) bool {
 	switch s := img.(type) {
 	case *image.YCbCr:
@@ -138,8 +138,43 @@ func gpuConvertToNRGBA(img image.Image, dst *image.NRGBA) bool {
 		st := C.fb_gray_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Pix[0])), C.int(s.Stride),
 			C.int(s.Rect.Dx()), C.int(s.Rect.Dy()), pix(dst), C.int(dst.Stride))
 		return st == C.FB_OK
+	case *image.RGBA: // png.Decode of truecolour without alpha, draw targets
+		return gpuConvertPix(C.FB_FMT_RGBA, s.Pix, s.Stride, s.Rect, nil, dst)
+	case *image.RGBA64:
+		return gpuConvertPix(C.FB_FMT_RGBA64, s.Pix, s.Stride, s.Rect, nil, dst)
+	case *image.NRGBA64:
+		return gpuConvertPix(C.FB_FMT_NRGBA64, s.Pix, s.Stride, s.Rect, nil, dst)
+	case *image.Gray16:
+		return gpuConvertPix(C.FB_FMT_GRAY16, s.Pix, s.Stride, s.Rect, nil, dst)
+	case *image.CMYK: // 4-component JPEGs
+		return gpuConvertPix(C.FB_FMT_CMYK, s.Pix, s.Stride, s.Rect, nil, dst)
+	case *image.Paletted:
+		if len(s.Palette) == 0 || len(s.Palette) > 256 {
+			return false
+		}
+		pal := make([]uint16, 4*len(s.Palette)) // the color.Color interface is evaluated here, once per entry
+		for i, c := range s.Palette {
+			r, g, b, a := c.RGBA()
+			pal[4*i], pal[4*i+1], pal[4*i+2], pal[4*i+3] = uint16(r), uint16(g), uint16(b), uint16(a)
+		}
+		return gpuConvertPix(C.FB_FMT_PALETTED, s.Pix, s.Stride, s.Rect, pal, dst)
 	}
 	return false
+}
+
+// gpuConvertPix hands a decoded image's Pix buffer to fb_convert_to_nrgba.  A palette index past the palette makes
+// the call fail (FB_E_INVALID); the caller then runs the pure-Go loop, which panics exactly as before.
+func gpuConvertPix(format C.int, p []uint8, stride int, r image.Rectangle, pal []uint16, dst *image.NRGBA) bool {
+	if r.Min != (image.Point{}) || len(p) == 0 {
+		return false
+	}
+	var pp *C.uint16_t
+	if len(pal) > 0 {
+		pp = (*C.uint16_t)(unsafe.Pointer(&pal[0]))
+	}
+	st := C.fb_convert_to_nrgba(format, (*C.uint8_t)(unsafe.Pointer(&p[0])), C.int(stride), C.int(r.Dx()), C.int(r.Dy()),
+		pp, C.int(len(pal)/4), pix(dst), C.int(dst.Stride))
+	return st == C.FB_OK
 }
 
 // ssimSession keeps `src` (its SSIMFast thumbnail) on the device for the whole binary search of

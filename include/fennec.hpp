@@ -118,6 +118,24 @@ inline Image convertToNRGBA(const YCbCr &img) {
     return dst;
 }
 
+// convertToNRGBA — convert.go:34-64 — for the other decoder outputs: *image.RGBA / RGBA64 / NRGBA64 / Gray16 / CMYK /
+// Paletted, handed over as the Go image's Pix + Stride (Rect.Min == (0,0)).  Format = FB_FMT_*; Palette16 holds
+// Palette[i].RGBA() (4 x uint16 per entry) for FB_FMT_PALETTED.
+struct PixImage {
+    int Format = FB_FMT_RGBA;
+    std::vector<uint8_t> Pix;
+    int Stride = 0, W = 0, H = 0;
+    std::vector<uint16_t> Palette16;
+};
+inline Image convertToNRGBA(const PixImage &img) {
+    Image dst = NewNRGBA(img.W, img.H);
+    if (img.W <= 0 || img.H <= 0) return dst;
+    check(fb_convert_to_nrgba(img.Format, img.Pix.data(), img.Stride, img.W, img.H,
+                              img.Palette16.empty() ? nullptr : img.Palette16.data(), (int)(img.Palette16.size() / 4),
+                              dst->data(), dst->Stride));
+    return dst;
+}
+
 // The `src` side of compress.go:45-74's binary search kept on the device: SSIMFast(src, candidate) per iteration.
 class SSIMSession {
     fb_ssim_ref *h_ = nullptr;

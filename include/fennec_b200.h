@@ -133,6 +133,25 @@ FB_API int fb_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, c
 /* The same for *image.Gray (grayscale JPEGs). */
 FB_API int fb_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride);
 
+/* convertToNRGBA — convert.go:34-64 — for the other concrete types image/png and image/jpeg decode into.  `pix` /
+ * `stride` are the Go image's Pix / Stride (Rect.Min == (0,0)); the result is byte-for-byte what the reference's
+ * img.At(x,y).RGBA() loop writes, including the un-premultiply of translucent pixels (convert.go:54-59) and Go's
+ * truncating uint8() for colours above their alpha.
+ *   FB_FMT_RGBA     *image.RGBA     4 B/px R,G,B,A premultiplied      FB_FMT_RGBA64   *image.RGBA64   8 B/px big-endian
+ *   FB_FMT_NRGBA64  *image.NRGBA64  8 B/px big-endian, straight alpha FB_FMT_GRAY16   *image.Gray16   2 B/px big-endian
+ *   FB_FMT_CMYK     *image.CMYK     4 B/px C,M,Y,K                    FB_FMT_PALETTED *image.Paletted 1 B/px index
+ * For FB_FMT_PALETTED `palette16` holds ncolors (1..256) entries of 4 uint16 — Palette[i].RGBA() as Go returns it
+ * (the Go shim evaluates the color.Color interface once per entry); other formats ignore it (NULL).  Go panics on
+ * an index >= len(Palette): the host entry writes such pixels as 0 and returns FB_E_INVALID. */
+#define FB_FMT_RGBA 1
+#define FB_FMT_RGBA64 2
+#define FB_FMT_NRGBA64 3
+#define FB_FMT_GRAY16 4
+#define FB_FMT_CMYK 5
+#define FB_FMT_PALETTED 6
+FB_API int fb_convert_to_nrgba(int format, const uint8_t *pix, int stride, int w, int h, const uint16_t *palette16,
+                        int ncolors, uint8_t *dst, int dstStride);
+
 /* Reference-image session for the binary search of compress.go:45-74: `src` is uploaded and box-
  * downsampled ONCE (ssim.go:57 recomputes it every iteration); each iteration then sends only the
  * decoded candidate — as YCbCr planes (1.5 B/px at 4:2:0) or NRGBA — and gets SSIMFast(src, candidate)
@@ -218,6 +237,10 @@ FB_API int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a,
 FB_API int fb_ycbcr_to_nrgba_batch_dev(int device, void *stream, const uint8_t *y, int64_t yImgStride, int yStride,
                                 const uint8_t *cb, const uint8_t *cr, int64_t cImgStride, int cStride, int w,
                                 int h, int ratio, uint8_t *dst, int64_t dstImgStride, int dstRowStride, int n);
+/* n device-resident images of one format; Paletted: one 256-entry slot (2048 bytes, device memory) per image. */
+FB_API int fb_convert_to_nrgba_batch_dev(int device, void *stream, int format, const uint8_t *pix, int64_t imgStride,
+                                  int rowStride, int w, int h, int n, const uint16_t *palettes16, int ncolors,
+                                  uint8_t *dst, int64_t dstImgStride, int dstRowStride);
 FB_API int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst,
                                int64_t imgStride, int rowStride, int w, int h, int n,
                                const double *kernel_host, int radius);

@@ -872,6 +872,81 @@ void fo_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst,
         }
 }
 
+/* ---- convertToNRGBA (convert.go:34-64) for the other concrete types image/png and image/jpeg decode into -----
+ * Step 1 is Go's At(x, y).RGBA() of each type (image/image.go, image/color/color.go, image/color/ycbcr.go — Go
+ * 1.25.5 standard library, not vendored; restated from the published source), step 2 is convert.go:42-60 verbatim:
+ * a == 0 -> zeros; a == 0xffff -> channel >> 8; else uint8(((c * 0xffff) / a) >> 8), alpha a >> 8, in uint32
+ * arithmetic with Go's truncating uint8() conversion.  Rect.Min == (0, 0) as every decoder returns.
+ *   1 *image.RGBA     Pix R,G,B,A 8-bit premultiplied: color.RGBA.RGBA() = v | v<<8 per field
+ *   2 *image.RGBA64   Pix big-endian 16-bit R,G,B,A premultiplied: the fields themselves
+ *   3 *image.NRGBA64  big-endian 16-bit, straight alpha: c * a / 0xffff per colour field, a
+ *   4 *image.Gray16   big-endian 16-bit Y: (y, y, y, 0xffff)
+ *   5 *image.CMYK     Pix C,M,Y,K: w = 0xffff - k*0x101; (0xffff - c*0x101) * w / 0xffff; alpha 0xffff
+ *   6 *image.Paletted Pix = index; pal16 holds Palette[i].RGBA() as 4 x uint16 per entry (the caller evaluates the
+ *                     color.Color interface; values are <= 0xffff by contract).  Go panics on an index >= len(Palette):
+ *                     the restatement returns -2 instead. */
+static void fo_convert_px(uint32_t r, uint32_t g, uint32_t b, uint32_t a, uint8_t *o) {
+    if (a == 0) {
+        o[0] = o[1] = o[2] = o[3] = 0;
+    } else if (a == 0xffff) {
+        o[0] = (uint8_t)(r >> 8); o[1] = (uint8_t)(g >> 8); o[2] = (uint8_t)(b >> 8); o[3] = 0xff;
+    } else {
+        o[0] = (uint8_t)(((r * 0xffffu) / a) >> 8);
+        o[1] = (uint8_t)(((g * 0xffffu) / a) >> 8);
+        o[2] = (uint8_t)(((b * 0xffffu) / a) >> 8);
+        o[3] = (uint8_t)(a >> 8);
+    }
+}
+
+static uint32_t fo_be16(const uint8_t *p) { return ((uint32_t)p[0] << 8) | p[1]; }
+
+int fo_convert_to_nrgba(int fmt, const uint8_t *pix, int stride, int w, int h, const uint16_t *pal16, int ncolors,
+                        uint8_t *dst, int dstStride) {
+    if (fmt < 1 || fmt > 6) return -1;
+    if (fmt == 6 && (!pal16 || ncolors < 1 || ncolors > 256)) return -1;
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            uint32_t r, g, b, a;
+            const uint8_t *row = pix + (size_t)y * stride;
+            switch (fmt) {
+                case 1: {
+                    const uint8_t *p = row + (size_t)x * 4;
+                    r = p[0] | ((uint32_t)p[0] << 8); g = p[1] | ((uint32_t)p[1] << 8);
+                    b = p[2] | ((uint32_t)p[2] << 8); a = p[3] | ((uint32_t)p[3] << 8);
+                } break;
+                case 2: {
+                    const uint8_t *p = row + (size_t)x * 8;
+                    r = fo_be16(p); g = fo_be16(p + 2); b = fo_be16(p + 4); a = fo_be16(p + 6);
+                } break;
+                case 3: {
+                    const uint8_t *p = row + (size_t)x * 8;
+                    a = fo_be16(p + 6);
+                    r = fo_be16(p) * a / 0xffffu; g = fo_be16(p + 2) * a / 0xffffu; b = fo_be16(p + 4) * a / 0xffffu;
+                } break;
+                case 4: {
+                    r = g = b = fo_be16(row + (size_t)x * 2);
+                    a = 0xffff;
+                } break;
+                case 5: {
+                    const uint8_t *p = row + (size_t)x * 4;
+                    uint32_t wk = 0xffffu - (uint32_t)p[3] * 0x101u;
+                    r = (0xffffu - (uint32_t)p[0] * 0x101u) * wk / 0xffffu;
+                    g = (0xffffu - (uint32_t)p[1] * 0x101u) * wk / 0xffffu;
+                    b = (0xffffu - (uint32_t)p[2] * 0x101u) * wk / 0xffffu;
+                    a = 0xffff;
+                } break;
+                default: {
+                    int i = row[x];
+                    if (i >= ncolors) return -2;
+                    r = pal16[4 * i]; g = pal16[4 * i + 1]; b = pal16[4 * i + 2]; a = pal16[4 * i + 3];
+                } break;
+            }
+            fo_convert_px(r, g, b, a, dst + (size_t)y * dstStride + (size_t)x * 4);
+        }
+    }
+    return 0;
+}
+
 /* ---- §8(f2): Analyze (analyze.go:26-176) — the measured part: one full scan + two sampled scans ------------
  * Sequential, source order, binary64 unfused — exactly as the Go loops.  math.Log2 is Go's own
  * (Frexp; frac == 0.5 -> exp-1; else Log(frac)*(1/Ln2) + exp), restated with libm's log: entropy may differ from Go

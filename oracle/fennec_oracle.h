@@ -108,6 +108,10 @@ int fo_smart_resize_dims(int srcW, int srcH, int maxW, int maxH, int *dstW, int 
 int fo_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const uint8_t *cr, int cStride,
                       int w, int h, int ratio, uint8_t *dst, int dstStride);
 void fo_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride);
+/* convertToNRGBA for *image.RGBA (1), RGBA64 (2), NRGBA64 (3), Gray16 (4), CMYK (5), Paletted (6; pal16 = ncolors x
+ * 4 uint16 = Palette[i].RGBA()).  0, -1 bad arguments, -2 palette index out of range (Go panics). */
+int fo_convert_to_nrgba(int fmt, const uint8_t *pix, int stride, int w, int h, const uint16_t *pal16, int ncolors,
+                        uint8_t *dst, int dstStride);
 
 /* Analyze (analyze.go:26-176) and the recommendation rules (analyze.go:183-232). */
 typedef struct {

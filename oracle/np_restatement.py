@@ -433,6 +433,52 @@ def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
     return out
 
 
+# ---- convertToNRGBA (convert.go:34-64) for the other decoder outputs ------------------------------------------
+# Vectorised, independent of the C oracle: At().RGBA() per concrete type (image/color), then convert.go:42-60.
+FMT_RGBA, FMT_RGBA64, FMT_NRGBA64, FMT_GRAY16, FMT_CMYK, FMT_PALETTED = 1, 2, 3, 4, 5, 6
+
+
+def _be16(a: np.ndarray) -> np.ndarray:
+    """(..., 2k) big-endian bytes -> (..., k) uint64 values."""
+    a = a.astype(np.uint64)
+    return (a[..., 0::2] << np.uint64(8)) | a[..., 1::2]
+
+
+def convert_to_nrgba(fmt: int, pix: np.ndarray, pal16: np.ndarray = None) -> np.ndarray:
+    """pix: (h, w, 4) uint8 for RGBA / CMYK, (h, w, 8) for the 64-bit types, (h, w, 2) for Gray16, (h, w) indices
+    for Paletted (pal16: (n, 4) uint16 = Palette[i].RGBA())."""
+    u = np.uint64
+    if fmt == FMT_RGBA:
+        v = pix.astype(u)
+        rgba = v | (v << u(8))
+    elif fmt == FMT_RGBA64:
+        rgba = _be16(pix)
+    elif fmt == FMT_NRGBA64:
+        v = _be16(pix)
+        a = v[..., 3:4]
+        rgba = np.concatenate([v[..., :3] * a // u(0xFFFF), a], -1)
+    elif fmt == FMT_GRAY16:
+        y = _be16(pix)
+        rgba = np.concatenate([y, y, y, np.full_like(y, 0xFFFF)], -1)
+    elif fmt == FMT_CMYK:
+        v = pix.astype(u)
+        wk = u(0xFFFF) - v[..., 3:4] * u(0x101)
+        rgb = (u(0xFFFF) - v[..., :3] * u(0x101)) * wk // u(0xFFFF)
+        rgba = np.concatenate([rgb, np.full_like(wk, 0xFFFF)], -1)
+    elif fmt == FMT_PALETTED:
+        assert pix.max(initial=0) < len(pal16), "Go panics: index out of range"
+        rgba = pal16.astype(u)[pix]
+    else:
+        raise ValueError(fmt)
+    a = rgba[..., 3:4]
+    safe = np.where(a == 0, u(1), a)
+    mid = (((rgba[..., :3] * u(0xFFFF)) // safe) >> u(8)) & u(0xFF)         # uint8() keeps the low byte
+    rgb = np.where(a == 0xFFFF, rgba[..., :3] >> u(8), mid)
+    out = np.concatenate([rgb, a >> u(8)], -1)
+    out = np.where(a == 0, u(0), out)
+    return out.astype(np.uint8)
+
+
 # ---- §8(f2): Analyze (analyze.go:26-176) --------------------------------------------------------------------
 # Independent restatement: vectorised per-pixel float64 luminance, np.cumsum for the SEQUENTIAL sums (cumsum adds in
 # order, unlike np.sum's pairwise reduction), a dict-free distinct count for the capped colour set.

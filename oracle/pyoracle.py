@@ -81,6 +81,8 @@ def lib():
         L.fo_apply_palette.restype = None
         L.fo_ycbcr_to_nrgba.argtypes = [_u8p, C.c_int, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.fo_gray_to_nrgba.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
+        L.fo_convert_to_nrgba.argtypes = [C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_int, _u8p, C.c_int]
+        L.fo_convert_to_nrgba.restype = C.c_int
         _lib = L
     return _lib
 
@@ -284,6 +286,33 @@ def gray_to_nrgba(g: np.ndarray) -> np.ndarray:
     pg, sg = _plane(g)
     pd, sd = _img(dst)
     lib().fo_gray_to_nrgba(pg, sg, w, h, pd, sd)
+    return dst
+
+
+_FMT_BPP = {1: 4, 2: 8, 3: 8, 4: 2, 5: 4, 6: 1}
+
+
+def convert_to_nrgba(fmt: int, pix: np.ndarray, pal16: np.ndarray = None) -> np.ndarray:
+    """convertToNRGBA (convert.go:34-64) of *image.RGBA (1), RGBA64 (2), NRGBA64 (3), Gray16 (4), CMYK (5), Paletted (6).
+    pix: (h, w, bytes-per-pixel) uint8 — (h, w) for Paletted; rows may be strided."""
+    bpp = _FMT_BPP[fmt]
+    if pix.ndim == 2:
+        pix = pix[..., None]
+    h, w = pix.shape[:2]
+    assert pix.dtype == np.uint8 and pix.shape[2] == bpp
+    assert (bpp == 1 or pix.strides[2] == 1) and (w <= 1 or pix.strides[1] == bpp), "pixels must be packed within a row"
+    dst = _new(h, w)
+    pd, sd = _img(dst)
+    pp = None
+    n = 0
+    if pal16 is not None:
+        pal16 = np.ascontiguousarray(pal16, dtype=np.uint16)
+        pp, n = pal16.ctypes.data_as(C.POINTER(C.c_uint16)), len(pal16)
+    stride = int(pix.strides[0]) if h > 1 else w * bpp
+    rc = lib().fo_convert_to_nrgba(fmt, pix.ctypes.data_as(_u8p), stride, w, h, pp, n, pd, sd)
+    if rc == -2:
+        raise IndexError("palette index out of range (Go panics)")
+    assert rc == 0
     return dst
 
 

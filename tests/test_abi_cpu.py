@@ -139,6 +139,14 @@ def test_new_entry_points_validate_before_touching_the_gpu(lib):
     pal[2, 3] = 254
     assert lib.fb_apply_palette(p(dst), 32, 8, 4, p(pal), 4, p(idx), 8, None, 0) == _lib.FB_E_INVALID
     assert b"alpha" in lib.fb_last_error()
+    # convertToNRGBA formats: unknown format, short stride, missing / oversized palette, empty image
+    pal16 = np.zeros((4, 4), np.uint16).ctypes.data_as(C.POINTER(C.c_uint16))
+    assert lib.fb_convert_to_nrgba(0, p(dst), 32, 8, 4, None, 0, p(dst), 32) == _lib.FB_E_INVALID
+    assert b"format" in lib.fb_last_error()
+    assert lib.fb_convert_to_nrgba(2, p(dst), 32, 8, 4, None, 0, p(dst), 32) == _lib.FB_E_INVALID      # RGBA64 needs 64 B/row
+    assert lib.fb_convert_to_nrgba(6, p(idx), 8, 8, 4, None, 0, p(dst), 32) == _lib.FB_E_INVALID
+    assert lib.fb_convert_to_nrgba(6, p(idx), 8, 8, 4, pal16, 257, p(dst), 32) == _lib.FB_E_INVALID
+    assert lib.fb_convert_to_nrgba(1, None, 0, 0, 0, None, 0, None, 0) == _lib.FB_OK                   # nothing to do
     # session: null outputs
     assert lib.fb_ssim_ref_create(p(dst), 32, 8, 4, None) == _lib.FB_E_INVALID
     assert lib.fb_ssim_ref_score_nrgba(None, p(dst), 32, None) == _lib.FB_E_INVALID

@@ -124,6 +124,18 @@ if want("palette"):
     report("applyPalette 256 colours 4032x3024, photo-like image + palette sampled from it (f3)", timeit(lambda: batch.apply_palette_batch(ph, pal2, 256), 5), 4,
            12.192768, 4032 * 3024 * 9)
     del x, pal, ph, pal2, flat, base
+if want("pixfmt"):
+    x = noise(16, 3024, 4032, 21)
+    y = torch.empty_like(x)
+    x[..., 3] = 255
+    report("convertToNRGBA *image.RGBA opaque 4032x3024", timeit(lambda: batch.convert_to_nrgba_batch(1, x, out=y), 10), 16, 12.192768, 4032 * 3024 * 8)
+    x = noise(16, 3024, 4032, 22)
+    x[..., :3] = (x[..., :3].to(torch.int32) * x[..., 3:4].to(torch.int32) // 255).to(torch.uint8)
+    report("convertToNRGBA *image.RGBA translucent (3 divisions per pixel) 4032x3024", timeit(lambda: batch.convert_to_nrgba_batch(1, x, out=y), 10), 16, 12.192768, 4032 * 3024 * 8)
+    x64 = torch.randint(0, 256, (8, 3024, 4032, 8), dtype=torch.uint8, device="cuda")
+    y8 = torch.empty((8, 3024, 4032, 4), dtype=torch.uint8, device="cuda")
+    report("convertToNRGBA *image.NRGBA64 random alpha 4032x3024", timeit(lambda: batch.convert_to_nrgba_batch(3, x64, out=y8), 10), 8, 12.192768, 4032 * 3024 * 12)
+    del x, y, x64, y8
 if want("msssim"):
     a, b = noise(16, 4320, 7680, 7), noise(16, 4320, 7680, 8)
     report("MSSSIM 7680x4320 (config 5)", timeit(lambda: batch.msssim_batch(a, b), 5), 16, 33.1776, 2 * 7680 * 4320 * 4)
