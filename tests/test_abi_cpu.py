@@ -189,3 +189,13 @@ def test_analyze_finish_is_host_arithmetic(lib, oracle):
     assert abs(st.contrast - want["contrast"]) <= 1e-9 and abs(st.edge_density - want["edge_density"]) <= 1e-12
     assert (st.recommended_format, st.recommended_quality) == (want["recommended_format"], want["recommended_quality"])
     assert abs(st.estimated_compression - want["estimated_compression"]) <= 1e-12
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/fennec_b200.h must compile as C99 (cgo compiles it as C), not only as C++."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "fennec_b200.h"\nint main(void) { fb_image_stats s; (void)s; return FB_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-c", str(src), "-o", str(tmp_path / "t.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
