@@ -109,14 +109,6 @@ __device__ __forceinline__ float byte_to_float(uint32_t px, int k) {
     return __uint_as_float(m) - 8388608.0f;
 }
 
-// Round v (known to be within [-0.25, 255.25]) to nearest; flag when within eps of a tie.
-__device__ __forceinline__ uint32_t round_flag(float v, float lim, bool &amb) {
-    float t = v + 12582912.0f;             // 1.5 * 2^23: the integer lands in the low mantissa bits
-    float rounded = t - 12582912.0f;
-    amb = fabsf(v - rounded) >= lim;       // lim = 0.5 - eps
-    return __float_as_uint(t) & 0x1FFu;
-}
-
 // Round + pack the kTile outputs of a thread.  The accumulators are (even output, odd output) pairs per channel, so
 // the magic-number rounding runs as packed FADD2/FFMA2 (t = v + 1.5*2^23, r = t - 1.5*2^23, d = v - r); the low byte of
 // t's bit pattern IS the rounded value (v is within [-0.25, 255.25]), so three PRMTs assemble R|G|B|alpha without
@@ -216,21 +208,6 @@ __device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *
     __syncwarp();
     if (lane == 0) *cnt = n;
     __syncwarp();
-}
-
-// Exact FP64 tap sum of one output (the reference's sequence, effects.go:172-188) over taps that were
-// staged as packed pixels at `px[k * strideWords]`, k = 0..2R (clamping already applied by the stager).
-__device__ __forceinline__ uint32_t blur_exact_taps(const uint32_t *px, int strideWords, int taps,
-                                                    const double *kernel) {
-    double r = 0.0, g = 0.0, b = 0.0;
-    for (int k = 0; k < taps; k++) {
-        uint32_t v = px[k * strideWords];
-        double wt = __ldg(kernel + k);
-        r = __dadd_rn(r, __dmul_rn((double)(v & 0xFF), wt));
-        g = __dadd_rn(g, __dmul_rn((double)((v >> 8) & 0xFF), wt));
-        b = __dadd_rn(b, __dmul_rn((double)((v >> 16) & 0xFF), wt));
-    }
-    return clampf_dev(r) | (clampf_dev(g) << 8) | (clampf_dev(b) << 16);
 }
 
 // Accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar; B of outputs (2m, 2m+1)
@@ -703,16 +680,17 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
                 const uint32_t brb = ((hPrevRB[i] + 2 * hCurRB[i] + hNextRB[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
                 const uint32_t bga = ((hPrevGA[i] + 2 * hCurGA[i] + hNextGA[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
                 if (MODE == 1 && INTK >= 0) {
+                    constexpr int K = INTK >= 0 ? INTK : 0;      // INTK < 0 never reaches here; keeps the shifts well-formed
                     // Integer unsharp on packed 16-bit lanes (R|B and G|A): per lane
                     //   T = orig*(A + 2^k) - blur*A + half + bias,   bias = 1024 << k  (lanes stay in [0, 32767])
                     //   out = relu(min((T >> k) - 1024, 255))        one DPX instruction (VIADDMNMX.S16x2.RELU)
                     // == min(max(((orig << k) + A*(orig - blur) + half) >> k, 0), 255), the exact form of effects.go:37-38
                     // for dyadic amounts (checked for every (orig, blur) pair and every (A, k) the launcher can pick).
-                    const uint32_t cst = (uint32_t)((1024 << INTK) + p.half) * 0x00010001u;
-                    const uint32_t msk = (uint32_t)(0xFFFF >> INTK) * 0x00010001u;
+                    const uint32_t cst = (uint32_t)((1024 << K) + p.half) * 0x00010001u;
+                    const uint32_t msk = (uint32_t)(0xFFFF >> K) * 0x00010001u;
                     const uint32_t orb = c & 0x00FF00FFu, oga = (c >> 8) & 0x00FF00FFu;
-                    const uint32_t trb = ((orb * (uint32_t)(p.A + (1 << INTK)) + cst - brb * (uint32_t)p.A) >> INTK) & msk;
-                    const uint32_t tga = ((oga * (uint32_t)(p.A + (1 << INTK)) + cst - bga * (uint32_t)p.A) >> INTK) & msk;
+                    const uint32_t trb = ((orb * (uint32_t)(p.A + (1 << K)) + cst - brb * (uint32_t)p.A) >> K) & msk;
+                    const uint32_t tga = ((oga * (uint32_t)(p.A + (1 << K)) + cst - bga * (uint32_t)p.A) >> K) & msk;
                     const uint32_t rrb = __viaddmin_s16x2_relu(trb, 0xFC00FC00u, 0x00FF00FFu);   // + (-1024) per lane
                     const uint32_t rga = __viaddmin_s16x2_relu(tga, 0xFC00FC00u, 0x00FF00FFu);
                     out[i] = ((rrb | (rga << 8)) & 0x00FFFFFFu) | (c & 0xFF000000u);
@@ -793,8 +771,9 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
                         const int orig = (int)((c >> (8 * ch)) & 0xFF);
                         const int diff = orig - bl[ch];
                         if (INTK >= 0) {
-                            int V = (orig << INTK) + p.A * diff + p.half;   // exact (see header comment)
-                            V = V < 0 ? 0 : (V >> INTK);
+                            constexpr int K = INTK >= 0 ? INTK : 0;
+                            int V = (orig << K) + p.A * diff + p.half;   // exact (see header comment)
+                            V = V < 0 ? 0 : (V >> K);
                             o[ch] = (uint32_t)min(V, 255);
                         } else {
                             double val = __dadd_rn(small_int_to_double(orig), __dmul_rn(amount, small_int_to_double(diff)));

@@ -568,7 +568,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(256, 2) ssim_ws_kernel(const SsimParams p) {
-    constexpr int CPL = 4, INC = 128, OUTC = 120;
+    constexpr int CPL = 4, OUTC = 120;
     extern __shared__ __align__(16) uint8_t ws_raw[];
     WsSmem &sm = *reinterpret_cast<WsSmem *>(ws_raw);
     const int lane = threadIdx.x & 31;
