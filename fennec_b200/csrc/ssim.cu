@@ -456,16 +456,179 @@ __device__ __forceinline__ double walk_strip_pipe(const StripCtx<4> &q) {
     return dsum;
 }
 
-#ifndef FB_SSIM_PIPE_DEFAULT
-#define FB_SSIM_PIPE_DEFAULT 0
+
+// ------------------------------------------------------------------------------------------------
+// Two rows per iteration (aligned inputs, CPL = 4).  walk_strip pays, per row, a three-level branch tree for the ring
+// slot, a loop branch and one shared-memory round trip with nothing else to issue (profiles/r1: 12 % of the warp
+// samples sit on BRA / ISETP / BSYNC / DEPBAR, and "wait" on fixed latencies is the largest stall).  Here one iteration
+// takes rows r and r+1: four slot cases instead of eight, half the branches per row, both vertical passes back to back
+// (16 independent FFMA2 chains), ONE __syncwarp for two rows, and the second row's neighbour loads are in flight
+// while the first row's horizontal taps issue.  Four V buffers (two iterations x two rows) keep the single-barrier
+// protocol of walk_strip valid.  An odd row count runs the second half of the last iteration on stale ring
+// data (finite: real pixel rows) with its outputs masked.
+// ------------------------------------------------------------------------------------------------
+struct HConsts {
+    float c, kTh;
+    float2 qpInit, one_two, neg2;
+};
+
+__device__ __forceinline__ void hpass_formula(const float4 (&own)[4], const float4 *vb, const float2 (&g2)[8],
+                                              const HConsts &k, const bool (&ok)[4], float (&fs)[4]) {
+    constexpr int CPL = 4, kVLanes = 36;
+    float4 it[CPL + 7];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) it[i] = own[i];
+#pragma unroll
+    for (int t = CPL; t < CPL + 7; t++) it[t] = vb[(t % CPL) * kVLanes + t / CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) {
+        float2 mab = __fmul2_rn(make_float2(it[i].x, it[i].y), g2[0]);
+        float2 mqp = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], k.qpInit);
+#pragma unroll
+        for (int t = 1; t < 8; t++) {
+            mab = __ffma2_rn(make_float2(it[i + t].x, it[i + t].y), g2[t], mab);
+            mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
+        }
+        const float2 sq = __fmul2_rn(mab, mab);
+        const float2 mn = make_float2(mab.x * mab.y, sq.x + sq.y);
+        const float th = fmaf(k.c, mab.x + mab.y, k.kTh);
+        const float2 AB1 = __ffma2_rn(make_float2(th, th), k.one_two, mn);
+        const float2 AB2 = __ffma2_rn(mn, k.neg2, make_float2(mqp.y, mqp.x));
+        const float2 nd = __fmul2_rn(AB1, AB2);
+        const float ssim4 = __fdividef(nd.x, nd.y);
+        fs[i] += ok[i] ? ssim4 : 0.f;
+    }
+}
+
+__device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
+    constexpr int CPL = 4;
+    const uint8_t *pa = q.pa, *pb = q.pb;
+    const int nIn = q.nIn, lane = q.lane;
+    const float2 s2 = make_float2(kLumaScale, kLumaScale);
+    const float2 K2 = make_float2(q.K, q.K);
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
+    HConsts hk;
+    hk.c = q.c;
+    hk.kTh = fmaf(q.c, q.c, 0.5f * kC1f);
+    hk.qpInit = make_float2(kC2f, 0.5f * kC2f);
+    hk.one_two = make_float2(1.f, 2.f);
+    hk.neg2 = make_float2(-1.f, -1.f);
+    float2 rab[8][CPL], rqp[8][CPL];
+    constexpr uint32_t kRowBuf = 32 * CPL * 4;
+    const uint32_t myRing = smem_u32(q.ring) + lane * 16;
+    const uint8_t *myRingP = q.ring + lane * 16;
+#pragma unroll
+    for (int row = 0; row < kStages; row++) {  // rows 0..3 exist (nIn >= 8)
+        cp_async<16>(myRing + (2 * row) * kRowBuf, pa);
+        cp_async<16>(myRing + (2 * row + 1) * kRowBuf, pb);
+        cp_async_commit();
+        pa += q.rowStrideA;
+        pb += q.rowStrideB;
+    }
+    // planes of row R (ring stage R & 3) into slot S, then refill the stage with row R + kStages
+#define W2_PLANES(S, R)                                                                         \
+    {                                                                                           \
+        cp_async_wait<kStages - 1>();                                                           \
+        const uint8_t *rb_ = myRingP + (2 * ((S) & (kStages - 1))) * kRowBuf;                   \
+        const uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                                \
+        const uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + kRowBuf);                      \
+        const uint32_t xa_[4] = {va_.x, va_.y, va_.z, va_.w}, xb_[4] = {vb_.x, vb_.y, vb_.z, vb_.w}; \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
+            float2 t = __ffma2_rn(f, s2, K2);                                                   \
+            float2 sq = __fmul2_rn(t, t);                                                       \
+            rab[S][i] = t;                                                                      \
+            rqp[S][i] = make_float2(sq.x + sq.y, t.x * t.y);                                    \
+        }                                                                                       \
+        if ((R) + kStages < nIn) {                                                              \
+            cp_async<16>(myRing + (2 * ((S) & (kStages - 1))) * kRowBuf, pa);                   \
+            cp_async<16>(myRing + (2 * ((S) & (kStages - 1)) + 1) * kRowBuf, pb);               \
+            pa += q.rowStrideA;                                                                 \
+            pb += q.rowStrideB;                                                                 \
+        }                                                                                       \
+        cp_async_commit();                                                                      \
+    }
+#define W2_VTAPS(S, V)                                                                          \
+    _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                           \
+        float2 vab = __fmul2_rn(rab[(S + 1) & 7][i], g2[0]);                                    \
+        float2 vqp = __fmul2_rn(rqp[(S + 1) & 7][i], g2[0]);                                    \
+        _Pragma("unroll") for (int j = 1; j < 8; j++) {                                         \
+            vab = __ffma2_rn(rab[(S + 1 + j) & 7][i], g2[j], vab);                              \
+            vqp = __ffma2_rn(rqp[(S + 1 + j) & 7][i], g2[j], vqp);                              \
+        }                                                                                       \
+        V[i] = make_float4(vab.x, vab.y, vqp.x, vqp.y);                                         \
+    }
+#pragma unroll
+    for (int r = 0; r < 7; r++) W2_PLANES(r, r)
+
+    float fs[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) fs[i] = 0.f;
+    constexpr int kVLanes = 36, kVBuf = CPL * kVLanes;
+    bool okA[CPL], okB[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) okA[i] = q.valid[i];
+
+#pragma unroll 1
+    for (int r = 7; r < nIn; r += 2) {
+        float4 vA[CPL], vB[CPL];
+#define W2_STEP(S0, S1)                                                                         \
+    case S0: {                                                                                  \
+        W2_PLANES(S0, r)                                                                        \
+        W2_VTAPS(S0, vA)                                                                        \
+        W2_PLANES(S1, r + 1)                                                                    \
+        W2_VTAPS(S1, vB)                                                                        \
+    } break;
+        switch (r & 7) {
+            W2_STEP(7, 0) W2_STEP(1, 2) W2_STEP(3, 4)
+            default: { W2_PLANES(5, r) W2_VTAPS(5, vA) W2_PLANES(6, r + 1) W2_VTAPS(6, vB) } break;
+        }
+#undef W2_STEP
+        float4 *vbA = q.vb0 + ((((r - 7) >> 1) & 1) ? 2 * kVBuf : 0) + lane;
+        float4 *vbB = vbA + kVBuf;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) { vbA[i * kVLanes] = vA[i]; vbB[i * kVLanes] = vB[i]; }
+        __syncwarp();
+        const bool second = r + 1 < nIn;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) okB[i] = q.valid[i] && second;
+        hpass_formula(vA, vbA, g2, hk, okA, fs);
+        hpass_formula(vB, vbB, g2, hk, okB, fs);
+    }
+#undef W2_PLANES
+#undef W2_VTAPS
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    return dsum;
+}
+
+// Defaults from the round-2 sweep on 64 4K pairs (profiles/r2_k1_variants.txt): walk_strip / 4 warps per block 2.062 ms,
+// walk_strip / 1 warp 1.882, walk_strip2 / 2 warps 1.956, walk_strip2 / 1 warp 1.769, walk_strip_pipe 2.272.
+#ifndef FB_SSIM_MODE_DEFAULT
+#define FB_SSIM_MODE_DEFAULT 2
+#endif
+#ifndef FB_SSIM_WPB_DEFAULT
+#define FB_SSIM_WPB_DEFAULT 1
 #endif
 
-template <int CPL, bool PIPE = false>
-__global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_strip_kernel(const SsimParams p) {
-    constexpr int WARPS = 4;
+// MODE 0: walk_strip, 1: walk_strip_pipe, 2: walk_strip2.  WPB = warps (independent strips) per block: warps never
+// synchronise with each other, so the block size only sets the granularity at which the SM's registers are handed out:
+// 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at ~200 registers without a cap below 8 blocks:
+// 9-10 warps per SM, a third warp on one or two schedulers).
+template <int CPL, int WPB>
+constexpr int ssim_min_blocks() { return CPL != 4 ? 16 / WPB : (WPB == 4 ? FB_SSIM_MINB4 : WPB == 2 ? 4 : 8); }
+
+template <int CPL, int MODE = 0, int WPB = 4>
+__global__ void __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>())) ssim_strip_kernel(const SsimParams p) {
+    constexpr int WARPS = WPB;
+    constexpr bool PIPE = MODE == 1;
+    constexpr int NVB = MODE == 2 ? 4 : 2;
     constexpr int INC = 32 * CPL;    // input columns per strip
     constexpr int OUTC = INC - 8;    // outputs per strip (multiple of 4 → 16-byte aligned strips)
-    __shared__ float4 vbuf[WARPS][2][CPL * 36];   // padded V rows, see walk_strip
+    __shared__ float4 vbuf[WARPS][NVB][CPL * 36];   // padded V rows, see walk_strip
     __shared__ __align__(128) uint8_t pxring[WARPS][kStages][2][INC * 4];
 
     const int lane = threadIdx.x & 31;
@@ -493,8 +656,8 @@ __global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_stri
     if (lane < 4) {  // zero the pad slots once (they feed masked outputs only, but must stay finite)
 #pragma unroll
         for (int i = 0; i < CPL; i++) {
-            vbuf[warp][0][i * 36 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            vbuf[warp][1][i * 36 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int v = 0; v < NVB; v++) vbuf[warp][v][i * 36 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     __syncwarp();
@@ -522,6 +685,7 @@ __global__ void __launch_bounds__(128, (CPL == 4 ? FB_SSIM_MINB4 : 4)) ssim_stri
 
     double dsum;
     if (PIPE && CPL == 4) dsum = fast ? walk_strip_pipe(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
+    else if (MODE == 2 && CPL == 4) dsum = fast ? walk_strip2(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
     else dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
@@ -917,9 +1081,21 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
         }
         ssim_ws_kernel<<<(unsigned)blocks, 256, sizeof(WsSmem), s>>>(p);
     } else if (g.cpl == 4) {
-        static const bool usePipe = [] { const char *e = getenv("FB_SSIM_PIPE"); return e ? e[0] == '1' : (FB_SSIM_PIPE_DEFAULT != 0); }();
-        if (usePipe) ssim_strip_kernel<4, true><<<(unsigned)blocks, 128, 0, s>>>(p);
-        else ssim_strip_kernel<4, false><<<(unsigned)blocks, 128, 0, s>>>(p);
+        // FB_SSIM_PIPE=1 / FB_SSIM_MODE=0|1|2 pick the row walk, FB_SSIM_WPB=1|4 the warps per block (experiments;
+        // every combination is parity-tested in tests/test_variants_gpu.py).
+        static const int mode = [] {
+            const char *e = getenv("FB_SSIM_PIPE");
+            if (e && e[0] == '1') return 1;
+            const char *m = getenv("FB_SSIM_MODE");
+            return (m && m[0] >= '0' && m[0] <= '2') ? m[0] - '0' : FB_SSIM_MODE_DEFAULT;
+        }();
+        static const int wpb = [] { const char *e = getenv("FB_SSIM_WPB"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : FB_SSIM_WPB_DEFAULT; }();
+        const unsigned nb = (unsigned)((segs + wpb - 1) / wpb);
+        if (mode == 1) ssim_strip_kernel<4, 1, 4><<<(unsigned)blocks, 128, 0, s>>>(p);
+        else if (mode == 2 && wpb == 1) ssim_strip_kernel<4, 2, 1><<<nb, 32, 0, s>>>(p);
+        else if (mode == 2) ssim_strip_kernel<4, 2, 2><<<(unsigned)((segs + 1) / 2), 64, 0, s>>>(p);   // 4 V buffers: 2 warps stay under 48 KB static
+        else if (wpb == 1) ssim_strip_kernel<4, 0, 1><<<nb, 32, 0, s>>>(p);
+        else ssim_strip_kernel<4, 0, 4><<<nb, 128, 0, s>>>(p);
     }
     else ssim_strip_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(p);
     FB_CUDA(cudaGetLastError());

@@ -17,6 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("env", [
     {"FB_SSIM_WS": "1"}, {"FB_SSIM_CPL": "2"},
+    {"FB_SSIM_MODE": "0", "FB_SSIM_WPB": "4"}, {"FB_SSIM_MODE": "0", "FB_SSIM_WPB": "1"},
+    {"FB_SSIM_MODE": "2", "FB_SSIM_WPB": "4"}, {"FB_SSIM_MODE": "1"},
     {"FB_BLUR_GENERIC": "1", "FB_FX_GENERIC": "1", "FB_RESIZE_GENERIC": "1"},
 ])
 def test_kernel_variant_matches_golden(env, lib):
