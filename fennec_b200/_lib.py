@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libfennec_b200.so")
 
 FB_OK, FB_IDENTITY = 0, 1
-FB_E_INVALID, FB_E_NOGPU, FB_E_CUDA, FB_E_OOM = -1, -2, -3, -4
+FB_E_INVALID, FB_E_NOGPU, FB_E_CUDA, FB_E_OOM, FB_E_CANCELLED = -1, -2, -3, -4, -5
+FB_OP_SSIM, FB_OP_SSIM_FAST, FB_OP_MSSSIM = 0, 1, 2
+FB_FX_GAUSSIAN_BLUR, FB_FX_SHARPEN, FB_FX_ADAPTIVE_SHARPEN = 0, 1, 2
 
 u8p = C.POINTER(C.c_uint8)
 dp = C.POINTER(C.c_double)
@@ -30,6 +32,28 @@ class FbImageStats(C.Structure):
                 ("unique_colors", C.c_int), ("entropy", C.c_double), ("edge_density", C.c_double),
                 ("mean_brightness", C.c_double), ("contrast", C.c_double), ("recommended_format", C.c_int),
                 ("recommended_quality", C.c_int), ("estimated_compression", C.c_double)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_void_p)
+
+
+class FbBatchOpts(C.Structure):
+    """struct fb_batch_opts (BatchOptions, batch.go:33-44)."""
+    _fields_ = [("workers_per_device", C.c_int), ("cancel", ip), ("on_item", PROGRESS_FN), ("user", C.c_void_p)]
+
+
+class FbPair(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("strideA", C.c_int), ("b", C.c_void_p), ("strideB", C.c_int), ("w", C.c_int), ("h", C.c_int)]
+
+
+class FbResizeItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("srcStride", C.c_int), ("srcW", C.c_int), ("srcH", C.c_int),
+                ("dst", C.c_void_p), ("dstStride", C.c_int), ("dstW", C.c_int), ("dstH", C.c_int)]
+
+
+class FbEffectItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("srcStride", C.c_int), ("dst", C.c_void_p), ("dstStride", C.c_int),
+                ("w", C.c_int), ("h", C.c_int)]
 
 
 _IMG = [u8p, C.c_int]
@@ -103,6 +127,13 @@ PROTOTYPES = {
     "fb_workspace_bytes": (C.c_size_t, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fb_batch_shard": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
     "fb_take_launch_count": (C.c_longlong, []),
+    "fb_score_batch_host": (C.c_int, [C.c_int, C.POINTER(FbPair), C.c_int, dp, ip, C.POINTER(FbBatchOpts)]),
+    "fb_lanczos_resize_batch_host": (C.c_int, [C.POINTER(FbResizeItem), C.c_int, ip, C.POINTER(FbBatchOpts)]),
+    "fb_effect_batch_host": (C.c_int, [C.c_int, C.c_double, C.POINTER(FbEffectItem), C.c_int, ip, C.POINTER(FbBatchOpts)]),
+    "fb_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+    "fb_free_pinned": (None, [C.c_void_p]),
+    "fb_debug_pool_size": (C.c_int, []),
+    "fb_debug_table_count": (C.c_int, []),
 }
 
 

@@ -384,3 +384,107 @@ def apply_palette(src: np.ndarray, palette: np.ndarray) -> Tuple[np.ndarray, np.
     pd, sd, _, _ = _img(dst)
     check(_lib.load().fb_apply_palette(p, stride, w, h, pal.ctypes.data_as(u8p), pal.shape[0], idx.ctypes.data_as(u8p), w, pd, sd))
     return idx, dst
+
+
+# ---- batch.go: CompressBatch's worker pool behind one call (host buffers, every initialised GPU) ---------------
+
+class _BatchOpts:
+    """Builds struct fb_batch_opts and keeps its ctypes objects alive for the duration of the call."""
+
+    def __init__(self, workers_per_device=0, cancel=None, on_item=None):
+        self.cancel = cancel if cancel is not None else C.c_int(0)
+        self._cb = _lib.PROGRESS_FN(lambda done, total, _u: on_item(done, total)) if on_item else _lib.PROGRESS_FN()
+        self.struct = _lib.FbBatchOpts(int(workers_per_device), C.pointer(self.cancel), self._cb, None)
+
+
+def _statuses(n):
+    return (C.c_int * max(n, 1))()
+
+
+def score_batch(op: str, pairs, workers_per_device: int = 0, cancel=None, on_item=None):
+    """fb_score_batch_host: fennec.SSIM / SSIMFast / MSSSIM for a list of (img1, img2) host pairs, sharded over every
+    initialised GPU from this one process (batch.go:58-128).  Returns (scores, statuses) in input order; items whose
+    status is negative (failed or cancelled) carry NaN."""
+    code = {"ssim": _lib.FB_OP_SSIM, "ssim_fast": _lib.FB_OP_SSIM_FAST, "msssim": _lib.FB_OP_MSSSIM}[op]
+    n = len(pairs)
+    arr = (_lib.FbPair * max(n, 1))()
+    for i, (a, b) in enumerate(pairs):
+        pa, sa, w, h = _img(a)
+        pb, sb, wb, hb = _img(b)
+        if (w, h) != (wb, hb):
+            raise ValueError(f"pair {i}: images must have equal dimensions")
+        arr[i] = _lib.FbPair(C.cast(pa, C.c_void_p), sa, C.cast(pb, C.c_void_p), sb, w, h)
+    scores = np.full(max(n, 1), np.nan, dtype=np.float64)
+    st = _statuses(n)
+    opts = _BatchOpts(workers_per_device, cancel, on_item)
+    check(_lib.load().fb_score_batch_host(code, arr, n, scores.ctypes.data_as(dp), st, C.byref(opts.struct)))
+    st = list(st)[:n]
+    scores = scores[:n]
+    scores[[i for i, s_ in enumerate(st) if s_ < 0]] = np.nan
+    return scores, st
+
+
+def lanczos_resize_batch(imgs, dst_w: int, dst_h: int, workers_per_device: int = 0, cancel=None, on_item=None):
+    """fb_lanczos_resize_batch_host: lanczosResize (resize.go:37-53) of every image of a list → (outputs, statuses)."""
+    n = len(imgs)
+    arr = (_lib.FbResizeItem * max(n, 1))()
+    outs = []
+    for i, im in enumerate(imgs):
+        ps, ss, sw, sh = _img(im)
+        dst = _new(max(dst_h, 0), max(dst_w, 0))
+        pd, sd, _, _ = _img(dst)
+        outs.append(dst)
+        arr[i] = _lib.FbResizeItem(C.cast(ps, C.c_void_p), ss, sw, sh, C.cast(pd, C.c_void_p), sd, dst_w, dst_h)
+    st = _statuses(n)
+    opts = _BatchOpts(workers_per_device, cancel, on_item)
+    check(_lib.load().fb_lanczos_resize_batch_host(arr, n, st, C.byref(opts.struct)))
+    st = list(st)[:n]
+    return [(_empty() if s_ == FB_IDENTITY else o) for o, s_ in zip(outs, st)], st
+
+
+def effect_batch(effect: str, param: float, imgs, workers_per_device: int = 0, cancel=None, on_item=None):
+    """fb_effect_batch_host: GaussianBlur(sigma) / Sharpen(strength) / AdaptiveSharpen(strength) of every image of a
+    list; where the reference returns its input pointer (effects.go:11-22,147-149) the SAME array object comes back."""
+    code = {"gaussian_blur": _lib.FB_FX_GAUSSIAN_BLUR, "sharpen": _lib.FB_FX_SHARPEN,
+            "adaptive_sharpen": _lib.FB_FX_ADAPTIVE_SHARPEN}[effect]
+    n = len(imgs)
+    arr = (_lib.FbEffectItem * max(n, 1))()
+    outs = []
+    for i, im in enumerate(imgs):
+        ps, ss, w, h = _img(im)
+        dst = _new(h, w)
+        pd, sd, _, _ = _img(dst)
+        outs.append(dst)
+        arr[i] = _lib.FbEffectItem(C.cast(ps, C.c_void_p), ss, C.cast(pd, C.c_void_p), sd, w, h)
+    st = _statuses(n)
+    opts = _BatchOpts(workers_per_device, cancel, on_item)
+    check(_lib.load().fb_effect_batch_host(code, float(param), arr, n, st, C.byref(opts.struct)))
+    st = list(st)[:n]
+    return [(im if s_ == FB_IDENTITY else o) for im, o, s_ in zip(imgs, outs, st)], st
+
+
+def init(devices=None) -> int:
+    """fb_init: select the GPUs this process uses (None = all visible); returns the device count."""
+    if devices is None:
+        return check(_lib.load().fb_init(None, 0))
+    arr = (C.c_int * len(devices))(*devices)
+    return check(_lib.load().fb_init(arr, len(devices)))
+
+
+def shutdown() -> None:
+    _lib.load().fb_shutdown()
+
+
+def pinned_empty(shape) -> np.ndarray:
+    """A uint8 array in page-locked host memory (fb_alloc_pinned): uploads from it are DMA'ed without staging.  The
+    memory is released when the array (and every view of it) is garbage-collected."""
+    import weakref
+    nbytes = int(np.prod(shape))
+    L = _lib.load()
+    ptr = L.fb_alloc_pinned(nbytes)
+    if not ptr:
+        check(_lib.FB_E_OOM)
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes).reshape(shape)
+    weakref.finalize(buf, L.fb_free_pinned, ptr)
+    return arr

@@ -187,17 +187,28 @@ def gaussian_blur_batch(src: torch.Tensor, sigma: float, out: Optional[torch.Ten
         kernel = np.ascontiguousarray(kernel, dtype=np.float64)
         radius = (len(kernel) - 1) // 2
     ps, i_s, rs, w, h, n = _batch(src)
-    if out is None:
-        out = torch.empty_like(src)
+    out = _like(src, out)
     check(_lib.load().fb_gaussian_blur_batch_dev(_dev(src), _stream(src), ps, out.data_ptr(), i_s, rs, w, h, n,
                                                  kernel.ctypes.data_as(dp), radius))
     return out
 
 
+def _like(src: torch.Tensor, out: Optional[torch.Tensor]) -> torch.Tensor:
+    """Destination for the blur / sharpen entry points, which apply src's image and row strides to dst as well: a fresh
+    tensor gets src's exact strides (empty_like would compact a row-padded or sliced src and the kernel would then
+    write past its end); a caller-supplied one must match src in shape AND strides."""
+    if out is None:
+        return torch.empty_strided(tuple(src.shape), tuple(src.stride()), dtype=src.dtype, device=src.device)
+    _batch(out)
+    if out.device != src.device or tuple(out.shape) != tuple(src.shape) or tuple(out.stride()) != tuple(src.stride()):
+        raise ValueError(f"out must match src in device, shape and strides: src {tuple(src.shape)}/{tuple(src.stride())}, "
+                         f"out {tuple(out.shape)}/{tuple(out.stride())}")
+    return out
+
+
 def _fx(fn, src, strength, out):
     ps, i_s, rs, w, h, n = _batch(src)
-    if out is None:
-        out = torch.empty_like(src)
+    out = _like(src, out)
     if check(fn(_dev(src), _stream(src), ps, out.data_ptr(), i_s, rs, w, h, n, float(strength))) == FB_IDENTITY:
         return src
     return out

@@ -10,8 +10,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -170,16 +174,46 @@ static void table_stats(const int *start, const double *weight, int n, int *maxT
         if (start[d + 1] - start[d] > *maxTaps) *maxTaps = start[d + 1] - start[d];
     }
 }
+// Contexts (stream + arenas) live in a process-wide pool keyed by device.  A thread checks one out on first use and
+// its thread_local destructor hands it back, so a worker that exits (a LockOSThread'ed goroutine ends its OS
+// thread; CompressBatch starts fresh workers per call, batch.go:84-124) leaves its 100 MB-class arenas to the next
+// worker instead of leaking them: the pool never holds more contexts than the peak number of concurrent threads.
+struct CtxPool {
+    std::mutex mu;
+    std::vector<std::vector<DevCtx *>> idle;   // per device
+};
+static CtxPool g_pool;
+
+static void destroy_ctx(DevCtx *c) {   // the device of *c is current
+    cudaStreamSynchronize(c->stream);
+    if (c->ws.base) cudaFree(c->ws.base);
+    if (c->pin.base) cudaFreeHost(c->pin.base);
+    if (c->stage) cudaFreeHost(c->stage);
+    if (c->ev) cudaEventDestroy(c->ev);
+    if (c->useEv) cudaEventDestroy(c->useEv);
+    for (int i = 0; i < 2; i++) if (c->stageEv[i]) cudaEventDestroy(c->stageEv[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
 struct ThreadState {
-    std::vector<DevCtx> ctxs;
-    std::vector<bool> pinBusy;
-    std::map<std::pair<int, TableKey>, LanczosTable> lanczos;  // (device, key) → device tables
+    std::vector<DevCtx *> ctxs;
     ~ThreadState() {
-        // Streams and arenas are reclaimed by fb_shutdown / process exit; destroying CUDA objects from
-        // a thread destructor can race with runtime teardown, so we deliberately leave them.
+        // No CUDA calls here (a thread destructor can race with runtime teardown): the contexts only change hands.
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        for (DevCtx *c : ctxs) {
+            if (!c) continue;
+            if ((int)g_pool.idle.size() <= c->dev) g_pool.idle.resize(c->dev + 1);
+            g_pool.idle[c->dev].push_back(c);
+        }
     }
 };
 static thread_local ThreadState t_state;
+
+static int phys_device(int dev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_devices[dev];
+}
 
 DevCtx *ctx(int dev) {
     int nd = ensure_init();
@@ -188,37 +222,70 @@ DevCtx *ctx(int dev) {
         set_error("device index %d out of range (fb_init selected %d device(s))", dev, nd);
         return nullptr;
     }
-    if ((int)t_state.ctxs.size() < nd) {
-        t_state.ctxs.resize(nd);
-        t_state.pinBusy.resize(nd, false);
-    }
-    DevCtx *c = &t_state.ctxs[dev];
-    int phys;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        phys = g_devices[dev];
-    }
-    if (cudaSetDevice(phys) != cudaSuccess) {
+    if ((int)t_state.ctxs.size() < nd) t_state.ctxs.resize(nd, nullptr);
+    if (cudaSetDevice(phys_device(dev)) != cudaSuccess) {
         cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
         return nullptr;
     }
-    if (c->dev < 0) {
+    DevCtx *c = t_state.ctxs[dev];
+    if (c) return c;
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        if ((int)g_pool.idle.size() > dev && !g_pool.idle[dev].empty()) {
+            c = g_pool.idle[dev].back();
+            g_pool.idle[dev].pop_back();
+        }
+    }
+    if (!c) {
+        c = new DevCtx();
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->useEv, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->stageEv[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->stageEv[1], cudaEventDisableTiming) != cudaSuccess) {
             cuda_fail(cudaGetLastError(), "stream/event creation", __FILE__, __LINE__);
+            destroy_ctx(c);
             return nullptr;
         }
         c->dev = dev;
     }
+    t_state.ctxs[dev] = c;
     return c;
 }
 
-int reserve(DevCtx *c, size_t dev_bytes, size_t pinned_bytes) {
-    // The pinned arena may still feed an async H2D enqueued by a previous _dev call.
-    if (t_state.pinBusy[c->dev]) {
-        FB_CUDA(cudaEventSynchronize(c->ev));
-        t_state.pinBusy[c->dev] = false;
+// Every entry point that touches a device opens one: it restores the caller's current CUDA device on return (the
+// library selects its own; a *_batch_dev call for a tensor on cuda:1 must not leave the thread on cuda:1), and for
+// device-resident calls it records, behind the enqueued work, the event that orders the next user of the arena.
+struct ApiScope {
+    int prev = -1;
+    DevCtx *c = nullptr;
+    cudaStream_t s = nullptr;
+    ApiScope() {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
     }
+    void bind(DevCtx *ctx_, cudaStream_t stream) { c = ctx_; s = stream; }
+    ~ApiScope() {
+        if (c) {
+            if (cudaEventRecord(c->useEv, s) == cudaSuccess) { c->usePending = true; c->lastStream = s; }
+            else cudaGetLastError();
+        }
+        if (prev >= 0) {
+            int cur = -1;
+            if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+        }
+    }
+};
+
+int reserve(DevCtx *c, cudaStream_t s, size_t dev_bytes, size_t pinned_bytes) {
+    // The pinned arena may still feed an async H2D enqueued by a previous _dev call.
+    if (c->pinBusy) {
+        FB_CUDA(cudaEventSynchronize(c->ev));
+        c->pinBusy = false;
+    }
+    // The device arena may still be in use by work a previous _dev call enqueued on ANOTHER stream (host entry points
+    // run on c->stream and synchronise before returning; _dev calls run on the caller's stream and do not).
+    if (c->usePending && c->lastStream != s) FB_CUDA(cudaStreamWaitEvent(s, c->useEv, 0));
+    if (c->usePending && c->lastStream != s) c->usePending = false;
     dev_bytes += 4096;
     pinned_bytes += 4096;
     if (c->ws.cap < dev_bytes) {
@@ -255,7 +322,7 @@ int reserve(DevCtx *c, size_t dev_bytes, size_t pinned_bytes) {
 
 static void mark_pin_busy(DevCtx *c, cudaStream_t s) {
     cudaEventRecord(c->ev, s);
-    t_state.pinBusy[c->dev] = true;
+    c->pinBusy = true;
 }
 
 // ---- host-side rules and table builders (host side of the boundary) -----------------------------
@@ -338,20 +405,29 @@ static int lanczos_build(int dstSize, int srcSize, int *start, int *index, doubl
     return n;
 }
 
-// Upload a CSR table into persistent device memory of this thread's context (cached per dims when
-// the library built it; caller-supplied tables are uploaded per call into the arena instead).
-static int lanczos_table_cached(DevCtx *c, int dstSize, int srcSize, LanczosTable *out) {
-    std::pair<int, TableKey> key{c->dev, TableKey{1, dstSize, srcSize}};
-    auto it = t_state.lanczos.find(key);
-    if (it != t_state.lanczos.end()) {
-        *out = it->second;
-        return FB_OK;
-    }
+// Library-built CSR tables live in persistent device memory, shared by every thread (they are immutable once
+// uploaded) and bounded: at most kLanczosCacheMax (dstSize, srcSize) pairs per process, least recently used first out.
+// Eviction synchronises the device before freeing (a kernel enqueued by another thread may still read the table);
+// it only happens when a service cycles through more than kLanczosCacheMax distinct resize geometries.
+// Caller-supplied tables are uploaded per call into the arena instead.
+constexpr size_t kLanczosCacheMax = 64;
+struct CachedTable { LanczosTable t; unsigned long long stamp; };
+static std::mutex g_tab_mu;
+static std::map<std::pair<int, TableKey>, CachedTable> g_lanczos;   // (device, key) → device tables
+static unsigned long long g_tab_clock = 0;
+
+static void free_table(LanczosTable &t) {
+    cudaFree(t.start); cudaFree(t.index); cudaFree(t.weight); cudaFree(t.weight32); cudaFree(t.first); cudaFree(t.wpadT);
+    t = LanczosTable();
+}
+
+static int lanczos_table_upload(int dstSize, int srcSize, LanczosTable *out) {
     int cap = lanczos_cap(dstSize, srcSize);
     std::vector<int> start(dstSize + 1), index(cap + 1);
     std::vector<double> weight(cap + 1);
     int n = lanczos_build(dstSize, srcSize, start.data(), index.data(), weight.data());
-    LanczosTable t;
+    LanczosTable &t = *out;
+    t = LanczosTable();
     t.entries = n;
     table_stats(start.data(), weight.data(), dstSize, &t.maxTaps, &t.wabs);
     detect_int_ratio(start.data(), index.data(), weight.data(), dstSize, srcSize, &t.ir);
@@ -373,7 +449,35 @@ static int lanczos_table_cached(DevCtx *c, int dstSize, int srcSize, LanczosTabl
         FB_CUDA(cudaMemcpy(t.first, first.data(), sizeof(int) * dstSize, cudaMemcpyHostToDevice));
         FB_CUDA(cudaMemcpy(t.wpadT, wpadT.data(), sizeof(float) * wpadT.size(), cudaMemcpyHostToDevice));
     }
-    t_state.lanczos[key] = t;
+    return FB_OK;
+}
+
+static int lanczos_table_cached(DevCtx *c, int dstSize, int srcSize, LanczosTable *out) {
+    std::pair<int, TableKey> key{c->dev, TableKey{1, dstSize, srcSize}};
+    std::lock_guard<std::mutex> lk(g_tab_mu);   // the device of *c is current (ctx() selected it)
+    auto it = g_lanczos.find(key);
+    if (it != g_lanczos.end()) {
+        it->second.stamp = ++g_tab_clock;
+        *out = it->second.t;
+        return FB_OK;
+    }
+    if (g_lanczos.size() >= kLanczosCacheMax) {
+        auto victim = g_lanczos.end();
+        for (auto j = g_lanczos.begin(); j != g_lanczos.end(); ++j)
+            if (j->first.first == c->dev && (victim == g_lanczos.end() || j->second.stamp < victim->second.stamp)) victim = j;
+        if (victim != g_lanczos.end()) {
+            FB_CUDA(cudaDeviceSynchronize());
+            free_table(victim->second.t);
+            g_lanczos.erase(victim);
+        }
+    }
+    LanczosTable t;
+    int rc = lanczos_table_upload(dstSize, srcSize, &t);
+    if (rc < 0) {   // partial allocations of a failed upload do not stay behind
+        free_table(t);
+        return rc;
+    }
+    g_lanczos[key] = CachedTable{t, ++g_tab_clock};
     *out = t;
     return FB_OK;
 }
@@ -584,17 +688,109 @@ static int check_img(const char *fn, const void *p, int stride, int w, int h) {
     return FB_OK;
 }
 
+// Pageable caller memory (a Go Pix slice, a numpy array) cannot be DMA'ed directly: cudaMemcpyAsync stages it
+// inside the driver, one copy at a time per process (measured: 12 GB/s, and concurrent callers serialise).  The library
+// stages it itself instead — rows are packed into one of two pinned chunks by the calling thread while the previous
+// chunk's DMA is in flight — so every caller thread overlaps its own memcpy with its own DMA and N threads stage in
+// parallel.  Pinned or registered caller memory (fb_alloc_pinned) takes the direct path.
+constexpr size_t kStageChunk = 4u << 20;
+
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int stage_acquire(DevCtx *c, int *slot, char **buf) {
+    if (!c->stage) {
+        void *p = nullptr;
+        FB_CUDA(cudaMallocHost(&p, 2 * kStageChunk));
+        c->stage = (char *)p;
+    }
+    const int k = (int)(c->stageNext++ & 1);
+    if (c->stageBusy[k]) {
+        FB_CUDA(cudaEventSynchronize(c->stageEv[k]));
+        c->stageBusy[k] = false;
+    }
+    *slot = k;
+    *buf = c->stage + (size_t)k * kStageChunk;
+    return FB_OK;
+}
+
+// rows x rowBytes from host (stride hostStride) to device (pitch devPitch) on c->stream.
+static int upload_rows(DevCtx *c, const uint8_t *host, size_t hostStride, uint8_t *dev, size_t devPitch, size_t rowBytes,
+                       int rows) {
+    static const bool noStage = getenv("FB_NO_STAGING") != nullptr;
+    if (rows <= 0 || rowBytes == 0) return FB_OK;
+    if (noStage || rowBytes > kStageChunk || !host_is_pageable(host)) {
+        FB_CUDA(cudaMemcpy2DAsync(dev, devPitch, host, hostStride, rowBytes, rows, cudaMemcpyHostToDevice, c->stream));
+        return FB_OK;
+    }
+    const int per = (int)(kStageChunk / rowBytes);
+    for (int r0 = 0; r0 < rows; r0 += per) {
+        const int nr = rows - r0 < per ? rows - r0 : per;
+        int slot;
+        char *buf;
+        FB_TRY(stage_acquire(c, &slot, &buf));
+        const uint8_t *src = host + (size_t)r0 * hostStride;
+        if (hostStride == rowBytes) memcpy(buf, src, rowBytes * nr);
+        else for (int r = 0; r < nr; r++) memcpy(buf + (size_t)r * rowBytes, src + (size_t)r * hostStride, rowBytes);
+        FB_CUDA(cudaMemcpy2DAsync(dev + (size_t)r0 * devPitch, devPitch, buf, rowBytes, rowBytes, nr, cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(cudaEventRecord(c->stageEv[slot], c->stream));
+        c->stageBusy[slot] = true;
+    }
+    return FB_OK;
+}
+
+// device → host; returns after the caller's buffer holds the data when it was staged (pageable), otherwise the copy is
+// only enqueued and the entry point's cudaStreamSynchronize completes it.
+static int download_rows(DevCtx *c, const uint8_t *dev, size_t devPitch, uint8_t *host, size_t hostStride, size_t rowBytes,
+                         int rows) {
+    static const bool noStage = getenv("FB_NO_STAGING") != nullptr;
+    if (rows <= 0 || rowBytes == 0) return FB_OK;
+    if (noStage || rowBytes > kStageChunk || !host_is_pageable(host)) {
+        FB_CUDA(cudaMemcpy2DAsync(host, hostStride, dev, devPitch, rowBytes, rows, cudaMemcpyDeviceToHost, c->stream));
+        return FB_OK;
+    }
+    const int per = (int)(kStageChunk / rowBytes);
+    int pendSlot = -1, pendR0 = 0, pendN = 0;
+    char *pendBuf = nullptr;
+    auto drain = [&]() -> int {
+        if (pendSlot < 0) return FB_OK;
+        FB_CUDA(cudaEventSynchronize(c->stageEv[pendSlot]));
+        c->stageBusy[pendSlot] = false;
+        uint8_t *dst = host + (size_t)pendR0 * hostStride;
+        if (hostStride == rowBytes) memcpy(dst, pendBuf, rowBytes * pendN);
+        else for (int r = 0; r < pendN; r++) memcpy(dst + (size_t)r * hostStride, pendBuf + (size_t)r * rowBytes, rowBytes);
+        pendSlot = -1;
+        return FB_OK;
+    };
+    for (int r0 = 0; r0 < rows; r0 += per) {
+        const int nr = rows - r0 < per ? rows - r0 : per;
+        int slot;
+        char *buf;
+        FB_TRY(stage_acquire(c, &slot, &buf));
+        FB_CUDA(cudaMemcpy2DAsync(buf, rowBytes, dev + (size_t)r0 * devPitch, devPitch, rowBytes, nr, cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(cudaEventRecord(c->stageEv[slot], c->stream));
+        c->stageBusy[slot] = true;
+        FB_TRY(drain());   // the previous chunk is copied out while this one is in flight
+        pendSlot = slot; pendR0 = r0; pendN = nr; pendBuf = buf;
+    }
+    return drain();
+}
+
 static int upload(DevCtx *c, const uint8_t *host, int stride, int w, int h, uint8_t **dev, int *pitch) {
     *pitch = dev_pitch(w);
     *dev = (uint8_t *)c->ws.take((size_t)*pitch * h + 16);
     if (!*dev) { set_error("internal: workspace under-reserved (upload)"); return FB_E_INVALID; }
-    FB_CUDA(cudaMemcpy2DAsync(*dev, *pitch, host, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, c->stream));
-    return FB_OK;
+    return upload_rows(c, host, (size_t)stride, *dev, (size_t)*pitch, (size_t)w * 4, h);
 }
 
 static int download(DevCtx *c, const uint8_t *dev, int pitch, uint8_t *host, int stride, int w, int h) {
-    FB_CUDA(cudaMemcpy2DAsync(host, stride, dev, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, c->stream));
-    return FB_OK;
+    return download_rows(c, dev, (size_t)pitch, host, (size_t)stride, (size_t)w * 4, h);
 }
 
 static int finish_score(DevCtx *c, const double *dscore, double *out) {
@@ -617,6 +813,7 @@ static int host_score(const char *fn, ScoreOp op, const uint8_t *a, int strideA,
         *out = 1.0;
         return FB_OK;
     }
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     size_t img = (size_t)dev_pitch(w) * h + 512;
@@ -624,7 +821,7 @@ static int host_score(const char *fn, ScoreOp op, const uint8_t *a, int strideA,
     if (op == OP_SSIM || op == OP_PIXEL) need += ssim_scratch_bytes(w, h, 1);
     if (op == OP_SSIM_FAST) need += ssim_fast_scratch(w, h, 1);
     if (op == OP_MSSSIM) need += msssim_scratch(w, h, 1);
-    FB_TRY(reserve(c, need, 256));
+    FB_TRY(reserve(c, c->stream, need, 256));
     uint8_t *da, *db;
     int pa, pb;
     FB_TRY(upload(c, a, strideA, w, h, &da, &pa));
@@ -678,36 +875,61 @@ int fb_init(const int *devices, int n) {
 }
 
 void fb_shutdown(void) {
-    // Per-thread objects of the calling thread are released; other threads' objects go with the process.
-    for (auto &c : t_state.ctxs) {
-        if (c.dev < 0) continue;
-        int phys;
-        {
-            std::lock_guard<std::mutex> lk(g_mu);
-            phys = g_devices[c.dev];
-        }
-        cudaSetDevice(phys);
-        cudaStreamSynchronize(c.stream);
-        if (c.ws.base) cudaFree(c.ws.base);
-        if (c.pin.base) cudaFreeHost(c.pin.base);
-        cudaEventDestroy(c.ev);
-        cudaStreamDestroy(c.stream);
-        c = DevCtx();
-    }
-    for (auto &kv : t_state.lanczos) {
-        cudaFree(kv.second.start);
-        cudaFree(kv.second.index);
-        cudaFree(kv.second.weight);
-        cudaFree(kv.second.weight32);
-        cudaFree(kv.second.first);
-        cudaFree(kv.second.wpadT);
-    }
-    t_state.lanczos.clear();
+    // Releases the calling thread's contexts, every pooled (idle) context and the shared tables.  Contexts still
+    // checked out by other live threads go with the process (call fb_shutdown after the workers have finished).
+    std::vector<DevCtx *> victims;
+    for (auto &c : t_state.ctxs) if (c) victims.push_back(c);
     t_state.ctxs.clear();
-    t_state.pinBusy.clear();
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        for (auto &v : g_pool.idle) { victims.insert(victims.end(), v.begin(), v.end()); v.clear(); }
+    }
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    for (DevCtx *c : victims) {
+        cudaSetDevice(phys_device(c->dev));
+        destroy_ctx(c);
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_tab_mu);
+        for (auto &kv : g_lanczos) {
+            cudaSetDevice(phys_device(kv.first.first));
+            cudaDeviceSynchronize();
+            free_table(kv.second.t);
+        }
+        g_lanczos.clear();
+    }
+    if (prev >= 0) cudaSetDevice(prev);
     std::lock_guard<std::mutex> lk(g_mu);
     g_inited = false;
     g_devices.clear();
+}
+
+// Pinned host memory for callers that want their pixel buffers DMA-able (a Go caller can wrap it with unsafe.Slice and
+// decode into it): uploads from such buffers skip the staging copy that pageable memory needs.
+void *fb_alloc_pinned(size_t bytes) {
+    if (ensure_init() < 0) return nullptr;
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaMallocHost", __FILE__, __LINE__);
+        return nullptr;
+    }
+    return p;
+}
+void fb_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// Idle contexts held by the pool / live Lanczos tables: what tests/test_resources_gpu.py watches.
+int fb_debug_pool_size(void) {
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    int n = 0;
+    for (auto &v : g_pool.idle) n += (int)v.size();
+    return n;
+}
+int fb_debug_table_count(void) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    return (int)g_lanczos.size();
 }
 
 int fb_device_count(void) {
@@ -753,9 +975,10 @@ int fb_box_downsample(const uint8_t *src, int srcStride, int srcW, int srcH, uin
     if (srcW <= 0 || srcH <= 0 || dstW <= 0 || dstH <= 0) return FB_IDENTITY;  // ssim.go:246-248
     FB_TRY(check_img("fb_box_downsample", src, srcStride, srcW, srcH));
     FB_TRY(check_img("fb_box_downsample", dst, dstStride, dstW, dstH));
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
-    FB_TRY(reserve(c, (size_t)dev_pitch(srcW) * srcH + (size_t)dev_pitch(dstW) * dstH + 4096, 256));
+    FB_TRY(reserve(c, c->stream, (size_t)dev_pitch(srcW) * srcH + (size_t)dev_pitch(dstW) * dstH + 4096, 256));
     uint8_t *ds;
     int ps;
     FB_TRY(upload(c, src, srcStride, srcW, srcH, &ds, &ps));
@@ -788,11 +1011,21 @@ static int blur_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, uint8_
     long long timg = (long long)tpitch * h;
     uint8_t *tmp = (uint8_t *)c->ws.take((size_t)timg * n);
     if (!kpin || !fpin || !kdev || !fdev || !tmp) { set_error("internal: workspace under-reserved (blur)"); return FB_E_INVALID; }
-    for (int i = 0; i < taps; i++) { kpin[i] = kernel_host[i]; fpin[i] = (float)kernel_host[i]; }
+    // The FP32 fast path rounds values known to lie in [0, 255] (a convex combination of bytes).  A caller-supplied
+    // table with negative taps or a gain above 1 leaves that range: it takes the exact FP64 kernels only (wabs huge).
+    double wabs = 0.0;
+    bool convex = true;
+    for (int i = 0; i < taps; i++) {
+        kpin[i] = kernel_host[i];
+        fpin[i] = (float)kernel_host[i];
+        wabs += fabs(kernel_host[i]);
+        if (!(kernel_host[i] >= 0.0)) convex = false;
+    }
+    if (!convex || !(wabs <= 1.000001)) wabs = 1e9;
     FB_CUDA(cudaMemcpyAsync(kdev, kpin, sizeof(double) * taps, cudaMemcpyHostToDevice, s));
     FB_CUDA(cudaMemcpyAsync(fdev, fpin, sizeof(float) * taps, cudaMemcpyHostToDevice, s));
     mark_pin_busy(c, s);
-    return launch_gaussian_blur(s, dsrc, ddst, imgStride, rowStride, w, h, n, kdev, fdev, radius, tmp, timg, tpitch);
+    return launch_gaussian_blur(s, dsrc, ddst, imgStride, rowStride, w, h, n, kdev, fdev, radius, wabs, tmp, timg, tpitch);
 }
 
 int fb_gaussian_blur(const uint8_t *src, int srcStride, int w, int h, const double *kernel, int radius,
@@ -801,11 +1034,12 @@ int fb_gaussian_blur(const uint8_t *src, int srcStride, int w, int h, const doub
     FB_TRY(check_img("fb_gaussian_blur", dst, dstStride, w, h));
     if (!kernel || radius < 0) { set_error("fb_gaussian_blur: kernel table missing or radius < 0"); return FB_E_INVALID; }
     if (w == 0 || h == 0) return FB_OK;
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     int taps = 2 * radius + 1;
     size_t img = (size_t)dev_pitch(w) * h + 512;
-    FB_TRY(reserve(c, 3 * img + 16 * (size_t)taps + 4096, 16 * (size_t)taps + 256));
+    FB_TRY(reserve(c, c->stream, 3 * img + 16 * (size_t)taps + 4096, 16 * (size_t)taps + 256));
     uint8_t *ds;
     int ps;
     FB_TRY(upload(c, src, srcStride, w, h, &ds, &ps));
@@ -834,10 +1068,11 @@ static int host_fx(const char *fn, int mode, const uint8_t *src, int srcStride, 
     FB_TRY(check_img(fn, src, srcStride, w, h));
     FB_TRY(check_img(fn, dst, dstStride, w, h));
     if (w == 0 || h == 0) return FB_OK;
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     size_t img = (size_t)dev_pitch(w) * h + 512;
-    FB_TRY(reserve(c, 2 * img + 4096, 256));
+    FB_TRY(reserve(c, c->stream, 2 * img + 4096, 256));
     uint8_t *ds;
     int ps;
     FB_TRY(upload(c, src, srcStride, w, h, &ds, &ps));
@@ -940,6 +1175,7 @@ int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH, uin
     }
     FB_TRY(check_weights("fb_lanczos_resize", wx, dstW, srcW));
     FB_TRY(check_weights("fb_lanczos_resize", wy, dstH, srcH));
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     size_t tabBytes = 0;
@@ -947,7 +1183,7 @@ int fb_lanczos_resize(const uint8_t *src, int srcStride, int srcW, int srcH, uin
     if (wy) tabBytes += 24 * (size_t)(wy->start[dstH] + dstH + 8);
     size_t need = (size_t)dev_pitch(srcW) * srcH + (size_t)dev_pitch(dstW) * srcH + (size_t)dev_pitch(dstW) * dstH +
                   tabBytes + 8192;
-    FB_TRY(reserve(c, need, tabBytes + 4096));
+    FB_TRY(reserve(c, c->stream, need, tabBytes + 4096));
     LanczosTable tx, ty;
     if (wx) FB_TRY(upload_weights(c, c->stream, wx, &tx)); else FB_TRY(lanczos_table_cached(c, dstW, srcW, &tx));
     if (wy) FB_TRY(upload_weights(c, c->stream, wy, &ty)); else FB_TRY(lanczos_table_cached(c, dstH, srcH, &ty));
@@ -998,8 +1234,10 @@ int fb_ssim_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t 
     FB_TRY(check_batch("fb_ssim_batch_dev", b, imgStride, rowStride, w, h, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_ssim_batch_dev", device, &c));
-    FB_TRY(reserve(c, ssim_scratch_bytes(w, h, n) + 1024, 256));
+    scope_.bind(c, (cudaStream_t)stream);
+    FB_TRY(reserve(c, (cudaStream_t)stream, ssim_scratch_bytes(w, h, n) + 1024, 256));
     void *scratch = c->ws.take(ssim_scratch_bytes(w, h, n));
     return launch_ssim(c, (cudaStream_t)stream, a, b, imgStride, imgStride, rowStride, rowStride, w, h, n, scores, 1,
                        scratch);
@@ -1011,8 +1249,10 @@ int fb_ssim_fast_batch_dev(int device, void *stream, const uint8_t *a, const uin
     FB_TRY(check_batch("fb_ssim_fast_batch_dev", b, imgStride, rowStride, w, h, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_ssim_fast_batch_dev", device, &c));
-    FB_TRY(reserve(c, ssim_fast_scratch(w, h, n), 256));
+    scope_.bind(c, (cudaStream_t)stream);
+    FB_TRY(reserve(c, (cudaStream_t)stream, ssim_fast_scratch(w, h, n), 256));
     return pipeline_ssim_fast(c, (cudaStream_t)stream, ImgBatch{a, imgStride, rowStride}, ImgBatch{b, imgStride, rowStride},
                               w, h, n, scores, 1);
 }
@@ -1023,8 +1263,10 @@ int fb_msssim_batch_dev(int device, void *stream, const uint8_t *a, const uint8_
     FB_TRY(check_batch("fb_msssim_batch_dev", b, imgStride, rowStride, w, h, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_msssim_batch_dev", device, &c));
-    FB_TRY(reserve(c, msssim_scratch(w, h, n), 1024));
+    scope_.bind(c, (cudaStream_t)stream);
+    FB_TRY(reserve(c, (cudaStream_t)stream, msssim_scratch(w, h, n), 1024));
     return pipeline_msssim(c, (cudaStream_t)stream, ImgBatch{a, imgStride, rowStride}, ImgBatch{b, imgStride, rowStride},
                            w, h, n, scores);
 }
@@ -1036,7 +1278,9 @@ int fb_box_downsample_batch_dev(int device, void *stream, const uint8_t *src, in
     FB_TRY(check_batch("fb_box_downsample_batch_dev", src, srcImgStride, srcRowStride, srcW, srcH, n));
     FB_TRY(check_batch("fb_box_downsample_batch_dev", dst, dstImgStride, dstRowStride, dstW, dstH, n));
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_box_downsample_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     return launch_box((cudaStream_t)stream, src, srcImgStride, srcRowStride, srcW, srcH, dst, dstImgStride,
                       dstRowStride, dstW, dstH, n, nullptr);
 }
@@ -1055,7 +1299,9 @@ int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a, const 
     FB_TRY(check_batch(fn, halfB, halfImgStride, halfRowStride, w / 2, h / 2, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for(fn, device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = launch_box_fused(s, a, imgStride, rowStride, b, imgStride, rowStride, w, h, thumbA, thumbB, thumbImgStride,
                               thumbRowStride, tw, th, halfA, halfB, halfImgStride, halfRowStride, n);
@@ -1074,9 +1320,11 @@ int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uin
     if (!kernel_host || radius < 0) { set_error("fb_gaussian_blur_batch_dev: kernel table missing"); return FB_E_INVALID; }
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_gaussian_blur_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     int taps = 2 * radius + 1;
-    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h * n + 16 * (size_t)taps + 4096, 16 * (size_t)taps + 256));
+    FB_TRY(reserve(c, (cudaStream_t)stream, (size_t)dev_pitch(w) * h * n + 16 * (size_t)taps + 4096, 16 * (size_t)taps + 256));
     return blur_on_device(c, (cudaStream_t)stream, src, dst, imgStride, rowStride, w, h, n, kernel_host, radius);
 }
 
@@ -1088,7 +1336,9 @@ static int fx_batch(const char *fn, int adaptive, int device, void *stream, cons
     FB_TRY(check_batch(fn, dst, imgStride, rowStride, w, h, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for(fn, device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     double amount = adaptive ? 1.0 + strength * 2.0 : 1.0 + strength * 1.5;
     return launch_sharpen((cudaStream_t)stream, src, dst, imgStride, rowStride, w, h, n, imgStride, rowStride, amount,
                           adaptive);
@@ -1111,7 +1361,9 @@ int fb_lanczos_resize_batch_dev(int device, void *stream, const uint8_t *src, in
     FB_TRY(check_batch("fb_lanczos_resize_batch_dev", dst, dstImgStride, dstRowStride, dstW, dstH, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_lanczos_resize_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     if (srcW == dstW && srcH == dstH) {
         for (int i = 0; i < n; i++)
@@ -1119,7 +1371,7 @@ int fb_lanczos_resize_batch_dev(int device, void *stream, const uint8_t *src, in
                                       srcRowStride, (size_t)srcW * 4, srcH, cudaMemcpyDeviceToDevice, s));
         return FB_OK;
     }
-    FB_TRY(reserve(c, (size_t)dev_pitch(dstW) * srcH * n + 8192, 256));
+    FB_TRY(reserve(c, (cudaStream_t)stream, (size_t)dev_pitch(dstW) * srcH * n + 8192, 256));
     LanczosTable tx, ty;
     FB_TRY(lanczos_table_cached(c, dstW, srcW, &tx));
     FB_TRY(lanczos_table_cached(c, dstH, srcH, &ty));
@@ -1182,9 +1434,9 @@ static int ycbcr_upload_convert(DevCtx *c, const uint8_t *y, int yStride, const 
     *pitch = dev_pitch(w);
     *out = (uint8_t *)c->ws.take((size_t)*pitch * h + 16);
     if (!dy || !dcb || !dcr || !*out) { set_error("internal: workspace under-reserved (ycbcr)"); return FB_E_INVALID; }
-    FB_CUDA(cudaMemcpy2DAsync(dy, yp, y, yStride, (size_t)w, h, cudaMemcpyHostToDevice, c->stream));
-    FB_CUDA(cudaMemcpy2DAsync(dcb, cp, cb, cStride, (size_t)cw, ch, cudaMemcpyHostToDevice, c->stream));
-    FB_CUDA(cudaMemcpy2DAsync(dcr, cp, cr, cStride, (size_t)cw, ch, cudaMemcpyHostToDevice, c->stream));
+    FB_TRY(upload_rows(c, y, (size_t)yStride, dy, (size_t)yp, (size_t)w, h));
+    FB_TRY(upload_rows(c, cb, (size_t)cStride, dcb, (size_t)cp, (size_t)cw, ch));
+    FB_TRY(upload_rows(c, cr, (size_t)cStride, dcr, (size_t)cp, (size_t)cw, ch));
     return launch_ycbcr_to_nrgba(c->stream, dy, 0, yp, dcb, dcr, 0, cp, w, h, ratio, *out, 0, *pitch, 1);
 }
 
@@ -1236,9 +1488,10 @@ int fb_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const ui
     int cw, ch;
     FB_TRY(check_planes("fb_ycbcr_to_nrgba", y, yStride, cb, cr, cStride, w, h, ratio, &cw, &ch));
     FB_TRY(check_img("fb_ycbcr_to_nrgba", dst, dstStride, w, h));
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
-    FB_TRY(reserve(c, ycbcr_scratch(w, h, cw, ch), 256));
+    FB_TRY(reserve(c, c->stream, ycbcr_scratch(w, h, cw, ch), 256));
     uint8_t *d;
     int pitch;
     FB_TRY(ycbcr_upload_convert(c, y, yStride, cb, cr, cStride, w, h, ratio, cw, ch, &d, &pitch));
@@ -1250,13 +1503,14 @@ int fb_ycbcr_to_nrgba(const uint8_t *y, int yStride, const uint8_t *cb, const ui
 int fb_gray_to_nrgba(const uint8_t *g, int gStride, int w, int h, uint8_t *dst, int dstStride) {
     if (w <= 0 || h <= 0 || !g || gStride < w) { set_error("fb_gray_to_nrgba: bad plane"); return FB_E_INVALID; }
     FB_TRY(check_img("fb_gray_to_nrgba", dst, dstStride, w, h));
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     const int gp = (int)align_up((size_t)w, 16), pitch = dev_pitch(w);
-    FB_TRY(reserve(c, (size_t)gp * h + (size_t)pitch * h + 4096, 256));
+    FB_TRY(reserve(c, c->stream, (size_t)gp * h + (size_t)pitch * h + 4096, 256));
     uint8_t *dg = (uint8_t *)c->ws.take((size_t)gp * h);
     uint8_t *d = (uint8_t *)c->ws.take((size_t)pitch * h + 16);
-    FB_CUDA(cudaMemcpy2DAsync(dg, gp, g, gStride, (size_t)w, h, cudaMemcpyHostToDevice, c->stream));
+    FB_TRY(upload_rows(c, g, (size_t)gStride, dg, (size_t)gp, (size_t)w, h));
     FB_TRY(launch_gray_to_nrgba(c->stream, dg, 0, gp, w, h, d, 0, pitch, 1));
     FB_TRY(download(c, d, pitch, dst, dstStride, w, h));
     FB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1284,12 +1538,13 @@ int fb_convert_to_nrgba(int format, const uint8_t *pix, int stride, int w, int h
     FB_TRY(check_pixfmt("fb_convert_to_nrgba", format, pix, stride, w, h, palette16, ncolors));
     FB_TRY(check_img("fb_convert_to_nrgba", dst, dstStride, w, h));
     if (w == 0 || h == 0) return FB_OK;
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     const int bpp = pixfmt_bytes_per_pixel(format);
     const size_t sp = align_up((size_t)w * bpp, 256);
     const int pitch = dev_pitch(w);
-    FB_TRY(reserve(c, sp * h + (size_t)pitch * h + 2048 + 256 + 4096, 2048 + 256));
+    FB_TRY(reserve(c, c->stream, sp * h + (size_t)pitch * h + 2048 + 256 + 4096, 2048 + 256));
     uint8_t *ds = (uint8_t *)c->ws.take(sp * h);
     uint8_t *d = (uint8_t *)c->ws.take((size_t)pitch * h + 16);
     uint16_t *dpal = (uint16_t *)c->ws.take(2048);
@@ -1297,7 +1552,7 @@ int fb_convert_to_nrgba(int format, const uint8_t *pix, int stride, int w, int h
     uint16_t *ppal = (uint16_t *)c->pin.take(2048);
     unsigned int *pbad = (unsigned int *)c->pin.take(16);
     if (!ds || !d || !dpal || !dbad || !ppal || !pbad) { set_error("internal: workspace under-reserved (convert)"); return FB_E_INVALID; }
-    FB_CUDA(cudaMemcpy2DAsync(ds, sp, pix, stride, (size_t)w * bpp, h, cudaMemcpyHostToDevice, c->stream));
+    FB_TRY(upload_rows(c, pix, (size_t)stride, ds, (size_t)sp, (size_t)w * bpp, h));
     if (format == FB_FMT_PALETTED) {
         memset(ppal, 0, 2048);
         memcpy(ppal, palette16, (size_t)ncolors * 8);
@@ -1324,7 +1579,9 @@ int fb_convert_to_nrgba_batch_dev(int device, void *stream, int format, const ui
     FB_TRY(check_batch("fb_convert_to_nrgba_batch_dev", dst, dstImgStride, dstRowStride, w, h, n));
     if (n == 0 || w == 0 || h == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_convert_to_nrgba_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     return launch_pixfmt_to_nrgba((cudaStream_t)stream, format, pix, imgStride, rowStride, w, h, palettes16, ncolors, dst,
                                   dstImgStride, dstRowStride, n, nullptr);
 }
@@ -1337,7 +1594,9 @@ int fb_ycbcr_to_nrgba_batch_dev(int device, void *stream, const uint8_t *y, int6
     FB_TRY(check_batch("fb_ycbcr_to_nrgba_batch_dev", dst, dstImgStride, dstRowStride, w, h, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_ycbcr_to_nrgba_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     return launch_ycbcr_to_nrgba((cudaStream_t)stream, y, yImgStride, yStride, cb, cr, cImgStride, cStride, w, h, ratio, dst,
                                  dstImgStride, dstRowStride, n);
 }
@@ -1347,13 +1606,14 @@ int fb_ssim_ref_create(const uint8_t *src, int stride, int w, int h, fb_ssim_ref
     *out = nullptr;
     FB_TRY(check_img("fb_ssim_ref_create", src, stride, w, h));
     if (w <= 0 || h <= 0) { set_error("fb_ssim_ref_create: empty image"); return FB_E_INVALID; }
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     fb_ssim_ref r;
     r.dev = c->dev; r.w = w; r.h = h; r.tw = w; r.th = h;
     const bool down = ssim_fast_dims(w, h, &r.tw, &r.th) != 0;
     r.pitch = dev_pitch(r.tw);
-    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h + 4096, 256));
+    FB_TRY(reserve(c, c->stream, (size_t)dev_pitch(w) * h + 4096, 256));
     uint8_t *d;
     int pitch;
     FB_TRY(upload(c, src, stride, w, h, &d, &pitch));
@@ -1380,7 +1640,7 @@ int fb_ssim_ref_score_nrgba(const fb_ssim_ref *ref, const uint8_t *img, int stri
     FB_TRY(check_img("fb_ssim_ref_score_nrgba", img, stride, ref->w, ref->h));
     DevCtx *c = ctx(ref->dev);
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
-    FB_TRY(reserve(c, (size_t)dev_pitch(ref->w) * ref->h + ref_score_scratch(ref) + 4096, 256));
+    FB_TRY(reserve(c, c->stream, (size_t)dev_pitch(ref->w) * ref->h + ref_score_scratch(ref) + 4096, 256));
     uint8_t *d;
     int pitch;
     FB_TRY(upload(c, img, stride, ref->w, ref->h, &d, &pitch));
@@ -1394,7 +1654,7 @@ int fb_ssim_ref_score_ycbcr(const fb_ssim_ref *ref, const uint8_t *y, int yStrid
     FB_TRY(check_planes("fb_ssim_ref_score_ycbcr", y, yStride, cb, cr, cStride, ref->w, ref->h, ratio, &cw, &ch));
     DevCtx *c = ctx(ref->dev);
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
-    FB_TRY(reserve(c, ycbcr_scratch(ref->w, ref->h, cw, ch) + ref_score_scratch(ref), 256));
+    FB_TRY(reserve(c, c->stream, ycbcr_scratch(ref->w, ref->h, cw, ch) + ref_score_scratch(ref), 256));
     uint8_t *d;
     int pitch;
     FB_TRY(ycbcr_upload_convert(c, y, yStride, cb, cr, cStride, ref->w, ref->h, ratio, cw, ch, &d, &pitch));
@@ -1481,8 +1741,10 @@ int fb_analyze_batch_dev(int device, void *stream, const uint8_t *imgs, int64_t 
     if (!raw) { set_error("fb_analyze_batch_dev: null output"); return FB_E_INVALID; }
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_analyze_batch_dev", device, &c));
-    FB_TRY(reserve(c, analyze_scratch_bytes(w, h, n), 256));
+    scope_.bind(c, (cudaStream_t)stream);
+    FB_TRY(reserve(c, (cudaStream_t)stream, analyze_scratch_bytes(w, h, n), 256));
     void *scratch = c->ws.take(analyze_scratch_bytes(w, h, n) - 512);
     if (!scratch) { set_error("internal: workspace under-reserved (analyze)"); return FB_E_INVALID; }
     return launch_analyze((cudaStream_t)stream, imgs, imgStride, rowStride, w, h, n, (AnalyzeRaw *)raw, scratch);
@@ -1497,9 +1759,10 @@ int fb_analyze(const uint8_t *pix, int stride, int w, int h, fb_image_stats *out
         out->height = h;
         return FB_OK;
     }
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
-    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h + analyze_scratch_bytes(w, h, 1) + sizeof(AnalyzeRaw) + 4096, sizeof(AnalyzeRaw) + 256));
+    FB_TRY(reserve(c, c->stream, (size_t)dev_pitch(w) * h + analyze_scratch_bytes(w, h, 1) + sizeof(AnalyzeRaw) + 4096, sizeof(AnalyzeRaw) + 256));
     uint8_t *d;
     int pitch;
     FB_TRY(upload(c, pix, stride, w, h, &d, &pitch));
@@ -1533,9 +1796,10 @@ int fb_apply_orientation(const uint8_t *src, int srcStride, int w, int h, int or
     FB_TRY(check_img("fb_apply_orientation", src, srcStride, w, h));
     FB_TRY(check_img("fb_apply_orientation", dst, dstStride, dw, dh));
     if (w == 0 || h == 0) return FB_OK;
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
-    FB_TRY(reserve(c, (size_t)dev_pitch(w) * h + (size_t)dev_pitch(dw) * dh + 4096, 256));
+    FB_TRY(reserve(c, c->stream, (size_t)dev_pitch(w) * h + (size_t)dev_pitch(dw) * dh + 4096, 256));
     uint8_t *d;
     int pitch;
     FB_TRY(upload(c, src, srcStride, w, h, &d, &pitch));
@@ -1556,7 +1820,9 @@ int fb_apply_orientation_batch_dev(int device, void *stream, const uint8_t *src,
     FB_TRY(check_batch("fb_apply_orientation_batch_dev", dst, dstImgStride, dstRowStride, dw, dh, n));
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_apply_orientation_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     return launch_orient((cudaStream_t)stream, src, srcImgStride, srcRowStride, w, h, orient, dst, dstImgStride, dstRowStride, n);
 }
 
@@ -1581,10 +1847,11 @@ int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint
     if (dst) FB_TRY(check_img("fb_apply_palette", dst, dstStride, w, h));
     if (indices && idxStride < w) { set_error("fb_apply_palette: index stride %d < w", idxStride); return FB_E_INVALID; }
     if (w == 0 || h == 0) return FB_OK;
+    ApiScope scope_;
     DevCtx *c = ctx(current_device());
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     const int ipitch = (int)align_up((size_t)w, 16);
-    FB_TRY(reserve(c, 2 * ((size_t)dev_pitch(w) * h + 512) + (size_t)ipitch * h + palette_scratch_bytes(w, h, 1) + 4096, 2048));
+    FB_TRY(reserve(c, c->stream, 2 * ((size_t)dev_pitch(w) * h + 512) + (size_t)ipitch * h + palette_scratch_bytes(w, h, 1) + 4096, 2048));
     uint8_t *d;
     int pitch;
     FB_TRY(upload(c, src, srcStride, w, h, &d, &pitch));
@@ -1599,7 +1866,7 @@ int fb_apply_palette(const uint8_t *src, int srcStride, int w, int h, const uint
     memcpy(ppin, palette, (size_t)ncolors * 4);
     FB_CUDA(cudaMemcpyAsync(dpal, ppin, 1024, cudaMemcpyHostToDevice, c->stream));
     FB_TRY(launch_apply_palette(c->stream, d, 0, pitch, w, h, dpal, ncolors, didx, 0, ipitch, dout, 0, pitch, 1, cells));
-    if (indices) FB_CUDA(cudaMemcpy2DAsync(indices, idxStride, didx, ipitch, (size_t)w, h, cudaMemcpyDeviceToHost, c->stream));
+    if (indices) FB_TRY(download_rows(c, didx, (size_t)ipitch, indices, (size_t)idxStride, (size_t)w, h));
     if (dst) FB_TRY(download(c, dout, pitch, dst, dstStride, w, h));
     FB_CUDA(cudaStreamSynchronize(c->stream));
     return FB_OK;
@@ -1614,16 +1881,125 @@ int fb_apply_palette_batch_dev(int device, void *stream, const uint8_t *src, int
     if (indices && idxRowStride < w) { set_error("fb_apply_palette_batch_dev: index stride %d < w", idxRowStride); return FB_E_INVALID; }
     if (n == 0) return FB_OK;
     DevCtx *c;
+    ApiScope scope_;
     FB_TRY(dev_ctx_for("fb_apply_palette_batch_dev", device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
     const size_t cellBytes = palette_scratch_bytes(w, h, n);
     void *cells = nullptr;
     if (cellBytes) {
-        FB_TRY(reserve(c, cellBytes + 1024, 256));
+        FB_TRY(reserve(c, (cudaStream_t)stream, cellBytes + 1024, 256));
         cells = c->ws.take(cellBytes - 256);
         if (!cells) { set_error("internal: workspace under-reserved (palette cells)"); return FB_E_INVALID; }
     }
     return launch_apply_palette((cudaStream_t)stream, src, imgStride, rowStride, w, h, palettes, ncolors, indices, idxImgStride,
                                 idxRowStride, dst, dstImgStride, dstRowStride, n, cells);
+}
+
+}  // extern "C"
+
+
+// =====================================================================================================
+// Host-buffer batches: the worker pool of CompressBatch (batch.go:58-128) behind ONE call.
+// The item list is split over the initialised devices with fb_batch_shard (static contiguous blocks, input order kept);
+// inside a device's block `workers_per_device` library threads pull item indices from an atomic counter — the
+// reference's buffered channel of indices (batch.go:72-81) — and run the ordinary host entry point for each item on
+// their own stream, so one worker's staging / H2D overlaps another's kernels.  Results land at their input index
+// (batch.go:108-113); one failing item does not stop the rest; a raised cancel flag marks every item not yet started
+// with FB_E_CANCELLED (batch.go:90-98); on_item(completed, total) fires after each item, possibly concurrently
+// (batch.go:115-121).  No collective is involved: per-item work is independent and the outputs go straight to the
+// caller's buffers.
+// =====================================================================================================
+namespace fb {
+
+template <typename F>
+static int run_batch_host(const char *fn, int n, const fb_batch_opts *opts, int *status, F item_fn) {
+    if (n < 0) { set_error("%s: n = %d", fn, n); return FB_E_INVALID; }
+    if (n == 0) return 0;   // batch.go:59-61: nothing to do
+    const int nd = ensure_init();
+    if (nd < 0) return nd;
+    const int wpd = (opts && opts->workers_per_device > 0) ? opts->workers_per_device : 4;
+    const volatile int *cancel = opts ? opts->cancel : nullptr;
+    std::unique_ptr<std::atomic<int>[]> next(new std::atomic<int>[nd]);
+    std::atomic<int> completed{0}, failed{0};
+    std::atomic<long long> launches{0};
+    std::mutex errMu;
+    std::string firstErr;
+    std::vector<std::thread> workers;
+    for (int d = 0; d < nd; d++) {
+        int b = 0, e = 0;
+        fb_batch_shard(n, nd, d, &b, &e);
+        next[d].store(b);
+        const int nw = e - b < wpd ? e - b : wpd;
+        for (int k = 0; k < nw; k++) {
+            workers.emplace_back([&, d, e]() {
+                fb_set_device(d);
+                for (;;) {
+                    const int i = next[d].fetch_add(1);
+                    if (i >= e) break;
+                    int rc;
+                    if (cancel && *cancel) {
+                        rc = FB_E_CANCELLED;
+                    } else {
+                        rc = item_fn(i);
+                        if (rc < 0) {
+                            std::lock_guard<std::mutex> lk(errMu);
+                            if (firstErr.empty()) firstErr = std::string("item ") + std::to_string(i) + ": " + fb_last_error();
+                        }
+                    }
+                    if (status) status[i] = rc;
+                    if (rc < 0) failed.fetch_add(1);
+                    const int c = completed.fetch_add(1) + 1;
+                    if (opts && opts->on_item) opts->on_item(c, n, opts->user);
+                }
+                launches.fetch_add(t_launches);   // the workers' kernel launches count for the calling thread
+            });
+        }
+    }
+    for (auto &t : workers) t.join();
+    t_launches += launches.load();
+    if (!firstErr.empty()) set_error("%s: %s", fn, firstErr.c_str());
+    return failed.load();
+}
+
+}  // namespace fb
+
+extern "C" {
+
+int fb_score_batch_host(int op, const fb_pair *pairs, int n, double *scores, int *status, const fb_batch_opts *opts) {
+    if (op != FB_OP_SSIM && op != FB_OP_SSIM_FAST && op != FB_OP_MSSSIM) { set_error("fb_score_batch_host: unknown op %d", op); return FB_E_INVALID; }
+    if (n > 0 && (!pairs || !scores)) { set_error("fb_score_batch_host: null pairs / scores"); return FB_E_INVALID; }
+    return run_batch_host("fb_score_batch_host", n, opts, status, [&](int i) {
+        const fb_pair &p = pairs[i];
+        switch (op) {
+            case FB_OP_SSIM: return fb_ssim(p.a, p.strideA, p.b, p.strideB, p.w, p.h, &scores[i]);
+            case FB_OP_SSIM_FAST: return fb_ssim_fast(p.a, p.strideA, p.b, p.strideB, p.w, p.h, &scores[i]);
+            default: return fb_msssim(p.a, p.strideA, p.b, p.strideB, p.w, p.h, &scores[i]);
+        }
+    });
+}
+
+int fb_lanczos_resize_batch_host(const fb_resize_item *items, int n, int *status, const fb_batch_opts *opts) {
+    if (n > 0 && !items) { set_error("fb_lanczos_resize_batch_host: null items"); return FB_E_INVALID; }
+    return run_batch_host("fb_lanczos_resize_batch_host", n, opts, status, [&](int i) {
+        const fb_resize_item &t = items[i];
+        return fb_lanczos_resize(t.src, t.srcStride, t.srcW, t.srcH, t.dst, t.dstStride, t.dstW, t.dstH, nullptr, nullptr);
+    });
+}
+
+int fb_effect_batch_host(int effect, double param, const fb_effect_item *items, int n, int *status, const fb_batch_opts *opts) {
+    if (effect != FB_FX_GAUSSIAN_BLUR && effect != FB_FX_SHARPEN && effect != FB_FX_ADAPTIVE_SHARPEN) {
+        set_error("fb_effect_batch_host: unknown effect %d", effect);
+        return FB_E_INVALID;
+    }
+    if (n > 0 && !items) { set_error("fb_effect_batch_host: null items"); return FB_E_INVALID; }
+    return run_batch_host("fb_effect_batch_host", n, opts, status, [&](int i) {
+        const fb_effect_item &t = items[i];
+        switch (effect) {
+            case FB_FX_GAUSSIAN_BLUR: return fb_gaussian_blur_sigma(t.src, t.srcStride, t.w, t.h, param, t.dst, t.dstStride);
+            case FB_FX_SHARPEN: return fb_sharpen(t.src, t.srcStride, t.w, t.h, param, t.dst, t.dstStride);
+            default: return fb_adaptive_sharpen(t.src, t.srcStride, t.w, t.h, param, t.dst, t.dstStride);
+        }
+    });
 }
 
 }  // extern "C"

@@ -52,7 +52,18 @@ struct DevCtx {
     cudaStream_t stream = nullptr;  // owned stream used by the host entry points
     Arena ws;                        // device scratch (grow-only)
     Arena pin;                       // pinned host scratch (scores, small tables)
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr;        // last async H2D out of the pinned arena
+    bool pinBusy = false;
+    // Ordering of the device arena between streams: the last stream that was handed arena memory and an event
+    // recorded behind its work (api.cu: ApiScope / reserve).
+    cudaEvent_t useEv = nullptr;
+    cudaStream_t lastStream = nullptr;
+    bool usePending = false;
+    // Staging for pageable caller buffers (api.cu: upload / download): two pinned chunks and their events.
+    char *stage = nullptr;
+    cudaEvent_t stageEv[2] = {nullptr, nullptr};
+    bool stageBusy[2] = {false, false};
+    unsigned stageNext = 0;
 };
 
 int ensure_init();
@@ -61,7 +72,7 @@ int current_device();  // thread's device for host entry points
 // Context of this thread for `dev`; creates stream/events on first use. nullptr on failure.
 DevCtx *ctx(int dev);
 // Make sure the arenas can hold the given bytes (may synchronise + reallocate).
-int reserve(DevCtx *c, size_t dev_bytes, size_t pinned_bytes);
+int reserve(DevCtx *c, cudaStream_t s, size_t dev_bytes, size_t pinned_bytes);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Row pitch the library uses for its own device copies: 16-byte aligned rows enable 128-bit loads.
@@ -99,7 +110,7 @@ int launch_box_fused(cudaStream_t s, const uint8_t *srcA, long long srcImgStride
 // effects.cu
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
                          int rowStride, int w, int h, int n, const double *kernel_dev,
-                         const float *kernel32_dev, int radius, uint8_t *tmp, long long tmpImgStride,
+                         const float *kernel32_dev, int radius, double wabs, uint8_t *tmp, long long tmpImgStride,
                          int tmpRowStride);
 int launch_blur3x3(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride, int rowStride,
                    int w, int h, int n, long long dstImgStride, int dstRowStride);

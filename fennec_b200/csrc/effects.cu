@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(128) adaptive_tile_kernel(const FxTileParams p
 
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
                          int rowStride, int w, int h, int n, const double *kernel_dev,
-                         const float *kernel32_dev, int radius, uint8_t *tmp, long long tmpImgStride,
+                         const float *kernel32_dev, int radius, double wabs, uint8_t *tmp, long long tmpImgStride,
                          int tmpRowStride) {
     if (n <= 0 || w <= 0 || h <= 0) return FB_OK;
     BlurParams p;
@@ -999,8 +999,11 @@ int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long 
     p.kernel = kernel_dev; p.kernel32 = kernel32_dev;
     // FP32 error bound of the tap sum: each of the `taps` FMAs rounds a partial sum <= 255 (<= 255*2^-24 each)
     // and the FP32 weights differ from the FP64 ones by <= 2^-24 relative (<= 255*2^-24 in total); 25 % margin.
-    p.eps = (float)((2 * radius + 2) * 255.0 * 5.9604644775390625e-08 * 1.25);
-    p.exactOnly = (p.eps >= 0.25f) ? 1 : 0;  // absurdly long kernels: no useful fast path
+    // The bound assumes partial sums <= 255 (a convex combination); a caller-supplied kernel that is not normalised or
+    // has negative taps reaches 255 * sum|w| instead, so the bound scales with max(1, sum|w|) (NaN/inf: exact path only).
+    const double scale = (wabs == wabs && wabs < 1e6) ? (wabs > 1.0 ? wabs : 1.0) : 1e6;
+    p.eps = (float)((2 * radius + 2) * 255.0 * 5.9604644775390625e-08 * 1.25 * scale);
+    p.exactOnly = (p.eps >= 0.25f) ? 1 : 0;  // absurdly long (or huge-gain) kernels: no useful fast path
     dim3 grid((w + 255) / 256, h, n);
     // horizontal: src → tmp
     p.src = src; p.srcImgStride = imgStride; p.srcRowStride = rowStride;

@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace fb {
@@ -605,6 +606,116 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
     return dsum;
 }
 
+// Four rows per iteration: two slot cases, a quarter of the branches per row.  V rows go to shared memory as soon as they
+// are produced (own values are read back with the neighbours: 11 instead of 7 LDS.128 per lane and row), so the register
+// peak stays that of one row; the NR buffers are single-buffered behind a second __syncwarp.
+// NR = 2 with OWN-from-shared is the register-lean twin of walk_strip2.
+template <int NR>
+__device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
+    constexpr int CPL = 4;
+    static_assert(NR == 2 || NR == 4, "slots of one iteration must not wrap inside a case");
+    const uint8_t *pa = q.pa, *pb = q.pb;
+    const int nIn = q.nIn, lane = q.lane;
+    const float2 s2 = make_float2(kLumaScale, kLumaScale);
+    const float2 K2 = make_float2(q.K, q.K);
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
+    HConsts hk;
+    hk.c = q.c;
+    hk.kTh = fmaf(q.c, q.c, 0.5f * kC1f);
+    hk.qpInit = make_float2(kC2f, 0.5f * kC2f);
+    hk.one_two = make_float2(1.f, 2.f);
+    hk.neg2 = make_float2(-1.f, -1.f);
+    float2 rab[8][CPL], rqp[8][CPL];
+    constexpr uint32_t kRowBuf = 32 * CPL * 4;
+    const uint32_t myRing = smem_u32(q.ring) + lane * 16;
+    const uint8_t *myRingP = q.ring + lane * 16;
+#pragma unroll
+    for (int row = 0; row < kStages; row++) {
+        cp_async<16>(myRing + (2 * row) * kRowBuf, pa);
+        cp_async<16>(myRing + (2 * row + 1) * kRowBuf, pb);
+        cp_async_commit();
+        pa += q.rowStrideA;
+        pb += q.rowStrideB;
+    }
+#define WN_PLANES(S, R)                                                                         \
+    {                                                                                           \
+        cp_async_wait<kStages - 1>();                                                           \
+        const uint8_t *rb_ = myRingP + (2 * ((S) & (kStages - 1))) * kRowBuf;                   \
+        const uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                                \
+        const uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + kRowBuf);                      \
+        const uint32_t xa_[4] = {va_.x, va_.y, va_.z, va_.w}, xb_[4] = {vb_.x, vb_.y, vb_.z, vb_.w}; \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
+            float2 t = __ffma2_rn(f, s2, K2);                                                   \
+            float2 sq = __fmul2_rn(t, t);                                                       \
+            rab[(S) & 7][i] = t;                                                                \
+            rqp[(S) & 7][i] = make_float2(sq.x + sq.y, t.x * t.y);                              \
+        }                                                                                       \
+        if ((R) + kStages < nIn) {                                                              \
+            cp_async<16>(myRing + (2 * ((S) & (kStages - 1))) * kRowBuf, pa);                   \
+            cp_async<16>(myRing + (2 * ((S) & (kStages - 1)) + 1) * kRowBuf, pb);               \
+            pa += q.rowStrideA;                                                                 \
+            pb += q.rowStrideB;                                                                 \
+        }                                                                                       \
+        cp_async_commit();                                                                      \
+    }
+    // vertical taps of the row in slot S, stored straight to V buffer J
+#define WN_VTAPS_STS(S, J)                                                                      \
+    _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                           \
+        float2 vab = __fmul2_rn(rab[((S) + 1) & 7][i], g2[0]);                                  \
+        float2 vqp = __fmul2_rn(rqp[((S) + 1) & 7][i], g2[0]);                                  \
+        _Pragma("unroll") for (int j = 1; j < 8; j++) {                                         \
+            vab = __ffma2_rn(rab[((S) + 1 + j) & 7][i], g2[j], vab);                            \
+            vqp = __ffma2_rn(rqp[((S) + 1 + j) & 7][i], g2[j], vqp);                            \
+        }                                                                                       \
+        vb0[(J) * kVBuf + i * kVLanes] = make_float4(vab.x, vab.y, vqp.x, vqp.y);               \
+    }
+#pragma unroll
+    for (int r = 0; r < 7; r++) WN_PLANES(r, r)
+
+    float fs[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) fs[i] = 0.f;
+    constexpr int kVLanes = 36, kVBuf = CPL * kVLanes;
+    float4 *vb0 = q.vb0 + lane;
+
+#pragma unroll 1
+    for (int r = 7; r < nIn; r += NR) {
+        __syncwarp();   // every lane has finished reading the previous iteration's V rows
+#define WN_ROW(S, J) WN_PLANES((S) + (J), r + (J)) WN_VTAPS_STS((S) + (J), J)
+        if (NR == 4) {
+            if ((r & 7) == 7) { WN_ROW(7, 0) WN_ROW(7, 1) WN_ROW(7, 2) WN_ROW(7, 3) }
+            else              { WN_ROW(3, 0) WN_ROW(3, 1) WN_ROW(3, 2) WN_ROW(3, 3) }
+        } else {
+            switch (r & 7) {
+                case 7: { WN_ROW(7, 0) WN_ROW(7, 1) } break;
+                case 1: { WN_ROW(1, 0) WN_ROW(1, 1) } break;
+                case 3: { WN_ROW(3, 0) WN_ROW(3, 1) } break;
+                default: { WN_ROW(5, 0) WN_ROW(5, 1) } break;
+            }
+        }
+#undef WN_ROW
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+            const bool rowOK = r + j < nIn;
+            bool ok[CPL];
+            float4 own[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; i++) { ok[i] = q.valid[i] && rowOK; own[i] = vb0[j * kVBuf + i * kVLanes]; }
+            hpass_formula(own, vb0 + j * kVBuf, g2, hk, ok, fs);
+        }
+    }
+#undef WN_PLANES
+#undef WN_VTAPS_STS
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    return dsum;
+}
+
 // Defaults from the round-2 sweep on 64 4K pairs (profiles/r2_k1_variants.txt): walk_strip / 4 warps per block 2.062 ms,
 // walk_strip / 1 warp 1.882, walk_strip2 / 2 warps 1.956, walk_strip2 / 1 warp 1.769, walk_strip_pipe 2.272.
 #ifndef FB_SSIM_MODE_DEFAULT
@@ -614,7 +725,7 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
 #define FB_SSIM_WPB_DEFAULT 1
 #endif
 
-// MODE 0: walk_strip, 1: walk_strip_pipe, 2: walk_strip2.  WPB = warps (independent strips) per block: warps never
+// MODE 0: walk_strip, 1: walk_strip_pipe, 2: walk_strip2, 3: walk_stripN<4>, 4: walk_stripN<2>.  WPB = warps (independent strips) per block: warps never
 // synchronise with each other, so the block size only sets the granularity at which the SM's registers are handed out:
 // 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at ~200 registers without a cap below 8 blocks:
 // 9-10 warps per SM, a third warp on one or two schedulers).
@@ -625,7 +736,7 @@ template <int CPL, int MODE = 0, int WPB = 4>
 __global__ void __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>())) ssim_strip_kernel(const SsimParams p) {
     constexpr int WARPS = WPB;
     constexpr bool PIPE = MODE == 1;
-    constexpr int NVB = MODE == 2 ? 4 : 2;
+    constexpr int NVB = (MODE == 2 || MODE == 3) ? 4 : 2;   // MODE 4 (two rows, single-buffered) needs 2
     constexpr int INC = 32 * CPL;    // input columns per strip
     constexpr int OUTC = INC - 8;    // outputs per strip (multiple of 4 → 16-byte aligned strips)
     __shared__ float4 vbuf[WARPS][NVB][CPL * 36];   // padded V rows, see walk_strip
@@ -686,11 +797,16 @@ __global__ void __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>())) ssim_
     double dsum;
     if (PIPE && CPL == 4) dsum = fast ? walk_strip_pipe(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
     else if (MODE == 2 && CPL == 4) dsum = fast ? walk_strip2(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
+    else if (MODE == 3 && CPL == 4) dsum = fast ? walk_stripN<4>(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
+    else if (MODE == 4 && CPL == 4) dsum = fast ? walk_stripN<2>(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
     else dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
     if (lane == 0) p.partials[seg] = dsum * 4.0;
 }
+
+// (An explicit register cap was measured with __maxnreg__: 184 registers (11 warps per SM) and 168 (12) both spill and
+// lose 7-15 % against the uncapped one-warp blocks; profiles/r2_k1_variants.txt.)
 
 // ------------------------------------------------------------------------------------------------
 // Warp-specialised variant (aligned inputs only).  The monolithic kernel above is register-limited to
@@ -1040,6 +1156,27 @@ size_t ssim_scratch_bytes(int w, int h, int n) {
     return align_up(sizeof(double) * (size_t)n * g.nsx * g.nsy, 256);
 }
 
+// The strip kernels read pixels with cp.async.cg / ld.global.nc.L1::no_allocate: L1 has nothing to cache, so the whole
+// L1/shared array goes to shared memory (one-warp blocks need 10 x 13 KB; the driver's default carve-out heuristic is
+// free to pick less).  FB_SSIM_DEBUG=1 prints the resident blocks per SM once.
+template <typename K>
+static void prepare_kernel(K kernel, int threads, const char *name) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static const bool dbg = getenv("FB_SSIM_DEBUG") != nullptr;
+    if (dbg) {
+        int nb = 0;
+        cudaFuncAttributes fa;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0);
+        cudaFuncGetAttributes(&fa, kernel);
+        fprintf(stderr, "[fb] %s: %d regs, %zu B static smem, %d blocks (%d warps) per SM\n", name, fa.numRegs, fa.sharedSizeBytes, nb, nb * threads / 32);
+    }
+}
+#define FB_PREPARE(kernel, threads)                                          \
+    do {                                                                     \
+        static bool done_ = false;                                           \
+        if (!done_) { prepare_kernel(kernel, threads, #kernel); done_ = true; } \
+    } while (0)
+
 // Scores for n equal-sized pairs.  Dispatch of ssim.go:35-42: w<8||h<8 → pixelSSIM, else windowed.
 int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, long long imgStrideA,
                 long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h, int n,
@@ -1087,15 +1224,22 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
             const char *e = getenv("FB_SSIM_PIPE");
             if (e && e[0] == '1') return 1;
             const char *m = getenv("FB_SSIM_MODE");
-            return (m && m[0] >= '0' && m[0] <= '2') ? m[0] - '0' : FB_SSIM_MODE_DEFAULT;
+            return (m && m[0] >= '0' && m[0] <= '4') ? m[0] - '0' : FB_SSIM_MODE_DEFAULT;
         }();
         static const int wpb = [] { const char *e = getenv("FB_SSIM_WPB"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : FB_SSIM_WPB_DEFAULT; }();
-        const unsigned nb = (unsigned)((segs + wpb - 1) / wpb);
-        if (mode == 1) ssim_strip_kernel<4, 1, 4><<<(unsigned)blocks, 128, 0, s>>>(p);
-        else if (mode == 2 && wpb == 1) ssim_strip_kernel<4, 2, 1><<<nb, 32, 0, s>>>(p);
-        else if (mode == 2) ssim_strip_kernel<4, 2, 2><<<(unsigned)((segs + 1) / 2), 64, 0, s>>>(p);   // 4 V buffers: 2 warps stay under 48 KB static
-        else if (wpb == 1) ssim_strip_kernel<4, 0, 1><<<nb, 32, 0, s>>>(p);
-        else ssim_strip_kernel<4, 0, 4><<<nb, 128, 0, s>>>(p);
+#define FB_LAUNCH_STRIP(MODE_, WPB_)                                                           \
+    do {                                                                                          \
+        FB_PREPARE((ssim_strip_kernel<4, MODE_, WPB_>), 32 * WPB_);                                \
+        ssim_strip_kernel<4, MODE_, WPB_><<<(unsigned)((segs + WPB_ - 1) / WPB_), 32 * WPB_, 0, s>>>(p); \
+    } while (0)
+        if (mode == 1) FB_LAUNCH_STRIP(1, 4);
+        else if (mode == 3) FB_LAUNCH_STRIP(3, 1);
+        else if (mode == 4) FB_LAUNCH_STRIP(4, 1);
+        else if (mode == 2 && wpb == 1) FB_LAUNCH_STRIP(2, 1);
+        else if (mode == 2) FB_LAUNCH_STRIP(2, 2);   // 4 V buffers: 2 warps stay under 48 KB static
+        else if (wpb == 1) FB_LAUNCH_STRIP(0, 1);
+        else FB_LAUNCH_STRIP(0, 4);
+#undef FB_LAUNCH_STRIP
     }
     else ssim_strip_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(p);
     FB_CUDA(cudaGetLastError());

@@ -48,6 +48,7 @@ extern "C" {
 #define FB_E_NOGPU (-2)
 #define FB_E_CUDA (-3)
 #define FB_E_OOM (-4)
+#define FB_E_CANCELLED (-5) /* batch item not started: the caller's cancel flag was raised (batch.go:90-98) */
 
 /* ---- lifecycle --------------------------------------------------------------------------- */
 
@@ -262,6 +263,62 @@ FB_API size_t fb_workspace_bytes(const char *op, int w, int h, int dstW, int dst
  * [begin, end). Keeps input order, so results[idx] semantics (batch.go:71,108) hold after a
  * concatenating gather. */
 FB_API int fb_batch_shard(int n_items, int n_shards, int shard, int *begin, int *end);
+
+/* ---- host-buffer batches: CompressBatch's worker pool behind one call (batch.go:58-128) ---- */
+
+/* One call shards `n` items over every initialised device (fb_batch_shard: contiguous blocks, input order kept) and
+ * runs them on the library's own worker threads (workers_per_device per GPU, default 4; they pull indices from a
+ * shared counter like the reference's channel of indices, batch.go:72-81).  Results are written at their input
+ * index (batch.go:108-113).  status[i] (optional) receives the item's return code; a failing item does not stop
+ * the others (batch.go:107-113); if *cancel becomes non-zero, items not yet started get FB_E_CANCELLED
+ * (batch.go:90-98); on_item(completed, total, user) fires after every item and may run concurrently on several
+ * worker threads (batch.go:115-121).  Returns the number of failed / cancelled items (0 = all good) or a negative
+ * error for bad arguments.  This is what a cgo CompressBatch binds when it wants all GPUs of the box from ONE
+ * process; the multi-process form (one rank per GPU) uses fb_batch_shard + an all-gather instead. */
+typedef void (*fb_progress_fn)(int completed, int total, void *user);
+typedef struct fb_batch_opts {
+    int workers_per_device;       /* <= 0: 4 */
+    const volatile int *cancel;   /* optional cancellation flag (ctx.Done) */
+    fb_progress_fn on_item;       /* optional progress callback (BatchOptions.OnItem, batch.go:40) */
+    void *user;
+} fb_batch_opts;
+
+typedef struct fb_pair {          /* two NRGBA images of equal dims */
+    const uint8_t *a; int strideA;
+    const uint8_t *b; int strideB;
+    int w, h;
+} fb_pair;
+#define FB_OP_SSIM 0      /* fennec.SSIM (ssim.go:24) per pair */
+#define FB_OP_SSIM_FAST 1 /* fennec.SSIMFast (ssim.go:48) */
+#define FB_OP_MSSSIM 2    /* fennec.MSSSIM (ssim.go:313) */
+FB_API int fb_score_batch_host(int op, const fb_pair *pairs, int n, double *scores, int *status, const fb_batch_opts *opts);
+
+typedef struct fb_resize_item {   /* lanczosResize (resize.go:37) of one image; dst allocated by the caller */
+    const uint8_t *src; int srcStride, srcW, srcH;
+    uint8_t *dst; int dstStride, dstW, dstH;
+} fb_resize_item;
+FB_API int fb_lanczos_resize_batch_host(const fb_resize_item *items, int n, int *status, const fb_batch_opts *opts);
+
+typedef struct fb_effect_item {   /* src -> dst, same dims */
+    const uint8_t *src; int srcStride;
+    uint8_t *dst; int dstStride;
+    int w, h;
+} fb_effect_item;
+#define FB_FX_GAUSSIAN_BLUR 0     /* param = sigma  (effects.go:146) */
+#define FB_FX_SHARPEN 1           /* param = strength (effects.go:10) */
+#define FB_FX_ADAPTIVE_SHARPEN 2  /* param = strength (effects.go:49) */
+/* status[i] may be FB_IDENTITY: the reference returns its input (dst not written). */
+FB_API int fb_effect_batch_host(int effect, double param, const fb_effect_item *items, int n, int *status, const fb_batch_opts *opts);
+
+/* Pinned (page-locked) host memory: uploads from it are DMA'ed directly; uploads from ordinary pageable memory
+ * (a Go Pix slice) are staged through the library's own pinned chunks instead.  A Go caller can wrap the pointer
+ * with unsafe.Slice and decode into it. */
+FB_API void *fb_alloc_pinned(size_t bytes);
+FB_API void fb_free_pinned(void *p);
+
+/* Diagnostics: idle per-thread contexts (stream + arenas) parked in the pool, and cached Lanczos table pairs. */
+FB_API int fb_debug_pool_size(void);
+FB_API int fb_debug_table_count(void);
 
 /* Kernel launches issued by this thread since the last call (bench.py's gpu_launches). */
 FB_API long long fb_take_launch_count(void);

@@ -356,3 +356,75 @@ def test_lanczos_all_outputs_take_the_exact_queue(lib, oracle):
     assert np.array_equal(api.lanczos_resize(src, 512, 24), oracle.lanczos_resize(src, 512, 24))
     src[..., 3] = (np.arange(2048) % 3).astype(np.uint8)[None, :]   # alpha 0 / 1 / 2: the a > 0.5 gate itself is in play
     assert np.array_equal(api.lanczos_resize(src, 512, 24), oracle.lanczos_resize(src, 512, 24))
+
+
+# ---- BASELINE.json configs at their OWN size against the oracle ("three configs are not oracle-compared
+# at their own size").  The oracle needs seconds per case; inputs are generated on the host with fixed seeds. ----
+
+@pytest.mark.timeout(300)
+def test_config3_4k_blur_then_sharpen_vs_oracle(lib, oracle):
+    # config 3: GaussianBlur(sigma 2.0) then Sharpen(0.5) on 3840x2160, random alpha — every byte equal
+    x = S.noise_image(3840, 2160, 31, alpha="random")
+    want_blur = oracle.gaussian_blur(x, 2.0)
+    want = oracle.sharpen(want_blur, 0.5)
+    dx = torch.from_numpy(x[None]).cuda()
+    got_blur = batch.gaussian_blur_batch(dx, 2.0)
+    got = batch.sharpen_batch(got_blur, 0.5)
+    assert np.array_equal(got_blur[0].cpu().numpy(), want_blur)
+    assert np.array_equal(got[0].cpu().numpy(), want)
+    # the host-buffer entry points give the same bytes
+    assert np.array_equal(api.Sharpen(api.GaussianBlur(x, 2.0), 0.5), want)
+
+
+@pytest.mark.timeout(300)
+def test_config2_ssimfast_4032x3024_vs_oracle(lib, oracle):
+    # config 2's kernel work: SSIMFast on a 4032x3024 pair (box to 512x384, then the window)
+    a = S.gradient_noise_image(4032, 3024, 41)
+    b = S.perturb(a, 42, 6)
+    want = oracle.ssim_fast(a, b)
+    assert abs(api.SSIMFast(a, b) - want) <= SCORE_TIGHT
+    da, db = torch.from_numpy(a[None]).cuda(), torch.from_numpy(b[None]).cuda()
+    assert abs(batch.ssim_fast_batch(da, db).item() - want) <= SCORE_TIGHT
+    # the thumbnail itself is bit-exact
+    assert np.array_equal(batch.box_downsample_batch(da, 512, 384)[0].cpu().numpy(), oracle.box_downsample(a, 512, 384))
+
+
+@pytest.mark.timeout(600)
+def test_config5_msssim_7680x4320_vs_oracle(lib, oracle):
+    # config 5: the exact level plan of an 8K pair — box ratios 15 / 7.5 / 3.75 / 1.875 to 512x288, the 2x cascade,
+    # a batched thumbnail launch — against the oracle's MSSSIM on the same pair
+    a = S.gradient_noise_image(7680, 4320, 51)
+    b = S.perturb(a, 52, 8)
+    want = oracle.msssim(a, b)
+    da, db = torch.from_numpy(a[None]).cuda(), torch.from_numpy(b[None]).cuda()
+    got = batch.msssim_batch(da, db).item()
+    assert abs(got - want) <= SCORE_TOL, (got, want)
+    assert abs(got - want) <= SCORE_TIGHT, (got, want)
+    got3 = batch.msssim_batch(torch.cat([da, db, da]), torch.cat([db, da, da])).cpu().numpy()   # batch of 3: same plan, n > 1
+    assert abs(got3[0] - want) <= SCORE_TIGHT and abs(got3[1] - oracle.msssim(b, a)) <= SCORE_TIGHT and abs(got3[2] - 1.0) <= 1e-6
+    assert abs(api.MSSSIM(a, b) - want) <= SCORE_TIGHT
+
+
+@pytest.mark.timeout(300)
+def test_config4_lanczos_8k_full_image_vs_oracle(lib, oracle):
+    # config 4: one full 7680x4320 -> 1920x1080 image, translucent (premultiplied sums, a <= 0.5 -> 0), every byte
+    x = S.noise_image(7680, 4320, 61, alpha="random")
+    want = oracle.lanczos_resize(x, 1920, 1080)
+    got = batch.lanczos_resize_batch(torch.from_numpy(x[None]).cuda(), 1920, 1080)[0].cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_blur_sharpen_on_row_padded_batch_keeps_strides(lib, oracle):
+    # the blur / sharpen _dev entries apply src's strides to dst; a padded (non-dense) src must get a dst of
+    # the SAME strides, and a mismatching caller-supplied `out` must be refused instead of being overrun.
+    n, h, w, pad = 2, 70, 90, 6
+    full = _device_noise(n, h, w + pad, 71, alpha255=False)
+    src = full[:, :, :w, :]                       # row stride (w+pad)*4, not dense
+    dense = src.contiguous()
+    for fn, arg in ((batch.gaussian_blur_batch, 2.0), (batch.sharpen_batch, 0.5), (batch.adaptive_sharpen_batch, 0.7)):
+        got = fn(src, arg)
+        assert got.stride() == src.stride()
+        assert torch.equal(got, fn(dense, arg))
+        with pytest.raises(ValueError):
+            fn(src, arg, out=torch.empty_like(dense))
+    assert np.array_equal(batch.gaussian_blur_batch(src, 2.0)[1].cpu().numpy(), oracle.gaussian_blur(dense[1].cpu().numpy(), 2.0))
