@@ -127,6 +127,9 @@ PROTOTYPES = {
     "fb_workspace_bytes": (C.c_size_t, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fb_batch_shard": (C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
     "fb_take_launch_count": (C.c_longlong, []),
+    "fb_msssim_level2_batch_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "fb_score_batch_host": (C.c_int, [C.c_int, C.POINTER(FbPair), C.c_int, dp, ip, C.POINTER(FbBatchOpts)]),
     "fb_lanczos_resize_batch_host": (C.c_int, [C.POINTER(FbResizeItem), C.c_int, ip, C.POINTER(FbBatchOpts)]),
     "fb_effect_batch_host": (C.c_int, [C.c_int, C.c_double, C.POINTER(FbEffectItem), C.c_int, ip, C.POINTER(FbBatchOpts)]),

@@ -83,6 +83,23 @@ def msssim_level_batch(a: torch.Tensor, b: torch.Tensor, tw: int, th: int):
     return thumbs[0], thumbs[1], halves[0], halves[1]
 
 
+def msssim_level2_batch(a: torch.Tensor, b: torch.Tensor, tw: int, th: int):
+    """Two MS-SSIM level steps from one read: (thumb0A, thumb0B, thumb1A, thumb1B, quarterA, quarterB), or None when the
+    geometry has no common box period (fb_msssim_level2_batch_dev answers 1)."""
+    pa, i_s, rs, w, h, n = _batch(a)
+    pb = _batch(b)[0]
+    thumbs = [torch.zeros((n, th, tw, 4), dtype=torch.uint8, device=a.device) for _ in range(4)]
+    quarters = [torch.zeros((n, h // 4, w // 4, 4), dtype=torch.uint8, device=a.device) for _ in range(2)]
+    _, ti, tr, _, _, _ = _batch(thumbs[0])
+    _, qi, qr, _, _, _ = _batch(quarters[0])
+    rc = check(_lib.load().fb_msssim_level2_batch_dev(_dev(a), _stream(a), pa, pb, i_s, rs, w, h, n, thumbs[0].data_ptr(),
+                                                      thumbs[1].data_ptr(), thumbs[2].data_ptr(), thumbs[3].data_ptr(), ti, tr, tw, th,
+                                                      quarters[0].data_ptr(), quarters[1].data_ptr(), qi, qr))
+    if rc == 1:
+        return None
+    return thumbs[0], thumbs[1], thumbs[2], thumbs[3], quarters[0], quarters[1]
+
+
 def ycbcr_to_nrgba_batch(y: torch.Tensor, cb: torch.Tensor, cr: torch.Tensor, ratio: int,
                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """convertToNRGBA (convert.go:34-64) for n device-resident YCbCr images: y (n,h,w), cb/cr (n,ch,cw), uint8."""

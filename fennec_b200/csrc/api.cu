@@ -626,33 +626,59 @@ static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, in
         return rc;
     };
     ImgBatch ca = a, cb = b;
+    auto open_run = [&](int l, int tw, int th) -> int {   // room for the thumbnails of the levels the run can cover
+        const int cap = msssim_run_capacity(plan, l);
+        run.l0 = l; run.tw = tw; run.th = th; run.tpitch = dev_pitch(tw);
+        run.tBytes = (long long)run.tpitch * th;
+        run.ta = (uint8_t *)c->ws.take((size_t)run.tBytes * n * cap);
+        run.tb = (uint8_t *)c->ws.take((size_t)run.tBytes * n * cap);
+        if (!run.ta || !run.tb) { set_error("internal: workspace under-reserved (msssim thumbs)"); return FB_E_INVALID; }
+        return FB_OK;
+    };
+    auto level_images = [&](int l, ImgBatch *ia, ImgBatch *ib) -> int {
+        int pitch = dev_pitch(plan[l].w);
+        long long imgBytes = (long long)pitch * plan[l].h;
+        uint8_t *pa = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+        uint8_t *pb = (uint8_t *)c->ws.take((size_t)imgBytes * n);
+        if (!pa || !pb) { set_error("internal: workspace under-reserved (msssim level)"); return FB_E_INVALID; }
+        *ia = ImgBatch{pa, imgBytes, pitch};
+        *ib = ImgBatch{pb, imgBytes, pitch};
+        return FB_OK;
+    };
     for (int l = 0; l < L; l++) {
         const int lw = plan[l].w, lh = plan[l].h;
-        ImgBatch na{nullptr, 0, 0}, nb{nullptr, 0, 0};
-        if (l + 1 < L) {  // 2x box cascade (ssim.go:354-360)
-            int nw = plan[l + 1].w, nh = plan[l + 1].h;
-            int pitch = dev_pitch(nw);
-            long long imgBytes = (long long)pitch * nh;
-            uint8_t *pa = (uint8_t *)c->ws.take((size_t)imgBytes * n);
-            uint8_t *pb = (uint8_t *)c->ws.take((size_t)imgBytes * n);
-            if (!pa || !pb) { set_error("internal: workspace under-reserved (msssim level)"); return FB_E_INVALID; }
-            na = ImgBatch{pa, imgBytes, pitch};
-            nb = ImgBatch{pb, imgBytes, pitch};
+        int tw, th, tw1, th1;
+        // Two levels from one read (box.cu: box_fused2_kernel): levels l and l+1 both need a thumbnail and level l+2
+        // exists; level l+1 then never exists in HBM.
+        if (msssim_level_fusable(plan, l, &tw, &th) && msssim_level_fusable(plan, l + 1, &tw1, &th1) && tw1 == tw && th1 == th) {
+            if (run.count > 0 && (run.tw != tw || run.th != th)) FB_TRY(flush_run());
+            const size_t mark = c->ws.off;
+            if (run.count == 0) FB_TRY(open_run(l, tw, th));
+            ImgBatch l2a, l2b;
+            FB_TRY(level_images(l + 2, &l2a, &l2b));
+            uint8_t *t0a = run.ta + (size_t)run.tBytes * n * run.count, *t0b = run.tb + (size_t)run.tBytes * n * run.count;
+            uint8_t *t1a = t0a + (size_t)run.tBytes * n, *t1b = t0b + (size_t)run.tBytes * n;
+            int rc = launch_box_fused2(s, ca.p, ca.imgStride, ca.rowStride, cb.p, cb.imgStride, cb.rowStride, lw, lh, t0a, t0b,
+                                       run.tBytes, run.tpitch, tw, th, t1a, t1b, run.tBytes, run.tpitch, tw1, th1,
+                                       (uint8_t *)l2a.p, (uint8_t *)l2b.p, l2a.imgStride, l2a.rowStride, n);
+            if (rc < 0) return rc;
+            if (rc == FB_OK) {
+                run.count += 2;
+                ca = l2a;
+                cb = l2b;
+                l += 1;     // level l+1 is done too
+                continue;
+            }
+            c->ws.off = mark;   // nothing launched: give back what this attempt reserved (a run opened here has count 0 and is re-opened below)
         }
+        ImgBatch na{nullptr, 0, 0}, nb{nullptr, 0, 0};
+        if (l + 1 < L) FB_TRY(level_images(l + 1, &na, &nb));   // 2x box cascade (ssim.go:354-360)
         // Fused level step: when this level needs both a thumbnail (SSIMFast, > 512 px) and the next level's
         // image, one kernel reads it once and writes both (box.cu: box_fused_kernel).
-        int tw, th;
         bool fused = false;
         if (msssim_level_fusable(plan, l, &tw, &th)) {
             if (run.count > 0 && (run.tw != tw || run.th != th)) FB_TRY(flush_run());
-            if (run.count == 0) {   // open a run: room for the thumbnails of the levels it can cover
-                const int cap = msssim_run_capacity(plan, l);
-                run.l0 = l; run.tw = tw; run.th = th; run.tpitch = dev_pitch(tw);
-                run.tBytes = (long long)run.tpitch * th;
-                run.ta = (uint8_t *)c->ws.take((size_t)run.tBytes * n * cap);
-                run.tb = (uint8_t *)c->ws.take((size_t)run.tBytes * n * cap);
-                if (!run.ta || !run.tb) { set_error("internal: workspace under-reserved (msssim thumbs)"); return FB_E_INVALID; }
-            }
+            if (run.count == 0) FB_TRY(open_run(l, tw, th));
             uint8_t *ta = run.ta + (size_t)run.tBytes * n * run.count, *tb = run.tb + (size_t)run.tBytes * n * run.count;
             int rc = launch_box_fused(s, ca.p, ca.imgStride, ca.rowStride, cb.p, cb.imgStride, cb.rowStride, lw, lh, ta, tb,
                                       run.tBytes, run.tpitch, tw, th, (uint8_t *)na.p, (uint8_t *)nb.p, na.imgStride, na.rowStride, n);
@@ -1025,7 +1051,7 @@ static int blur_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, uint8_
     FB_CUDA(cudaMemcpyAsync(kdev, kpin, sizeof(double) * taps, cudaMemcpyHostToDevice, s));
     FB_CUDA(cudaMemcpyAsync(fdev, fpin, sizeof(float) * taps, cudaMemcpyHostToDevice, s));
     mark_pin_busy(c, s);
-    return launch_gaussian_blur(s, dsrc, ddst, imgStride, rowStride, w, h, n, kdev, fdev, radius, wabs, tmp, timg, tpitch);
+    return launch_gaussian_blur(s, dsrc, ddst, imgStride, rowStride, w, h, n, kdev, fdev, fpin, radius, wabs, tmp, timg, tpitch);
 }
 
 int fb_gaussian_blur(const uint8_t *src, int srcStride, int w, int h, const double *kernel, int radius,
@@ -1311,6 +1337,32 @@ int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a, const 
     FB_TRY(launch_box(s, b, imgStride, rowStride, w, h, thumbB, thumbImgStride, thumbRowStride, tw, th, n, nullptr));
     FB_TRY(launch_box(s, a, imgStride, rowStride, w, h, halfA, halfImgStride, halfRowStride, w / 2, h / 2, n, nullptr));
     return launch_box(s, b, imgStride, rowStride, w, h, halfB, halfImgStride, halfRowStride, w / 2, h / 2, n, nullptr);
+}
+
+int fb_msssim_level2_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride, int rowStride,
+                               int w, int h, int n, uint8_t *thumb0A, uint8_t *thumb0B, uint8_t *thumb1A, uint8_t *thumb1B,
+                               int64_t thumbImgStride, int thumbRowStride, int tw, int th, uint8_t *quarterA, uint8_t *quarterB,
+                               int64_t quarterImgStride, int quarterRowStride) {
+    const char *fn = "fb_msssim_level2_batch_dev";
+    if (w < 4 || h < 4 || tw <= 0 || th <= 0) { set_error("fb_msssim_level2_batch_dev: bad dims"); return FB_E_INVALID; }
+    FB_TRY(check_batch(fn, a, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch(fn, b, imgStride, rowStride, w, h, n));
+    FB_TRY(check_batch(fn, thumb0A, thumbImgStride, thumbRowStride, tw, th, n));
+    FB_TRY(check_batch(fn, thumb0B, thumbImgStride, thumbRowStride, tw, th, n));
+    FB_TRY(check_batch(fn, thumb1A, thumbImgStride, thumbRowStride, tw, th, n));
+    FB_TRY(check_batch(fn, thumb1B, thumbImgStride, thumbRowStride, tw, th, n));
+    FB_TRY(check_batch(fn, quarterA, quarterImgStride, quarterRowStride, w / 4, h / 4, n));
+    FB_TRY(check_batch(fn, quarterB, quarterImgStride, quarterRowStride, w / 4, h / 4, n));
+    if (n == 0) return FB_OK;
+    DevCtx *c;
+    ApiScope scope_;
+    FB_TRY(dev_ctx_for(fn, device, &c));
+    scope_.bind(c, (cudaStream_t)stream);
+    // FB_IDENTITY-style answer 1: the geometry has no common period (or buffers are unaligned) — nothing was written;
+    // the caller runs fb_msssim_level_batch_dev twice instead.
+    return launch_box_fused2((cudaStream_t)stream, a, imgStride, rowStride, b, imgStride, rowStride, w, h, thumb0A, thumb0B,
+                             thumbImgStride, thumbRowStride, tw, th, thumb1A, thumb1B, thumbImgStride, thumbRowStride, tw, th,
+                             quarterA, quarterB, quarterImgStride, quarterRowStride, n);
 }
 
 int fb_gaussian_blur_batch_dev(int device, void *stream, const uint8_t *src, uint8_t *dst, int64_t imgStride,

@@ -298,6 +298,184 @@ __global__ void __launch_bounds__(kThreads) box_fused_kernel(const BoxFusedParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two MS-SSIM levels from ONE read ("level 1 is re-read from HBM instead of being produced while level 0's
+// tile is on chip").  A CTA owns a band of level-l rows x a chunk of level-l columns chosen on the host so that every
+// product has whole rows / columns inside it: band and chunk boundaries are box edges of BOTH thumbnails, multiples of
+// 4 rows and 8 columns.  The level-(l+1) pixels — the rounded bytes boxDownsample would write (ssim.go:354-360,
+// 286-309) — only ever exist in registers: a thread turns 4 rows x 8 columns of level l into 2 x 4 pixels of level
+// l+1 and 1 x 2 pixels of level l+2, and feeds both levels' rows into the column sums of their thumbnails.  8K pairs
+// move 133 + 8.3 + 1.2 MB per image instead of 133 + 33 + 33 + 8.3 + 1.2.
+// (First version, measured slower than the two single-level passes: a 28 KB shared-memory tile for level l+1 and a
+// second walk over it — 2 CTAs per SM, 1.78 ms against 1.47 ms per 16 8K pairs.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kF2Threads = 256;
+constexpr int kF2MaxBand = 64;        // level-l rows per band
+constexpr int kF2MaxChunk = 512;      // level-l columns per chunk
+constexpr int kF2SmemBudget = 56 * 1024;
+struct BoxFused2Params {
+    const uint8_t *src[2];
+    long long srcImgStride[2];
+    int srcRowStride[2];
+    uint8_t *thumb0[2], *thumb1[2], *l2[2];
+    long long thumb0ImgStride, thumb1ImgStride, l2ImgStride;
+    int thumb0RowStride, thumb1RowStride, l2RowStride;
+    int srcW, srcH, n;
+    int tw0, th0, tw1, th1;
+    double xr0, yr0, xr1, yr1;
+    int bandRows, chunkCols;          // level-l rows per band, columns per chunk
+    int t0PerBand, t0PerChunk;        // level-l thumbnail rows per band / columns per chunk
+    int t1PerBand, t1PerChunk;        // level-(l+1) thumbnail rows per band / columns per chunk
+};
+
+// Packed 16-bit channel sums of one thumbnail row, flushed to shared memory when the walk crosses a box edge (runs of
+// different threads may end inside the same box, hence atomics).
+template <int NCOL>
+struct F2Acc {
+    uint32_t lo[NCOL], hi[NCOL];
+    int ty, tyEnd;
+    __device__ __forceinline__ void init(int dyFirst, double ratio, int imgRows, int firstRow) {
+#pragma unroll
+        for (int i = 0; i < NCOL; i++) lo[i] = hi[i] = 0;
+        int lo_;
+        ty = dyFirst;
+        box_edge(ty, ratio, imgRows, lo_, tyEnd);
+        while (tyEnd <= firstRow) { ty++; box_edge(ty, ratio, imgRows, lo_, tyEnd); }
+    }
+    __device__ __forceinline__ void flush(uint2 *colsum, int dyFirst, int pitch, int col0) {
+        uint2 *cs = colsum + (size_t)(ty - dyFirst) * pitch + col0;
+#pragma unroll
+        for (int i = 0; i < NCOL; i++) {
+            atomicAdd(&cs[i].x, lo[i]);
+            atomicAdd(&cs[i].y, hi[i]);
+            lo[i] = hi[i] = 0;
+        }
+    }
+    // one image row (NCOL pixels) at row y
+    __device__ __forceinline__ void add(const uint32_t (&v)[NCOL], int y, uint2 *colsum, int dyFirst, int pitch, int col0, double ratio,
+                                        int imgRows) {
+        if (y >= tyEnd) {   // crossed into the next thumbnail row
+            flush(colsum, dyFirst, pitch, col0);
+            ty++;
+            int lo_;
+            box_edge(ty, ratio, imgRows, lo_, tyEnd);
+        }
+#pragma unroll
+        for (int i = 0; i < NCOL; i++) {
+            lo[i] += v[i] & 0x00FF00FFu;          // R, B
+            hi[i] += (v[i] >> 8) & 0x00FF00FFu;   // G, A
+        }
+    }
+};
+
+// Thumbnail pixels of `nTy` thumbnail rows x [dx0, dx1) from the column sums (one thread per output pixel).
+__device__ __forceinline__ void f2_outputs(const uint2 *colsum, int csPitch, int x0, int dyFirst, int nTy, int dx0, int dx1,
+                                           double xRatio, double yRatio, int imgW, int imgH, uint8_t *td, int tdRowStride) {
+    const int nTx = dx1 - dx0;
+    for (int idx = threadIdx.x; idx < nTy * nTx; idx += kF2Threads) {
+        const int ty = idx / nTx, dx = dx0 + idx - ty * nTx;
+        int sy0, sy1, sx0, sx1;
+        box_edge(dyFirst + ty, yRatio, imgH, sy0, sy1);
+        box_edge(dx, xRatio, imgW, sx0, sx1);
+        const uint2 *cs = colsum + (size_t)ty * csPitch - x0;
+        uint32_t sr = 0, sg = 0, sb = 0, sa = 0;
+        for (int xx = sx0; xx < sx1; xx++) {
+            const uint2 c = cs[xx];
+            sr += c.x & 0xFFFFu; sb += c.x >> 16;
+            sg += c.y & 0xFFFFu; sa += c.y >> 16;
+        }
+        *reinterpret_cast<uint32_t *>(td + (long long)(dyFirst + ty) * tdRowStride + (long long)dx * 4) =
+            box_finish(sr, sg, sb, sa, (sy1 - sy0) * (sx1 - sx0));
+    }
+}
+
+// A thread owns a stripe of 4 level-l columns (one 128-bit load per row, contiguous across the warp) and a run of
+// 4-row steps.  One step = 4 loads -> 2 rows x 2 pixels of level l+1 (registers only) -> 1 pixel of level l+2 (a 4-byte
+// store, contiguous across the warp); two steps are in flight at a time.  Every level-l row and every level-(l+1) row
+// is added to the column sums of the thumbnail row that contains it.
+__device__ __forceinline__ uint32_t mean2x2_px(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+    const uint32_t rb = (a0 & 0x00FF00FFu) + (a1 & 0x00FF00FFu) + (b0 & 0x00FF00FFu) + (b1 & 0x00FF00FFu);
+    const uint32_t ga = ((a0 >> 8) & 0x00FF00FFu) + ((a1 >> 8) & 0x00FF00FFu) + ((b0 >> 8) & 0x00FF00FFu) + ((b1 >> 8) & 0x00FF00FFu);
+    return (((rb + 0x00020002u) >> 2) & 0x00FF00FFu) | ((((ga + 0x00020002u) >> 2) & 0x00FF00FFu) << 8);
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kF2Threads, MINB) box_fused2_kernel(const BoxFused2Params p) {
+    extern __shared__ __align__(16) uint8_t f2smem[];
+    const int which = (int)blockIdx.z >= p.n ? 1 : 0;
+    const int img = (int)blockIdx.z - which * p.n;
+    const int rs = p.srcRowStride[which];
+    const uint8_t *s = p.src[which] + (long long)img * p.srcImgStride[which];
+    uint8_t *l2 = p.l2[which] + (long long)img * p.l2ImgStride;
+    const int X0 = blockIdx.x * p.chunkCols, Y0 = blockIdx.y * p.bandRows;
+    const int X1 = min(X0 + p.chunkCols, p.srcW), Y1 = min(Y0 + p.bandRows, p.srcH);
+    const int cols = X1 - X0, rows = Y1 - Y0;                  // multiples of 8 and 4
+    const int h1 = p.srcH >> 1;
+    const int dy0 = blockIdx.y * p.t0PerBand, nTy0 = min(p.t0PerBand, p.th0 - dy0);
+    const int dy1 = blockIdx.y * p.t1PerBand, nTy1 = min(p.t1PerBand, p.th1 - dy1);
+    uint2 *colsum0 = reinterpret_cast<uint2 *>(f2smem);                       // [t0PerBand][chunkCols]
+    uint2 *colsum1 = colsum0 + (size_t)p.t0PerBand * p.chunkCols;              // [t1PerBand][chunkCols / 2]
+    const int pitch0 = p.chunkCols, pitch1 = p.chunkCols >> 1;
+    for (int i = threadIdx.x; i < p.t0PerBand * pitch0 + p.t1PerBand * pitch1; i += kF2Threads) colsum0[i] = make_uint2(0u, 0u);
+    __syncthreads();
+    {
+        const int stripes = cols >> 2, steps = rows >> 2;
+        int groups = kF2Threads / stripes;
+        if (groups < 1) groups = 1;
+        if (groups > steps) groups = steps;
+        const int spg = (steps + groups - 1) / groups;
+        for (int work = threadIdx.x; work < stripes * groups; work += kF2Threads) {
+            const int st = work % stripes, g = work / stripes;
+            const int k0 = g * spg, k1 = min(k0 + spg, steps);
+            if (k0 >= k1) continue;
+            F2Acc<4> a0;
+            F2Acc<2> a1;
+            a0.init(dy0, p.yr0, p.srcH, Y0 + 4 * k0);
+            a1.init(dy1, p.yr1, h1, (Y0 >> 1) + 2 * k0);
+            const uint8_t *q = s + (long long)(Y0 + 4 * k0) * rs + (long long)(X0 + 4 * st) * 4;
+            uint8_t *o = l2 + (long long)((Y0 >> 2) + k0) * p.l2RowStride + (long long)((X0 >> 2) + st) * 4;
+            auto step = [&](const uint4 (&t)[4], int k, uint8_t *op) {
+                uint32_t L1[2][2];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t v[4] = {t[r].x, t[r].y, t[r].z, t[r].w};
+                    a0.add(v, Y0 + 4 * k + r, colsum0, dy0, pitch0, 4 * st, p.yr0, p.srcH);
+                }
+#pragma unroll
+                for (int hr = 0; hr < 2; hr++) {
+                    L1[hr][0] = mean2x2_px(t[2 * hr].x, t[2 * hr].y, t[2 * hr + 1].x, t[2 * hr + 1].y);
+                    L1[hr][1] = mean2x2_px(t[2 * hr].z, t[2 * hr].w, t[2 * hr + 1].z, t[2 * hr + 1].w);
+                    a1.add(L1[hr], (Y0 >> 1) + 2 * k + hr, colsum1, dy1, pitch1, 2 * st, p.yr1, h1);
+                }
+                *reinterpret_cast<uint32_t *>(op) = mean2x2_px(L1[0][0], L1[0][1], L1[1][0], L1[1][1]);
+            };
+            int k = k0;
+            for (; k + 2 <= k1; k += 2, q += 8 * (long long)rs, o += 2 * (long long)p.l2RowStride) {
+                uint4 ta[4], tb[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) ta[r] = ld_nc_u128(q + (long long)r * rs);
+#pragma unroll
+                for (int r = 0; r < 4; r++) tb[r] = ld_nc_u128(q + (long long)(4 + r) * rs);
+                step(ta, k, o);
+                step(tb, k + 1, o + p.l2RowStride);
+            }
+            if (k < k1) {
+                uint4 ta[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) ta[r] = ld_nc_u128(q + (long long)r * rs);
+                step(ta, k, o);
+            }
+            a0.flush(colsum0, dy0, pitch0, 4 * st);
+            a1.flush(colsum1, dy1, pitch1, 2 * st);
+        }
+    }
+    __syncthreads();
+    f2_outputs(colsum0, pitch0, X0, dy0, nTy0, blockIdx.x * p.t0PerChunk, min((int)(blockIdx.x + 1) * p.t0PerChunk, p.tw0), p.xr0, p.yr0,
+               p.srcW, p.srcH, p.thumb0[which] + (long long)img * p.thumb0ImgStride, p.thumb0RowStride);
+    f2_outputs(colsum1, pitch1, X0 >> 1, dy1, nTy1, blockIdx.x * p.t1PerChunk, min((int)(blockIdx.x + 1) * p.t1PerChunk, p.tw1), p.xr1,
+               p.yr1, p.srcW >> 1, h1, p.thumb1[which] + (long long)img * p.thumb1ImgStride, p.thumb1RowStride);
+}
+
 // Generic fallback: one thread per output pixel walks its own box (upsampling, boxes taller than
 // 256 rows or wider than the shared-memory span). Same arithmetic.
 __global__ void __launch_bounds__(kThreads) box_naive_kernel(const BoxParams p) {
@@ -456,6 +634,93 @@ int launch_box_fused(cudaStream_t s, const uint8_t *srcA, long long srcImgStride
     p.dyPerCta = maxBoxH >= 32 ? 1 : (32 / maxBoxH < 1 ? 1 : 32 / maxBoxH);
     dim3 grid((tw + chunk - 1) / chunk, (th + p.dyPerCta - 1) / p.dyPerCta, 2 * n);
     box_fused_kernel<<<grid, kThreads, 0, s>>>(p);
+    FB_LAUNCHED(1);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+}
+
+// Smallest period P (multiple of `mult`, <= maxP) such that every multiple of P below `src` is a box edge of the
+// src -> dst0 downsample AND (halved) of the src/2 -> dst1 downsample; 0 if none.  *per0 / *per1 = thumbnail boxes per period.
+static int common_period(int src, int dst0, int dst1, int mult, int maxP, int *per0, int *per1) {
+    std::vector<int> lo0(dst0), hi0(dst0), lo1(dst1), hi1(dst1);
+    box_edges_host(src, dst0, lo0.data(), hi0.data());
+    box_edges_host(src / 2, dst1, lo1.data(), hi1.data());
+    for (int P = mult; P <= maxP; P += mult) {
+        if (src % P) continue;
+        if ((long long)dst0 * P % src || (long long)dst1 * P % src) continue;
+        const int n0 = (int)((long long)dst0 * P / src), n1 = (int)((long long)dst1 * P / src);
+        if (n0 < 1 || n1 < 1) continue;
+        bool ok = true;
+        for (int k = 0; ok && k * P < src; k++) {
+            if (lo0[k * n0] != k * P || lo1[k * n1] != k * P / 2) ok = false;
+        }
+        if (ok) { *per0 = n0; *per1 = n1; return P; }
+    }
+    return 0;
+}
+
+// Levels l and l+1 of the MS-SSIM pyramid from one read of level l: thumbnails of both levels and the level-(l+2)
+// image.  Returns 1 (nothing launched) when the geometry has no common period; the caller then takes two single steps.
+int launch_box_fused2(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA, const uint8_t *srcB,
+                      long long srcImgStrideB, int srcRowStrideB, int srcW, int srcH, uint8_t *thumb0A, uint8_t *thumb0B,
+                      long long thumb0ImgStride, int thumb0RowStride, int tw0, int th0, uint8_t *thumb1A, uint8_t *thumb1B,
+                      long long thumb1ImgStride, int thumb1RowStride, int tw1, int th1, uint8_t *l2A, uint8_t *l2B,
+                      long long l2ImgStride, int l2RowStride, int n) {
+    if (n <= 0) return FB_OK;
+    if (getenv("FB_BOX_NOFUSE") != nullptr || getenv("FB_BOX_NOFUSE2") != nullptr) return 1;
+    if ((srcW & 7) || (srcH & 3) || tw0 < 1 || th0 < 1 || tw1 < 1 || th1 < 1) return 1;
+    const uintptr_t al = (uintptr_t)srcA | (uintptr_t)srcB | (uintptr_t)srcImgStrideA | (uintptr_t)srcImgStrideB |
+                         (uintptr_t)srcRowStrideA | (uintptr_t)srcRowStrideB;
+    if ((al & 15) || (((uintptr_t)l2A | (uintptr_t)l2B | (uintptr_t)l2ImgStride | (uintptr_t)l2RowStride) & 7)) return 1;
+    BoxFused2Params p;
+    p.xr0 = (double)srcW / (double)tw0; p.yr0 = (double)srcH / (double)th0;
+    p.xr1 = (double)(srcW / 2) / (double)tw1; p.yr1 = (double)(srcH / 2) / (double)th1;
+    auto fits = [](double r) { return r >= 1.0 && (int)r + 2 <= 256; };
+    if (!fits(p.xr0) || !fits(p.yr0) || !fits(p.xr1) || !fits(p.yr1)) return 1;
+    if (!boxes_tile(srcW, tw0) || !boxes_tile(srcH, th0) || !boxes_tile(srcW / 2, tw1) || !boxes_tile(srcH / 2, th1)) return 1;
+    int t0b, t1b, t0c, t1c;
+    const int band = common_period(srcH, th0, th1, 4, kF2MaxBand, &t0b, &t1b);
+    const int colP = common_period(srcW, tw0, tw1, 8, kF2MaxChunk, &t0c, &t1c);
+    if (!band || !colP) return 1;
+    // whole periods per CTA: up to 64 rows x ~480 columns, shrunk until the column sums of every thumbnail row of the
+    // band plus the level-(l+1) tile fit the shared-memory budget
+    const int rrep = kF2MaxBand / band;
+    int reps = 480 / colP > 0 ? 480 / colP : 1;
+    auto smem_for = [&](int reps_) {
+        const size_t chunk = (size_t)colP * reps_;
+        return (size_t)t0b * rrep * chunk * sizeof(uint2) + (size_t)t1b * rrep * (chunk / 2) * sizeof(uint2);
+    };
+    while (reps > 1 && smem_for(reps) > (size_t)kF2SmemBudget) reps--;
+    if (smem_for(reps) > (size_t)kF2SmemBudget) return 1;
+    p.bandRows = band * rrep; p.chunkCols = colP * reps;
+    p.t0PerBand = t0b * rrep; p.t1PerBand = t1b * rrep; p.t0PerChunk = t0c * reps; p.t1PerChunk = t1c * reps;
+    p.src[0] = srcA; p.src[1] = srcB;
+    p.srcImgStride[0] = srcImgStrideA; p.srcImgStride[1] = srcImgStrideB;
+    p.srcRowStride[0] = srcRowStrideA; p.srcRowStride[1] = srcRowStrideB;
+    p.thumb0[0] = thumb0A; p.thumb0[1] = thumb0B; p.thumb0ImgStride = thumb0ImgStride; p.thumb0RowStride = thumb0RowStride;
+    p.thumb1[0] = thumb1A; p.thumb1[1] = thumb1B; p.thumb1ImgStride = thumb1ImgStride; p.thumb1RowStride = thumb1RowStride;
+    p.l2[0] = l2A; p.l2[1] = l2B; p.l2ImgStride = l2ImgStride; p.l2RowStride = l2RowStride;
+    p.srcW = srcW; p.srcH = srcH; p.n = n;
+    p.tw0 = tw0; p.th0 = th0; p.tw1 = tw1; p.th1 = th1;
+    const size_t smem = smem_for(reps);
+    static bool attrSet = false;
+    if (!attrSet) {
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBudget));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBudget));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBudget));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBudget));
+        FB_CUDA(cudaFuncSetAttribute(box_fused2_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attrSet = true;
+    }
+    dim3 grid((srcW + p.chunkCols - 1) / p.chunkCols, (srcH + p.bandRows - 1) / p.bandRows, 2 * n);
+    static const int minb = [] { const char *e = getenv("FB_F2_MINB"); return (e && e[0] >= '2' && e[0] <= '5') ? e[0] - '0' : 3; }();
+    if (minb == 2) box_fused2_kernel<2><<<grid, kF2Threads, smem, s>>>(p);
+    else if (minb == 4) box_fused2_kernel<4><<<grid, kF2Threads, smem, s>>>(p);
+    else if (minb == 5) box_fused2_kernel<5><<<grid, kF2Threads, smem, s>>>(p);
+    else box_fused2_kernel<3><<<grid, kF2Threads, smem, s>>>(p);
     FB_LAUNCHED(1);
     FB_CUDA(cudaGetLastError());
     return FB_OK;

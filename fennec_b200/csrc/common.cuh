@@ -107,11 +107,18 @@ int launch_box_fused(cudaStream_t s, const uint8_t *srcA, long long srcImgStride
                      uint8_t *thumbA, uint8_t *thumbB, long long thumbImgStride, int thumbRowStride, int tw, int th,
                      uint8_t *halfA, uint8_t *halfB, long long halfImgStride, int halfRowStride, int n);
 
+// Two levels from one read (box_fused2_kernel): thumbnails of levels l and l+1 and the level-(l+2) image; 1 = not applicable.
+int launch_box_fused2(cudaStream_t s, const uint8_t *srcA, long long srcImgStrideA, int srcRowStrideA, const uint8_t *srcB,
+                      long long srcImgStrideB, int srcRowStrideB, int srcW, int srcH, uint8_t *thumb0A, uint8_t *thumb0B,
+                      long long thumb0ImgStride, int thumb0RowStride, int tw0, int th0, uint8_t *thumb1A, uint8_t *thumb1B,
+                      long long thumb1ImgStride, int thumb1RowStride, int tw1, int th1, uint8_t *l2A, uint8_t *l2B,
+                      long long l2ImgStride, int l2RowStride, int n);
+
 // effects.cu
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
                          int rowStride, int w, int h, int n, const double *kernel_dev,
-                         const float *kernel32_dev, int radius, double wabs, uint8_t *tmp, long long tmpImgStride,
-                         int tmpRowStride);
+                         const float *kernel32_dev, const float *kernel32_host, int radius, double wabs, uint8_t *tmp,
+                         long long tmpImgStride, int tmpRowStride);
 int launch_blur3x3(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride, int rowStride,
                    int w, int h, int n, long long dstImgStride, int dstRowStride);
 int launch_sharpen(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride, int rowStride,

@@ -28,6 +28,7 @@ struct BlurParams {
     int w, h, radius;
     const double *kernel;    // 2r+1 FP64 weights (caller-built)
     const float *kernel32;   // the same rounded to FP32
+    float w32[17];           // ... and by value for the fast kernels (radius <= 8): constant-bank operands, no loads
     float eps;
     int exactOnly;
 };
@@ -218,11 +219,11 @@ __device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *
 #define FB_BLUR_BA 0   // 1: B rides an FFMA2 together with the (discarded) alpha lane instead of a scalar FFMA
 #endif
 template <int R, int NIN, int OFF>
-__device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const float *kernel32,
+__device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const float (&w32)[17],
                                                float2 (&accRG)[kTile], float2 (&accB)[kTile / 2]) {
     float wt[2 * R + 1];
 #pragma unroll
-    for (int k = 0; k <= 2 * R; k++) wt[k] = __ldg(kernel32 + k);
+    for (int k = 0; k <= 2 * R; k++) wt[k] = w32[k];   // kernel parameters: uniform / constant-bank operands
 #pragma unroll
     for (int j = 0; j < kTile; j++) accRG[j] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -279,15 +280,17 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // Horizontal pass: a warp owns 512 output pixels of a row (16 per lane) and walks kHRows consecutive rows; row
 // y+1 is staged into the warp's second shared-memory buffer with cp.async while row y is evaluated, so the
 // global-load latency is paid once per warp instead of once per row.  No block-wide barrier.
-template <int R>
-__global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p) {
-    __shared__ __align__(16) uint8_t stage[4][2][34 * kChunkB];
-    __shared__ uint32_t ambQ[4][kAmbQ];
-    __shared__ int ambN[4];
+// WPB = warps per block.  The warps never synchronise with each other, so one-warp blocks only change the granularity
+// at which the SM takes on new work (no waiting for the slowest of four warps before the next block starts).
+template <int R, int WPB>
+__global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_h_fast_kernel(const BlurParams p) {
+    __shared__ __align__(16) uint8_t stage[WPB][2][34 * kChunkB];
+    __shared__ uint32_t ambQ[WPB][kAmbQ];
+    __shared__ int ambN[WPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) ambN[warp] = 0;
     __syncwarp();
-    const int yBeg = (blockIdx.y * 4 + warp) * kHRows, img = blockIdx.z;
+    const int yBeg = (blockIdx.y * WPB + warp) * kHRows, img = blockIdx.z;
     const int yEnd = min(yBeg + kHRows, p.h);
     if (yBeg >= p.h) return;  // warp-uniform; no block barrier below
     const int xs = blockIdx.x * (32 * kTile);
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p)
                 raw[v * 4 + 0] = q.x; raw[v * 4 + 1] = q.y; raw[v * 4 + 2] = q.z; raw[v * 4 + 3] = q.w;
             }
             float2 accRG[kTile], accB[kTile / 2];
-            blur_taps_fp32<R, 32, 8>(raw, p.kernel32, accRG, accB);
+            blur_taps_fp32<R, 32, 8>(raw, p.w32, accRG, accB);
             uint32_t out[kTile];
             uint32_t ambMask = blur_round_pack(accRG, accB, lim, out, [&](int j) { return raw[8 + j]; });  // alpha from the source (effects.go:189)
             uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
@@ -382,15 +385,15 @@ __global__ void __launch_bounds__(128, 4) blur_h_fast_kernel(const BlurParams p)
 #endif
 constexpr int kVSeg = FB_BLUR_VSEG;  // rows per thread segment (2160 = 9 * 240; halo 12/240)
 
-template <int R>
-__global__ void __launch_bounds__(128, 4) blur_v_fast_kernel(const BlurParams p) {
+template <int R, int WPB>
+__global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const BlurParams p) {
     constexpr int NIN = kTile + 2 * R;
-    __shared__ uint32_t ambQ[4][kAmbQ];
-    __shared__ int ambN[4];
+    __shared__ uint32_t ambQ[WPB][kAmbQ];
+    __shared__ int ambN[WPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) ambN[warp] = 0;
     __syncwarp();
-    const int x = blockIdx.x * 128 + threadIdx.x, img = blockIdx.z;
+    const int x = blockIdx.x * (32 * WPB) + threadIdx.x, img = blockIdx.z;
     const int ys = blockIdx.y * kVSeg;
     const int yEnd = min(ys + kVSeg, p.h);
     const bool active = x < p.w;   // inactive lanes still take part in the warp's queue drains
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(128, 4) blur_v_fast_kernel(const BlurParams p)
             }
         }
         float2 accRG[kTile], accB[kTile / 2];
-        blur_taps_fp32<R, NIN, R>(raw, p.kernel32, accRG, accB);
+        blur_taps_fp32<R, NIN, R>(raw, p.w32, accRG, accB);
         uint32_t out[kTile];
         uint32_t ambMask = blur_round_pack(accRG, accB, lim, out, [&](int j) { return raw[R + j]; });  // alpha rides in tmp (effects.go:189,215)
         {
@@ -455,12 +458,23 @@ __global__ void __launch_bounds__(128, 4) blur_v_fast_kernel(const BlurParams p)
 
 template <int R>
 static void launch_blur_fast(cudaStream_t s, BlurParams p, int n, bool vertical) {
+    static const bool wpb4 = [] { const char *e = getenv("FB_BLUR_WPB"); return e && e[0] == '4'; }();   // round-1 block shape
     if (!vertical) {
-        dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + 4 * kHRows - 1) / (4 * kHRows), n);
-        blur_h_fast_kernel<R><<<grid, 128, 0, s>>>(p);
+        if (wpb4) {
+            dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + 4 * kHRows - 1) / (4 * kHRows), n);
+            blur_h_fast_kernel<R, 4><<<grid, 128, 0, s>>>(p);
+        } else {
+            dim3 grid((p.w + 32 * kTile - 1) / (32 * kTile), (p.h + kHRows - 1) / kHRows, n);
+            blur_h_fast_kernel<R, 1><<<grid, 32, 0, s>>>(p);
+        }
     } else {
-        dim3 grid((p.w + 127) / 128, (p.h + kVSeg - 1) / kVSeg, n);
-        blur_v_fast_kernel<R><<<grid, 128, 0, s>>>(p);
+        if (wpb4) {
+            dim3 grid((p.w + 127) / 128, (p.h + kVSeg - 1) / kVSeg, n);
+            blur_v_fast_kernel<R, 4><<<grid, 128, 0, s>>>(p);
+        } else {
+            dim3 grid((p.w + 31) / 32, (p.h + kVSeg - 1) / kVSeg, n);
+            blur_v_fast_kernel<R, 1><<<grid, 32, 0, s>>>(p);
+        }
     }
 }
 
@@ -991,12 +1005,13 @@ __global__ void __launch_bounds__(128) adaptive_tile_kernel(const FxTileParams p
 
 int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long imgStride,
                          int rowStride, int w, int h, int n, const double *kernel_dev,
-                         const float *kernel32_dev, int radius, double wabs, uint8_t *tmp, long long tmpImgStride,
-                         int tmpRowStride) {
+                         const float *kernel32_dev, const float *kernel32_host, int radius, double wabs, uint8_t *tmp,
+                         long long tmpImgStride, int tmpRowStride) {
     if (n <= 0 || w <= 0 || h <= 0) return FB_OK;
     BlurParams p;
     p.w = w; p.h = h; p.radius = radius;
     p.kernel = kernel_dev; p.kernel32 = kernel32_dev;
+    for (int k = 0; k < 17; k++) p.w32[k] = (k <= 2 * radius && radius <= 8) ? kernel32_host[k] : 0.f;
     // FP32 error bound of the tap sum: each of the `taps` FMAs rounds a partial sum <= 255 (<= 255*2^-24 each)
     // and the FP32 weights differ from the FP64 ones by <= 2^-24 relative (<= 255*2^-24 in total); 25 % margin.
     // The bound assumes partial sums <= 255 (a convex combination); a caller-supplied kernel that is not normalised or

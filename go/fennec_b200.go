@@ -19,6 +19,7 @@ import "C"
 import (
 	"image"
 	"image/color"
+	"runtime"
 	"unsafe"
 )
 
@@ -101,12 +102,54 @@ func csr(w [][]weightEntry) (start, index []C.int, weight []C.double) {
 	return
 }
 
-// gpuLanczosResize replaces resizeH+resizeV (resize.go:51-52). Passing nil tables lets the library build
-// them (glibc sin); passing Go-built tables keeps bit parity independent of libm.
+// gpuLanczosResize replaces resizeH+resizeV (resize.go:51-52).  The two weight tables are the ones lanczosResize's
+// own precomputeWeights builds with Go's math.Sin (resize.go:164-197), flattened by csr(): bit parity of the pixels
+// then does not depend on glibc's sin agreeing with Go's (SURVEY H5).  The CSR slices are Go memory referenced from a
+// C struct, so they are pinned for the duration of the call (runtime.Pinner, Go >= 1.21).
 func gpuLanczosResize(src, dst *image.NRGBA) bool {
-	st := C.fb_lanczos_resize(pix(src), C.int(src.Stride), C.int(src.Bounds().Dx()), C.int(src.Bounds().Dy()),
-		pix(dst), C.int(dst.Stride), C.int(dst.Bounds().Dx()), C.int(dst.Bounds().Dy()), nil, nil)
+	sw, sh := src.Bounds().Dx(), src.Bounds().Dy()
+	dw, dh := dst.Bounds().Dx(), dst.Bounds().Dy()
+	ratioX, ratioY := float64(sw)/float64(dw), float64(sh)/float64(dh)
+	supX, supY := 3.0, 3.0 // resize.go:81-85 / 125-129
+	if ratioX > 1 {
+		supX = 3.0 * ratioX
+	}
+	if ratioY > 1 {
+		supY = 3.0 * ratioY
+	}
+	sx, ix, wx := csr(precomputeWeights(dw, sw, ratioX, supX))
+	sy, iy, wy := csr(precomputeWeights(dh, sh, ratioY, supY))
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	table := func(start, index []C.int, weight []C.double, n int) *C.fb_weights {
+		if len(index) == 0 {
+			return nil // degenerate table: let the library build it
+		}
+		pin.Pin(&start[0])
+		pin.Pin(&index[0])
+		pin.Pin(&weight[0])
+		return &C.fb_weights{n: C.int(n), start: &start[0], index: &index[0], weight: &weight[0]}
+	}
+	tx, ty := table(sx, ix, wx, dw), table(sy, iy, wy, dh)
+	st := C.fb_lanczos_resize(pix(src), C.int(src.Stride), C.int(sw), C.int(sh),
+		pix(dst), C.int(dst.Stride), C.int(dw), C.int(dh), tx, ty)
 	return st == C.FB_OK
+}
+
+// ---- CompressBatch (batch.go:58-128) on several GPUs -----------------------------------------------------
+
+// gpuWorkerInit is called once at the top of each CompressBatch worker goroutine (batch.go:84-88): the worker pins
+// itself to an OS thread and takes GPU `worker % nGPU`; every hot-path call CompressFile makes from this goroutine
+// (SSIMFast in the quality search, smartResize, boxDownsample) then runs on that device, on the thread's own
+// stream.  When the goroutine ends the OS thread dies with it (LockOSThread without Unlock) and the library hands
+// the thread's stream and arenas to the next worker (a pool, not a leak).
+func gpuWorkerInit(worker int) bool {
+	n := int(C.fb_device_count())
+	if n <= 0 {
+		return false
+	}
+	runtime.LockOSThread()
+	return C.fb_set_device(C.int(worker%n)) == C.FB_OK
 }
 
 // gpuShard is the partition CompressBatch uses when it hands whole sub-batches to per-GPU workers
@@ -117,6 +160,39 @@ func gpuShard(nItems, nShards, shard int) (begin, end int, ok bool) {
 	return int(b), int(e), st == C.FB_OK
 }
 
+// gpuScoreBatch scores a list of equal-sized pairs on every GPU of the box from this one call (fb_score_batch_host:
+// fb_batch_shard over the devices, the library's own worker threads, results in input order).  op is C.FB_OP_SSIM,
+// C.FB_OP_SSIM_FAST or C.FB_OP_MSSSIM.  status[i] < 0 marks an item that failed or was cancelled (*cancel != 0,
+// the analogue of ctx.Done() in batch.go:90-98); the caller re-runs those through the pure-Go body.
+func gpuScoreBatch(op C.int, as, bs []*image.NRGBA, cancel *int32) (scores []float64, status []int32, ok bool) {
+	n := len(as)
+	if n == 0 || n != len(bs) {
+		return nil, nil, n == 0
+	}
+	pairs := make([]C.fb_pair, n)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	for i := range as {
+		if len(as[i].Pix) == 0 || len(bs[i].Pix) == 0 {
+			return nil, nil, false
+		}
+		pin.Pin(&as[i].Pix[0]) // Go pointers stored inside C-visible structs must be pinned
+		pin.Pin(&bs[i].Pix[0])
+		pairs[i] = C.fb_pair{a: pix(as[i]), strideA: C.int(as[i].Stride), b: pix(bs[i]), strideB: C.int(bs[i].Stride),
+			w: C.int(as[i].Bounds().Dx()), h: C.int(as[i].Bounds().Dy())}
+	}
+	scores = make([]float64, n)
+	status = make([]int32, n)
+	opts := C.fb_batch_opts{workers_per_device: 4}
+	if cancel != nil {
+		pin.Pin(cancel)
+		opts.cancel = (*C.int)(unsafe.Pointer(cancel))
+	}
+	failed := C.fb_score_batch_host(op, &pairs[0], C.int(n), (*C.double)(unsafe.Pointer(&scores[0])),
+		(*C.int)(unsafe.Pointer(&status[0])), &opts)
+	return scores, status, failed >= 0
+}
+
 // ---- SURVEY §8(f1): the step before SSIMFast in the quality search (compress.go:53-62) ----------------
 
 // gpuConvertToNRGBA replaces convertToNRGBA's pixel loop (convert.go:38-63) for the concrete types jpeg.Decode and
@@ -124,30 +200,34 @@ func gpuShard(nItems, nShards, shard int) (begin, end int, ok bool) {
 func gpuConvertToNRGBA(img image.Image, dst *image.NRGBA) bool {
 	switch s := img.(type) {
 	case *image.YCbCr:
-		if s.Rect.Min != (image.Point{}) || len(s.Y) == 0 {
+		// Sub-images (SubImage shares the planes, Rect.Min != 0): the planes are addressed through YOffset / COffset
+		// exactly as convertToNRGBA's At() does (convert.go:34-64 walks Bounds()).  The chroma phase of the library's
+		// kernel starts at (0,0), so a sub-image must start on an even luma sample in every subsampled direction.
+		if len(s.Y) == 0 || s.Rect.Empty() || s.Rect.Min.X%2 != 0 || s.Rect.Min.Y%2 != 0 {
 			return false
 		}
-		st := C.fb_ycbcr_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Y[0])), C.int(s.YStride),
-			(*C.uint8_t)(unsafe.Pointer(&s.Cb[0])), (*C.uint8_t)(unsafe.Pointer(&s.Cr[0])), C.int(s.CStride),
+		yo, co := s.YOffset(s.Rect.Min.X, s.Rect.Min.Y), s.COffset(s.Rect.Min.X, s.Rect.Min.Y)
+		st := C.fb_ycbcr_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Y[yo])), C.int(s.YStride),
+			(*C.uint8_t)(unsafe.Pointer(&s.Cb[co])), (*C.uint8_t)(unsafe.Pointer(&s.Cr[co])), C.int(s.CStride),
 			C.int(s.Rect.Dx()), C.int(s.Rect.Dy()), C.int(s.SubsampleRatio), pix(dst), C.int(dst.Stride))
 		return st == C.FB_OK
 	case *image.Gray:
-		if s.Rect.Min != (image.Point{}) || len(s.Pix) == 0 {
+		if len(s.Pix) == 0 || s.Rect.Empty() {
 			return false
 		}
-		st := C.fb_gray_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Pix[0])), C.int(s.Stride),
+		st := C.fb_gray_to_nrgba((*C.uint8_t)(unsafe.Pointer(&s.Pix[s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y)])), C.int(s.Stride),
 			C.int(s.Rect.Dx()), C.int(s.Rect.Dy()), pix(dst), C.int(dst.Stride))
 		return st == C.FB_OK
 	case *image.RGBA: // png.Decode of truecolour without alpha, draw targets
-		return gpuConvertPix(C.FB_FMT_RGBA, s.Pix, s.Stride, s.Rect, nil, dst)
+		return gpuConvertPix(C.FB_FMT_RGBA, s.Pix, s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y), s.Stride, s.Rect, nil, dst)
 	case *image.RGBA64:
-		return gpuConvertPix(C.FB_FMT_RGBA64, s.Pix, s.Stride, s.Rect, nil, dst)
+		return gpuConvertPix(C.FB_FMT_RGBA64, s.Pix, s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y), s.Stride, s.Rect, nil, dst)
 	case *image.NRGBA64:
-		return gpuConvertPix(C.FB_FMT_NRGBA64, s.Pix, s.Stride, s.Rect, nil, dst)
+		return gpuConvertPix(C.FB_FMT_NRGBA64, s.Pix, s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y), s.Stride, s.Rect, nil, dst)
 	case *image.Gray16:
-		return gpuConvertPix(C.FB_FMT_GRAY16, s.Pix, s.Stride, s.Rect, nil, dst)
+		return gpuConvertPix(C.FB_FMT_GRAY16, s.Pix, s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y), s.Stride, s.Rect, nil, dst)
 	case *image.CMYK: // 4-component JPEGs
-		return gpuConvertPix(C.FB_FMT_CMYK, s.Pix, s.Stride, s.Rect, nil, dst)
+		return gpuConvertPix(C.FB_FMT_CMYK, s.Pix, s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y), s.Stride, s.Rect, nil, dst)
 	case *image.Paletted:
 		if len(s.Palette) == 0 || len(s.Palette) > 256 {
 			return false
@@ -157,22 +237,24 @@ func gpuConvertToNRGBA(img image.Image, dst *image.NRGBA) bool {
 			r, g, b, a := c.RGBA()
 			pal[4*i], pal[4*i+1], pal[4*i+2], pal[4*i+3] = uint16(r), uint16(g), uint16(b), uint16(a)
 		}
-		return gpuConvertPix(C.FB_FMT_PALETTED, s.Pix, s.Stride, s.Rect, pal, dst)
+		return gpuConvertPix(C.FB_FMT_PALETTED, s.Pix, s.PixOffset(s.Rect.Min.X, s.Rect.Min.Y), s.Stride, s.Rect, pal, dst)
 	}
 	return false
 }
 
-// gpuConvertPix hands a decoded image's Pix buffer to fb_convert_to_nrgba.  A palette index past the palette makes
-// the call fail (FB_E_INVALID); the caller then runs the pure-Go loop, which panics exactly as before.
-func gpuConvertPix(format C.int, p []uint8, stride int, r image.Rectangle, pal []uint16, dst *image.NRGBA) bool {
-	if r.Min != (image.Point{}) || len(p) == 0 {
+// gpuConvertPix hands a decoded image's Pix buffer to fb_convert_to_nrgba, starting at the byte offset of the
+// image's Rect.Min (PixOffset): sub-images share their parent's buffer and stride, which is all the library needs.
+// A palette index past the palette makes the call fail (FB_E_INVALID); the caller then runs the pure-Go loop, which
+// panics exactly as before.
+func gpuConvertPix(format C.int, p []uint8, off, stride int, r image.Rectangle, pal []uint16, dst *image.NRGBA) bool {
+	if r.Empty() || off < 0 || off >= len(p) {
 		return false
 	}
 	var pp *C.uint16_t
 	if len(pal) > 0 {
 		pp = (*C.uint16_t)(unsafe.Pointer(&pal[0]))
 	}
-	st := C.fb_convert_to_nrgba(format, (*C.uint8_t)(unsafe.Pointer(&p[0])), C.int(stride), C.int(r.Dx()), C.int(r.Dy()),
+	st := C.fb_convert_to_nrgba(format, (*C.uint8_t)(unsafe.Pointer(&p[off])), C.int(stride), C.int(r.Dx()), C.int(r.Dy()),
 		pp, C.int(len(pal)/4), pix(dst), C.int(dst.Stride))
 	return st == C.FB_OK
 }
@@ -200,11 +282,12 @@ func (s *ssimSession) score(decoded image.Image) (float64, bool) {
 	var out C.double
 	switch d := decoded.(type) {
 	case *image.YCbCr:
-		if d.Rect.Min != (image.Point{}) {
+		if d.Rect.Empty() || d.Rect.Min.X%2 != 0 || d.Rect.Min.Y%2 != 0 {
 			return 0, false
 		}
-		st := C.fb_ssim_ref_score_ycbcr(s.h, (*C.uint8_t)(unsafe.Pointer(&d.Y[0])), C.int(d.YStride),
-			(*C.uint8_t)(unsafe.Pointer(&d.Cb[0])), (*C.uint8_t)(unsafe.Pointer(&d.Cr[0])), C.int(d.CStride),
+		yo, co := d.YOffset(d.Rect.Min.X, d.Rect.Min.Y), d.COffset(d.Rect.Min.X, d.Rect.Min.Y)
+		st := C.fb_ssim_ref_score_ycbcr(s.h, (*C.uint8_t)(unsafe.Pointer(&d.Y[yo])), C.int(d.YStride),
+			(*C.uint8_t)(unsafe.Pointer(&d.Cb[co])), (*C.uint8_t)(unsafe.Pointer(&d.Cr[co])), C.int(d.CStride),
 			C.int(d.SubsampleRatio), &out)
 		return float64(out), st == C.FB_OK
 	case *image.NRGBA:

@@ -234,6 +234,14 @@ FB_API int fb_msssim_level_batch_dev(int device, void *stream, const uint8_t *a,
                               int rowStride, int w, int h, int n, uint8_t *thumbA, uint8_t *thumbB,
                               int64_t thumbImgStride, int thumbRowStride, int tw, int th, uint8_t *halfA,
                               uint8_t *halfB, int64_t halfImgStride, int halfRowStride);
+/* Two level steps from ONE read of level l (box.cu: box_fused2_kernel): the <= 512 px thumbnails of level l and of
+ * level l+1 (both tw x th) and the level-(l+2) image (w/4 x h/4), for both images of n pairs.  Level l+1 never exists
+ * in memory; bytes equal boxDownsample applied step by step (ssim.go:57-58, 354-360).  Returns 1 with nothing written
+ * when the geometry has no common box period (then call fb_msssim_level_batch_dev per level). */
+FB_API int fb_msssim_level2_batch_dev(int device, void *stream, const uint8_t *a, const uint8_t *b, int64_t imgStride, int rowStride,
+                               int w, int h, int n, uint8_t *thumb0A, uint8_t *thumb0B, uint8_t *thumb1A, uint8_t *thumb1B,
+                               int64_t thumbImgStride, int thumbRowStride, int tw, int th, uint8_t *quarterA, uint8_t *quarterB,
+                               int64_t quarterImgStride, int quarterRowStride);
 /* convertToNRGBA for n device-resident YCbCr images (planes of image i at base + i*ImgStride). */
 FB_API int fb_ycbcr_to_nrgba_batch_dev(int device, void *stream, const uint8_t *y, int64_t yImgStride, int yStride,
                                 const uint8_t *cb, const uint8_t *cr, int64_t cImgStride, int cStride, int w,

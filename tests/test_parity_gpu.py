@@ -301,6 +301,31 @@ def test_msssim_level_step_bit_exact(w, h, lib, oracle):
             assert np.array_equal(got_h[i].cpu().numpy(), oracle.box_downsample(img, w // 2, h // 2))
 
 
+@pytest.mark.parametrize("w,h", [(3840, 2160), (1920, 1080), (2048, 1152), (1200, 900), (7680, 4320)])
+def test_msssim_two_level_step_bit_exact(w, h, lib, oracle):
+    """Thumbnails of levels l and l+1 and the level-(l+2) image from ONE read (box.cu: box_fused2_kernel) == boxDownsample
+    applied step by step; level l+1 never touches memory.  Geometries without a common box period decline (None)."""
+    n = 1 if w > 4000 else 2
+    imgs_a = [S.noise_image(w, h, 140 + i, alpha="random") for i in range(n)]
+    imgs_b = [S.gradient_noise_image(w, h, 150 + i) for i in range(n)]
+    ok, tw, th = api.ssim_fast_dims(w, h)
+    ok1, tw1, th1 = api.ssim_fast_dims(w // 2, h // 2)
+    assert ok
+    got = batch.msssim_level2_batch(_to_dev(imgs_a), _to_dev(imgs_b), tw, th)
+    if not (ok1 and (tw1, th1) == (tw, th)) or got is None:
+        assert got is None or (tw1, th1) == (tw, th)
+        if got is None:
+            assert (w, h) == (1200, 900)          # 1200 -> 512 has no period <= 64 rows; the 16:9 sizes all do
+            return
+    t0a, t0b, t1a, t1b, qa, qb = got
+    for g0, g1, gq, imgs in ((t0a, t1a, qa, imgs_a), (t0b, t1b, qb, imgs_b)):
+        for i, img in enumerate(imgs):
+            half = oracle.box_downsample(img, w // 2, h // 2)
+            assert np.array_equal(g0[i].cpu().numpy(), oracle.box_downsample(img, tw, th))
+            assert np.array_equal(g1[i].cpu().numpy(), oracle.box_downsample(half, tw, th))
+            assert np.array_equal(gq[i].cpu().numpy(), oracle.box_downsample(half, w // 4, h // 4))
+
+
 def test_msssim_multi_level_vs_oracle(lib, oracle):
     # 2048x1152: levels 0 and 1 take the fused step (1024x576 still > 512), level 2 (512x288) scores directly
     a = S.gradient_noise_image(2048, 1152, 61)
