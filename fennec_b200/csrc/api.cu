@@ -650,7 +650,11 @@ static int pipeline_msssim(DevCtx *c, cudaStream_t s, ImgBatch a, ImgBatch b, in
         int tw, th, tw1, th1;
         // Two levels from one read (box.cu: box_fused2_kernel): levels l and l+1 both need a thumbnail and level l+2
         // exists; level l+1 then never exists in HBM.
-        if (msssim_level_fusable(plan, l, &tw, &th) && msssim_level_fusable(plan, l + 1, &tw1, &th1) && tw1 == tw && th1 == th) {
+        // (Levels below ~4 MP stay on the single-level step: per CTA the two thumbnails' outputs then weigh more than the
+        // read they save — 8K pairs: 0.178 ms for the fused 1920x1080 + 960x540 step against ~0.10 ms for the two single ones.)
+        static const long long f2MinPixels = [] { const char *e = getenv("FB_F2_MINPX"); return e ? atoll(e) : 4000000LL; }();
+        if ((long long)lw * lh >= f2MinPixels && msssim_level_fusable(plan, l, &tw, &th) && msssim_level_fusable(plan, l + 1, &tw1, &th1) &&
+            tw1 == tw && th1 == th) {
             if (run.count > 0 && (run.tw != tw || run.th != th)) FB_TRY(flush_run());
             const size_t mark = c->ws.off;
             if (run.count == 0) FB_TRY(open_run(l, tw, th));

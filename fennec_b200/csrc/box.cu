@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(kThreads) box_fused_kernel(const BoxFusedParam
 // ------------------------------------------------------------------------------------------------
 constexpr int kF2Threads = 256;
 constexpr int kF2MaxBand = 64;        // level-l rows per band
-constexpr int kF2MaxChunk = 512;      // level-l columns per chunk
-constexpr int kF2SmemBudget = 56 * 1024;
+constexpr int kF2MaxChunk = 2048;     // level-l columns per chunk
+constexpr int kF2SmemBudget = 96 * 1024;
 struct BoxFused2Params {
     const uint8_t *src[2];
     long long srcImgStride[2];
@@ -682,10 +682,12 @@ int launch_box_fused2(cudaStream_t s, const uint8_t *srcA, long long srcImgStrid
     const int band = common_period(srcH, th0, th1, 4, kF2MaxBand, &t0b, &t1b);
     const int colP = common_period(srcW, tw0, tw1, 8, kF2MaxChunk, &t0c, &t1c);
     if (!band || !colP) return 1;
-    // whole periods per CTA: up to 64 rows x ~480 columns, shrunk until the column sums of every thumbnail row of the
-    // band plus the level-(l+1) tile fit the shared-memory budget
+    // whole periods per CTA: up to 64 rows x ~1024 columns (one 4-column stripe per thread, each thread walking the whole
+    // band: 16 8K pairs take 1.60 / 1.28 / 1.12 / 1.23 ms at 240 / 480 / 960 / 1440 columns), shrunk until the column sums
+    // of every thumbnail row of the band fit the shared-memory budget
     const int rrep = kF2MaxBand / band;
-    int reps = 480 / colP > 0 ? 480 / colP : 1;
+    static const int chunkTarget = [] { const char *e = getenv("FB_F2_CHUNK"); int v = e ? atoi(e) : 0; return (v >= 64 && v <= kF2MaxChunk) ? v : 1024; }();
+    int reps = chunkTarget / colP > 0 ? chunkTarget / colP : 1;
     auto smem_for = [&](int reps_) {
         const size_t chunk = (size_t)colP * reps_;
         return (size_t)t0b * rrep * chunk * sizeof(uint2) + (size_t)t1b * rrep * (chunk / 2) * sizeof(uint2);
