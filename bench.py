@@ -347,6 +347,8 @@ def run_ours(args):
     ceiling_gbs = world * e2e_steps * E * BYTES_PER_PAIR / dt_copy / 1e9
     ceiling_mps = world * e2e_steps * E * MP_PER_PAIR / dt_copy
     del dst
+    api.init(list(range(torch.cuda.device_count())))   # back to "logical index == CUDA index" for the device-resident calls
+    api.set_device(local)
 
     # ---- extras: BASELINE.json configs 2-5 at their own sizes, device-resident, sharded under --gpus N ----
     extras = None
@@ -375,7 +377,8 @@ def run_ours(args):
                           "scores_match_per_rank_run": bool(ok)}
             except Exception as e:
                 single = {"unavailable": repr(e)[:200]}
-            api.init([local])
+            api.init(list(range(torch.cuda.device_count())))
+            api.set_device(local)
         barrier()
 
     if rank == 0:

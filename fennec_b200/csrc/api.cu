@@ -215,6 +215,8 @@ static int phys_device(int dev) {
     return g_devices[dev];
 }
 
+static DevCtx *ctx_phys(int phys);
+
 DevCtx *ctx(int dev) {
     int nd = ensure_init();
     if (nd < 0) return nullptr;
@@ -222,18 +224,25 @@ DevCtx *ctx(int dev) {
         set_error("device index %d out of range (fb_init selected %d device(s))", dev, nd);
         return nullptr;
     }
-    if ((int)t_state.ctxs.size() < nd) t_state.ctxs.resize(nd, nullptr);
-    if (cudaSetDevice(phys_device(dev)) != cudaSuccess) {
+    // Contexts, the pool and the table cache are keyed by the PHYSICAL device, so a later fb_init with another
+    // device list (which renumbers the logical indices) can never hand a thread a stream of the wrong GPU.
+    return ctx_phys(phys_device(dev));
+}
+
+static DevCtx *ctx_phys(int phys) {
+    if (phys < 0) return nullptr;
+    if ((int)t_state.ctxs.size() <= phys) t_state.ctxs.resize(phys + 1, nullptr);
+    if (cudaSetDevice(phys) != cudaSuccess) {
         cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
         return nullptr;
     }
-    DevCtx *c = t_state.ctxs[dev];
+    DevCtx *c = t_state.ctxs[phys];
     if (c) return c;
     {
         std::lock_guard<std::mutex> lk(g_pool.mu);
-        if ((int)g_pool.idle.size() > dev && !g_pool.idle[dev].empty()) {
-            c = g_pool.idle[dev].back();
-            g_pool.idle[dev].pop_back();
+        if ((int)g_pool.idle.size() > phys && !g_pool.idle[phys].empty()) {
+            c = g_pool.idle[phys].back();
+            g_pool.idle[phys].pop_back();
         }
     }
     if (!c) {
@@ -247,9 +256,9 @@ DevCtx *ctx(int dev) {
             destroy_ctx(c);
             return nullptr;
         }
-        c->dev = dev;
+        c->dev = phys;
     }
-    t_state.ctxs[dev] = c;
+    t_state.ctxs[phys] = c;
     return c;
 }
 
@@ -917,13 +926,13 @@ void fb_shutdown(void) {
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
     for (DevCtx *c : victims) {
-        cudaSetDevice(phys_device(c->dev));
+        cudaSetDevice(c->dev);   // physical id
         destroy_ctx(c);
     }
     {
         std::lock_guard<std::mutex> lk(g_tab_mu);
         for (auto &kv : g_lanczos) {
-            cudaSetDevice(phys_device(kv.first.first));
+            cudaSetDevice(kv.first.first);   // physical id
             cudaDeviceSynchronize();
             free_table(kv.second.t);
         }
@@ -1503,7 +1512,7 @@ static size_t ycbcr_scratch(int w, int h, int cw, int ch) {
 }  // namespace fb
 
 struct fb_ssim_ref {
-    int dev, w, h;       // device and dims of the reference image
+    int dev, w, h;       // PHYSICAL device and dims of the reference image
     int tw, th, pitch;   // what is kept: the SSIMFast thumbnail (or the image itself when <= 512 px)
     uint8_t *img;        // cudaMalloc'ed, owned
 };
@@ -1687,14 +1696,16 @@ int fb_ssim_ref_create(const uint8_t *src, int stride, int w, int h, fb_ssim_ref
 
 void fb_ssim_ref_destroy(fb_ssim_ref *ref) {
     if (!ref) return;
-    if (DevCtx *c = ctx(ref->dev)) { (void)c; cudaFree(ref->img); }
+    ApiScope scope_;
+    if (DevCtx *c = ctx_phys(ref->dev)) { (void)c; cudaFree(ref->img); }
     delete ref;
 }
 
 int fb_ssim_ref_score_nrgba(const fb_ssim_ref *ref, const uint8_t *img, int stride, double *score) {
     if (!ref || !score) { set_error("fb_ssim_ref_score_nrgba: null argument"); return FB_E_INVALID; }
     FB_TRY(check_img("fb_ssim_ref_score_nrgba", img, stride, ref->w, ref->h));
-    DevCtx *c = ctx(ref->dev);
+    ApiScope scope_;
+    DevCtx *c = ctx_phys(ref->dev);
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     FB_TRY(reserve(c, c->stream, (size_t)dev_pitch(ref->w) * ref->h + ref_score_scratch(ref) + 4096, 256));
     uint8_t *d;
@@ -1708,7 +1719,8 @@ int fb_ssim_ref_score_ycbcr(const fb_ssim_ref *ref, const uint8_t *y, int yStrid
     if (!ref || !score) { set_error("fb_ssim_ref_score_ycbcr: null argument"); return FB_E_INVALID; }
     int cw, ch;
     FB_TRY(check_planes("fb_ssim_ref_score_ycbcr", y, yStride, cb, cr, cStride, ref->w, ref->h, ratio, &cw, &ch));
-    DevCtx *c = ctx(ref->dev);
+    ApiScope scope_;
+    DevCtx *c = ctx_phys(ref->dev);
     if (!c) return ensure_init() < 0 ? FB_E_NOGPU : FB_E_CUDA;
     FB_TRY(reserve(c, c->stream, ycbcr_scratch(ref->w, ref->h, cw, ch) + ref_score_scratch(ref), 256));
     uint8_t *d;

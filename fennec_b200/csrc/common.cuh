@@ -48,7 +48,7 @@ struct Arena {
 };
 
 struct DevCtx {
-    int dev = -1;
+    int dev = -1;                    // PHYSICAL CUDA device of the stream and arenas
     cudaStream_t stream = nullptr;  // owned stream used by the host entry points
     Arena ws;                        // device scratch (grow-only)
     Arena pin;                       // pinned host scratch (scores, small tables)

@@ -19,6 +19,7 @@
 // This kernel is FMA-pipe-bound, not HBM-bound: ~87 FP32 lane-ops per pixel (profiles/).
 #include "common.cuh"
 
+#include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time through cudart, no libcuda link)
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -716,6 +717,218 @@ __device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
     return dsum;
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA variant of walk_strip2 (FB_SSIM_MODE=5): the pixel rows of a strip are staged by the Tensor Memory Accelerator —
+// one elected lane issues two cp.async.bulk.tensor.3d copies (image a and image b, boxes of 128 pixels x 4 or 8 rows out
+// of a {w, h, n} tensor map) per stage into a shared-memory ring of 16 rows and arms the stage's mbarrier with the
+// byte count; the warp waits on the barrier's phase parity before the first row of a stage.  Compared with the
+// per-lane cp.async ring this removes the per-row address arithmetic, LDGSTS, commit and wait_group of every lane
+// (about 9 instructions per row) for about 4 per row in one lane, and the tensor map zero-fills everything right of /
+// below the image, so ragged right edges need no re-aimed loads.  (Round 1 measured a 1-D bulk copy PER ROW slower
+// than cp.async: the elected-lane issue path then cost ~60 instructions per 512-byte row; with 2-D boxes of four
+// rows it is amortised.)  Everything after the pixel fetch is walk_strip2.
+// ------------------------------------------------------------------------------------------------
+// <rows per stage, stages in flight> (powers of two, rows <= 8): <4, 4> (FB_SSIM_MODE=5) and <8, 2> (FB_SSIM_MODE=6)
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TW_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TD_%=;\n"
+        "bra TW_%=;\n"
+        "TD_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+struct TmaCtx {
+    const CUtensorMap *ta, *tb;
+    int X0, Y0, img;          // strip origin (pixels / rows) and image index
+    uint32_t ring, bars;      // shared-memory addresses: kTmaStages x kTmaStageBytes, kTmaStages mbarriers
+    const uint8_t *ringP;
+};
+
+template <int kTmaRows, int kTmaStages>
+__device__ __forceinline__ double walk_strip_tma(const StripCtx<4> &q, const TmaCtx &t) {
+    constexpr int CPL = 4;
+    constexpr uint32_t kTmaStageBytes = 2u * kTmaRows * 512u;   // both images
+    const int nIn = q.nIn, lane = q.lane;
+    const float2 s2 = make_float2(kLumaScale, kLumaScale);
+    const float2 K2 = make_float2(q.K, q.K);
+    float2 g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
+    HConsts hk;
+    hk.c = q.c;
+    hk.kTh = fmaf(q.c, q.c, 0.5f * kC1f);
+    hk.qpInit = make_float2(kC2f, 0.5f * kC2f);
+    hk.one_two = make_float2(1.f, 2.f);
+    hk.neg2 = make_float2(-1.f, -1.f);
+    float2 rab[8][CPL], rqp[8][CPL];
+    // stage st <- rows [row0, row0 + kTmaRows) of both images (rows below the image arrive as zeros)
+    auto issue = [&](int st, int row0) {
+        const uint32_t bar = t.bars + 8u * st, dst = t.ring + (uint32_t)st * kTmaStageBytes;
+        mbar_expect_tx(bar, kTmaStageBytes);
+        tma_load_3d(dst, t.ta, t.X0, t.Y0 + row0, t.img, bar);
+        tma_load_3d(dst + kTmaRows * 512u, t.tb, t.X0, t.Y0 + row0, t.img, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kTmaStages; st++)
+            if (st * kTmaRows < nIn) issue(st, st * kTmaRows);
+    }
+    __syncwarp();
+    const uint8_t *myP = t.ringP + lane * 16;
+    // planes of row R (slot S = R & 7, so R's position inside its stage is known at compile time)
+#define WT_PLANES(S, R)                                                                         \
+    {                                                                                           \
+        const int st_ = ((R) / kTmaRows) & (kTmaStages - 1);                                    \
+        if (((S) & (kTmaRows - 1)) == 0) mbar_wait_parity(t.bars + 8u * st_, ((R) / (kTmaRows * kTmaStages)) & 1); \
+        const uint8_t *rb_ = myP + (size_t)st_ * kTmaStageBytes + ((S) & (kTmaRows - 1)) * 512; \
+        const uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                                \
+        const uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + kTmaRows * 512);               \
+        const uint32_t xa_[4] = {va_.x, va_.y, va_.z, va_.w}, xb_[4] = {vb_.x, vb_.y, vb_.z, vb_.w}; \
+        _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
+            float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
+            float2 tt = __ffma2_rn(f, s2, K2);                                                  \
+            float2 sq = __fmul2_rn(tt, tt);                                                     \
+            rab[S][i] = tt;                                                                     \
+            rqp[S][i] = make_float2(sq.x + sq.y, tt.x * tt.y);                                  \
+        }                                                                                       \
+        if (((S) & (kTmaRows - 1)) == kTmaRows - 1) {   /* last row of the stage: every lane has read it; refill it */ \
+            __syncwarp();                                                                       \
+            const int next_ = (R) + 1 + kTmaRows * (kTmaStages - 1);                            \
+            if (lane == 0 && next_ < nIn) issue(st_, next_);                                    \
+        }                                                                                       \
+    }
+#define WT_VTAPS(S, V)                                                                          \
+    _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                           \
+        float2 vab = __fmul2_rn(rab[(S + 1) & 7][i], g2[0]);                                    \
+        float2 vqp = __fmul2_rn(rqp[(S + 1) & 7][i], g2[0]);                                    \
+        _Pragma("unroll") for (int j = 1; j < 8; j++) {                                         \
+            vab = __ffma2_rn(rab[(S + 1 + j) & 7][i], g2[j], vab);                              \
+            vqp = __ffma2_rn(rqp[(S + 1 + j) & 7][i], g2[j], vqp);                              \
+        }                                                                                       \
+        V[i] = make_float4(vab.x, vab.y, vqp.x, vqp.y);                                         \
+    }
+#pragma unroll
+    for (int r = 0; r < 7; r++) WT_PLANES(r, r)
+
+    float fs[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) fs[i] = 0.f;
+    constexpr int kVLanes = 36, kVBuf = CPL * kVLanes;
+    bool okA[CPL], okB[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) okA[i] = q.valid[i];
+
+#pragma unroll 1
+    for (int r = 7; r < nIn; r += 2) {
+        float4 vA[CPL], vB[CPL];
+        // A stage is only waited for when one of its rows exists (r + 1 < nIn), so the odd tail row reuses the planes of
+        // an older row instead of waiting on a barrier nobody armed; its outputs are masked.
+        const bool second = r + 1 < nIn;
+#define WT_STEP(S0, S1)                                                                         \
+    case S0: {                                                                                  \
+        WT_PLANES(S0, r)                                                                        \
+        WT_VTAPS(S0, vA)                                                                        \
+        if (second) WT_PLANES(S1, r + 1)                                                        \
+        WT_VTAPS(S1, vB)                                                                        \
+    } break;
+        switch (r & 7) {
+            WT_STEP(7, 0) WT_STEP(1, 2) WT_STEP(3, 4)
+            default: { WT_PLANES(5, r) WT_VTAPS(5, vA) if (second) WT_PLANES(6, r + 1) WT_VTAPS(6, vB) } break;
+        }
+#undef WT_STEP
+        float4 *vbA = q.vb0 + ((((r - 7) >> 1) & 1) ? 2 * kVBuf : 0) + lane;
+        float4 *vbB = vbA + kVBuf;
+#pragma unroll
+        for (int i = 0; i < CPL; i++) { vbA[i * kVLanes] = vA[i]; vbB[i * kVLanes] = vB[i]; }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CPL; i++) okB[i] = q.valid[i] && second;
+        hpass_formula(vA, vbA, g2, hk, okA, fs);
+        hpass_formula(vB, vbB, g2, hk, okB, fs);
+    }
+#undef WT_PLANES
+#undef WT_VTAPS
+    double dsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    return dsum;
+}
+
+// One warp per block = one strip segment; aligned inputs only (the host falls back to the cp.async kernel otherwise).
+template <int kTmaRows, int kTmaStages>
+__global__ void __launch_bounds__(32, 8) ssim_strip_tma_kernel(const __grid_constant__ CUtensorMap ta, const __grid_constant__ CUtensorMap tb,
+                                                               const SsimParams p) {
+    constexpr int CPL = 4, OUTC = 120;
+    constexpr uint32_t kTmaStageBytes = 2u * kTmaRows * 512u;
+    __shared__ __align__(128) uint8_t ring[kTmaStages * kTmaStageBytes];
+    __shared__ float4 vbuf[4][CPL * 36];
+    __shared__ __align__(8) unsigned long long bars[kTmaStages];
+    const int lane = threadIdx.x;
+    const long long segsPerImg = (long long)p.nsx * p.nsy;
+    const long long seg = blockIdx.x;
+    const int img = (int)(seg / segsPerImg);
+    const int rseg = (int)(seg - (long long)img * segsPerImg);
+    const int sy = rseg / p.nsx, sx = rseg - sy * p.nsx;
+    const int X0 = sx * OUTC, Y0 = sy * p.rs;
+    const int nOut = min(p.rs, (p.h - 8) - Y0);
+    const int xl = X0 + CPL * lane;
+    if (lane < kTmaStages) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[lane])), "r"(1));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < CPL; i++) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) vbuf[v][i * 36 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __syncwarp();
+    StripCtx<CPL> q;
+    q.nIn = nOut + 7;
+    q.lane = lane;
+    q.nvalid = CPL;
+    q.rowStrideA = p.rowStrideA;
+    q.rowStrideB = p.rowStrideB;
+    q.vb0 = &vbuf[0][0];
+    q.vb1 = &vbuf[1][0];
+    q.ring = ring;
+    q.pa = q.pb = nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; j++) q.g[j] = p.g[j];
+#pragma unroll
+    for (int i = 0; i < CPL; i++) q.valid[i] = (CPL * lane + i < OUTC) && (xl + i < p.w - 8);
+    {   // centring constant: luma of image a at the strip's centre pixel (same rule as ssim_strip_kernel)
+        const uint8_t *ia = p.a + (long long)img * p.imgStrideA;
+        int cx = min(X0 + OUTC / 2, p.w - 1), cy = min(Y0 + q.nIn / 2, p.h - 1);
+        float f = luma_magic(ld_nc_u32(ia + (long long)cy * p.rowStrideA + (long long)cx * 4));
+        q.K = -(f * kLumaScale);
+        q.c = -fmaf(8388608.0f, kLumaScale, q.K);
+    }
+    TmaCtx t;
+    t.ta = &ta; t.tb = &tb;
+    t.X0 = X0; t.Y0 = Y0; t.img = img;
+    t.ring = smem_u32(ring);
+    t.bars = smem_u32(bars);
+    t.ringP = ring;
+    double dsum = walk_strip_tma<kTmaRows, kTmaStages>(q, t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    if (lane == 0) p.partials[seg] = dsum * 4.0;
+}
+
 // Defaults from the round-2 sweep on 64 4K pairs (profiles/r2_k1_variants.txt): walk_strip / 4 warps per block 2.062 ms,
 // walk_strip / 1 warp 1.882, walk_strip2 / 2 warps 1.956, walk_strip2 / 1 warp 1.769, walk_strip_pipe 2.272.
 #ifndef FB_SSIM_MODE_DEFAULT
@@ -725,7 +938,7 @@ __device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
 #define FB_SSIM_WPB_DEFAULT 1
 #endif
 
-// MODE 0: walk_strip, 1: walk_strip_pipe, 2: walk_strip2, 3: walk_stripN<4>, 4: walk_stripN<2>.  WPB = warps (independent strips) per block: warps never
+// MODE 0: walk_strip, 1: walk_strip_pipe, 2: walk_strip2, 3: walk_stripN<4>, 4: walk_stripN<2> (5: ssim_strip_tma_kernel).  WPB = warps (independent strips) per block: warps never
 // synchronise with each other, so the block size only sets the granularity at which the SM's registers are handed out:
 // 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at ~200 registers without a cap below 8 blocks:
 // 9-10 warps per SM, a third warp on one or two schedulers).
@@ -1177,6 +1390,34 @@ static void prepare_kernel(K kernel, int threads, const char *name) {
         if (!done_) { prepare_kernel(kernel, threads, #kernel); done_ = true; } \
     } while (0)
 
+// {w, h, n} tensor map over a batch of NRGBA images (pixels as 32-bit elements), boxes of 128 pixels x kTmaRows rows.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+static bool make_image_map(CUtensorMap *m, const uint8_t *base, long long imgStride, int rowStride, int w, int h, int n, int boxRows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t img = imgStride > 0 ? (cuuint64_t)imgStride : (cuuint64_t)rowStride * (cuuint64_t)h;
+    const cuuint64_t strides[2] = {(cuuint64_t)rowStride, img};
+    const cuuint32_t box[3] = {128u, (cuuint32_t)boxRows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Scores for n equal-sized pairs.  Dispatch of ssim.go:35-42: w<8||h<8 → pixelSSIM, else windowed.
 int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, long long imgStrideA,
                 long long imgStrideB, int rowStrideA, int rowStrideB, int w, int h, int n,
@@ -1224,7 +1465,7 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
             const char *e = getenv("FB_SSIM_PIPE");
             if (e && e[0] == '1') return 1;
             const char *m = getenv("FB_SSIM_MODE");
-            return (m && m[0] >= '0' && m[0] <= '4') ? m[0] - '0' : FB_SSIM_MODE_DEFAULT;
+            return (m && m[0] >= '0' && m[0] <= '6') ? m[0] - '0' : FB_SSIM_MODE_DEFAULT;
         }();
         static const int wpb = [] { const char *e = getenv("FB_SSIM_WPB"); return (e && e[0] == '1') ? 1 : (e && e[0] == '4') ? 4 : FB_SSIM_WPB_DEFAULT; }();
 #define FB_LAUNCH_STRIP(MODE_, WPB_)                                                           \
@@ -1232,7 +1473,24 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
         FB_PREPARE((ssim_strip_kernel<4, MODE_, WPB_>), 32 * WPB_);                                \
         ssim_strip_kernel<4, MODE_, WPB_><<<(unsigned)((segs + WPB_ - 1) / WPB_), 32 * WPB_, 0, s>>>(p); \
     } while (0)
-        if (mode == 1) FB_LAUNCH_STRIP(1, 4);
+        bool done = false;
+        if ((mode == 5 || mode == 6) && p.vecOK && (imgStrideA > 0 || n == 1) && (imgStrideB > 0 || n == 1)) {   // TMA-staged rows
+            CUtensorMap ta, tb;
+            const int boxRows = mode == 5 ? 4 : 8;
+            if (make_image_map(&ta, a, imgStrideA, rowStrideA, w, h, n, boxRows) && make_image_map(&tb, b, imgStrideB, rowStrideB, w, h, n, boxRows)) {
+                if (mode == 5) {
+                    FB_PREPARE((ssim_strip_tma_kernel<4, 4>), 32);
+                    ssim_strip_tma_kernel<4, 4><<<(unsigned)segs, 32, 0, s>>>(ta, tb, p);
+                } else {
+                    FB_PREPARE((ssim_strip_tma_kernel<8, 2>), 32);
+                    ssim_strip_tma_kernel<8, 2><<<(unsigned)segs, 32, 0, s>>>(ta, tb, p);
+                }
+                done = true;
+            }
+        }
+        if (done) {}
+        else if (mode >= 5) FB_LAUNCH_STRIP(2, 1);   // unaligned buffers / no driver entry point: the cp.async twin
+        else if (mode == 1) FB_LAUNCH_STRIP(1, 4);
         else if (mode == 3) FB_LAUNCH_STRIP(3, 1);
         else if (mode == 4) FB_LAUNCH_STRIP(4, 1);
         else if (mode == 2 && wpb == 1) FB_LAUNCH_STRIP(2, 1);
