@@ -153,9 +153,10 @@ def load():
     """Load the shared library (no GPU needed for loading or for the host-only helpers)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(SO_PATH):
-            raise FennecError(FB_E_INVALID, f"{SO_PATH} not built — run `python -m fennec_b200.build`")
-        lib = C.CDLL(SO_PATH)
+        path = os.environ.get("FB_LIB_PATH") or SO_PATH   # FB_LIB_PATH: tuning builds of tools/build_variant.sh
+        if not os.path.exists(path):
+            raise FennecError(FB_E_INVALID, f"{path} not built — run `python -m fennec_b200.build`")
+        lib = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError if the header and the binary drift apart
             fn.restype = res

@@ -17,6 +17,7 @@
 #include <string>
 #include <thread>
 #include <utility>
+#include <cmath>
 #include <vector>
 
 namespace fb {
@@ -134,6 +135,30 @@ static void detect_int_ratio(const int *start, const int *index, const double *w
     float ws = 0.f;
     for (int k = 0; k < T; k++) { ir->w[k] = (float)weight[start[mid] + k]; ws += ir->w[k]; }
     ir->wsum = ws;
+    // Fully opaque windows: the reference computes r = sum(R * (255 * w)), a = sum(255 * w), v = r * (1/a), all in
+    // binary64 (resize.go:99-110) — sum(R * w) / W with W = sum(w), up to ~1e-13.  The kernel evaluates sum(R * wn) with
+    // wn = fl32(w / W) as a chain of FP32 FMAs in tap order.  Bound: the weights are off by <= 2^-24 |w/W| each
+    // (255 * 2^-24 * sum|wn| in the sum) and FMA k rounds a partial sum of magnitude <= 255 * P_k, P_k = sum_{s<=k} |wn_s|
+    // (2^-24 each); 5 % margin plus 1e-6 for the binary64 roundings and the last-bit differences between the weight
+    // rows of different destinations.  The alpha byte clampF(a) is the same for every such window unless a sits next to
+    // a tie, in which case the shortcut stays off.
+    double W = 0.0, a64 = 0.0;
+    for (int k = 0; k < T; k++) { W += weight[start[mid] + k]; a64 += 255.0 * weight[start[mid] + k]; }
+    for (int k = 0; k < 28; k++) ir->wn[k] = 0.f;
+    ir->Eo = 0.f; ir->opaqueA = 0u;
+    const double fracA = a64 - std::floor(a64);
+    if (W > 0.5 && a64 > 1.0 && a64 < 1e6 && std::fabs(fracA - 0.5) > 1e-6) {
+        double wabsn = 0.0, psum = 0.0, P = 0.0;
+        for (int k = 0; k < T; k++) {
+            ir->wn[k] = (float)(weight[start[mid] + k] / W);
+            wabsn += std::fabs((double)ir->wn[k]);
+        }
+        for (int k = 0; k < T; k++) { P += std::fabs((double)ir->wn[k]); psum += P; }
+        ir->Eo = (float)(255.0 * 5.9604644775390625e-08 * (wabsn + psum) * 1.05 + 1e-6);
+        const double ra = std::floor(a64 + 0.5);   // clampF: half away from zero, a64 > 0
+        const unsigned ab = ra >= 255.0 ? 255u : (unsigned)ra;
+        if (ir->Eo < 0.05f && ab > 0u) ir->opaqueA = ab << 24;
+    }
 }
 
 // Grouped layout (see resize.cu ResizeParams): returns false when some destination's taps are not contiguous.

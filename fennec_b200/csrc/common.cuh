@@ -172,6 +172,10 @@ struct IntRatioInfo {
     int ratio = 0, taps = 0, off = 0, dLo = 0, dHi = 0;
     float wsum = 0.f;
     float w[28];
+    // fully opaque windows (resize.cu int_ratio_window): normalised weights, their FP32 error bound, the alpha byte
+    float wn[28];
+    float Eo = 0.f;
+    unsigned int opaqueA = 0;   // alpha byte << 24; 0 disables the shortcut
 };
 int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,

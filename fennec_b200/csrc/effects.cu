@@ -311,18 +311,29 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_h_fast_kernel(const B
             for (int k = 0; k < (34 * 4 + 31) / 32; k++)
                 if (k < 4 || lane < 34 * 4 - 128) cp_async16(s0 + k * 8 * kChunkB, g0 + k * 512);
         } else {
-#pragma unroll 1
-            for (int v = lane; v < 34 * 4; v += 32) {
-                const int chunk = v >> 2, quad = v & 3;
-                const int px0 = xs + (chunk - 1) * kTile + quad * 4;
-                uint8_t *dstp = st + chunk * kChunkB + quad * 16;
-                uint32_t t[4];
+            // Edge blocks (the first and the last of a row: 2 of 8 at 3840 px).  Quads that lie inside the row still go
+            // through cp.async; only the few that cross an end are loaded by hand with clamp-to-edge.  Unrolled, so the
+            // hand loads of different quads are independent.  [A rolled load -> store loop here left every edge warp
+            // waiting on four dependent DRAM round trips per row: 23 % of the kernel's stall samples, profiles/r2s2.]
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    int sx = min(max(px0 + i, 0), p.w - 1);
-                    t[i] = ld_nc_u32(srow + (long long)sx * 4);
+            for (int k = 0; k < (34 * 4 + 31) / 32; k++) {
+                const int v = lane + 32 * k;
+                if (k < 4 || v < 34 * 4) {
+                    const int chunk = v >> 2, quad = v & 3;
+                    const int px0 = xs + (chunk - 1) * kTile + quad * 4;
+                    uint8_t *dstp = st + chunk * kChunkB + quad * 16;
+                    if (vecOK && px0 >= 0 && px0 + 4 <= p.w) {
+                        cp_async16(dstp, srow + (long long)px0 * 4);
+                    } else {
+                        uint32_t t[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            int sx = min(max(px0 + i, 0), p.w - 1);
+                            t[i] = ld_nc_u32(srow + (long long)sx * 4);
+                        }
+                        *reinterpret_cast<uint4 *>(dstp) = make_uint4(t[0], t[1], t[2], t[3]);
+                    }
                 }
-                *reinterpret_cast<uint4 *>(dstp) = make_uint4(t[0], t[1], t[2], t[3]);
             }
         }
         cp_async_commit_group();
@@ -385,15 +396,28 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_h_fast_kernel(const B
 #endif
 constexpr int kVSeg = FB_BLUR_VSEG;  // rows per thread segment (2160 = 9 * 240; halo 12/240)
 
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// The kTile new rows of the NEXT chunk travel through a per-warp shared-memory buffer filled by cp.async (two buffers,
+// alternating), not through registers: ptxas put the 16 prefetch LDGs of the register version on the same scoreboard
+// as the release of their address registers, so the first instruction of the tap block that reused one of those
+// registers waited for ALL the loads — the prefetch was fully exposed (23.6 % of the stall samples on one PRMT,
+// profiles/r2s2_blur).  cp.async has no destination registers; its completion is an explicit wait_group at the end of
+// the chunk.  Whole-warp-inside-the-row segments copy 16 bytes per lane (8 lanes per row, 4 rows per instruction);
+// otherwise every lane copies its own (clamped) column 4 bytes at a time.
 template <int R, int WPB>
 __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const BlurParams p) {
     constexpr int NIN = kTile + 2 * R;
     __shared__ uint32_t ambQ[WPB][kAmbQ];
     __shared__ int ambN[WPB];
+    __shared__ __align__(16) uint32_t nxtBuf[WPB][2][kTile][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) ambN[warp] = 0;
     __syncwarp();
-    const int x = blockIdx.x * (32 * WPB) + threadIdx.x, img = blockIdx.z;
+    const int xw = blockIdx.x * (32 * WPB) + warp * 32;   // first column of this warp
+    const int x = xw + lane, img = blockIdx.z;
     const int ys = blockIdx.y * kVSeg;
     const int yEnd = min(ys + kVSeg, p.h);
     const bool active = x < p.w;   // inactive lanes still take part in the warp's queue drains
@@ -403,27 +427,34 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const B
     const uint8_t *scol = simg + (long long)xc * 4;
     uint8_t *dcol = dimg + (long long)xc * 4;
     const float lim = 0.5f - p.eps;
+    const bool wide = xw + 32 <= p.w && ((((uintptr_t)p.src | (uintptr_t)p.srcImgStride | (uintptr_t)p.srcRowStride) & 15) == 0);
     auto ld_row = [&](int y) -> uint32_t {
         const int sy = min(max(y, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
         return __ldg(reinterpret_cast<const uint32_t *>(scol + (long long)sy * p.srcRowStride));
     };
-    uint32_t raw[NIN], nxt[kTile];
+    // rows yn .. yn + kTile - 1 (clamped to the last row) of this warp's 32 columns into buf[kTile][32]
+    auto stage_rows = [&](int yn, uint32_t (*buf)[32]) {
+        if (wide) {
+            const uint8_t *g0 = simg + (long long)xw * 4 + (lane & 7) * 16;
+#pragma unroll
+            for (int k = 0; k < kTile / 4; k++) {
+                const int r = (lane >> 3) + 4 * k;
+                cp_async16(&buf[r][(lane & 7) * 4], g0 + (long long)min(yn + r, p.h - 1) * p.srcRowStride);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kTile; r++) cp_async4(&buf[r][lane], scol + (long long)min(yn + r, p.h - 1) * p.srcRowStride);
+        }
+        cp_async_commit_group();
+    };
+    uint32_t raw[NIN];
 #pragma unroll
     for (int i = 0; i < NIN; i++) raw[i] = ld_row(ys - R + i);
+    int par = 0;
 #pragma unroll 1
-    for (int y0 = ys; y0 < yEnd; y0 += kTile) {
+    for (int y0 = ys; y0 < yEnd; y0 += kTile, par ^= 1) {
         const bool more = y0 + kTile < yEnd;
-        if (more) {
-            const int yn = y0 + kTile + R;  // first row of the next chunk's new rows
-            if (yn + kTile <= p.h) {       // no clamping: one running pointer
-                const uint8_t *np = scol + (long long)yn * p.srcRowStride;
-#pragma unroll
-                for (int i = 0; i < kTile; i++, np += p.srcRowStride) nxt[i] = __ldg(reinterpret_cast<const uint32_t *>(np));
-            } else {
-#pragma unroll
-                for (int i = 0; i < kTile; i++) nxt[i] = ld_row(yn + i);
-            }
-        }
+        if (more) stage_rows(y0 + kTile + R, nxtBuf[warp][par]);   // first new row of the next chunk
         float2 accRG[kTile], accB[kTile / 2];
         blur_taps_fp32<R, NIN, R>(raw, p.w32, accRG, accB);
         uint32_t out[kTile];
@@ -443,13 +474,14 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const B
             }
         }
         if (active) amb_push(ambMask, x, y0, 0, 1, ambQ[warp], &ambN[warp]);  // exact FP64 path deferred (see amb_drain)
-        __syncwarp();
+        if (more) cp_async_wait_group<0>();
+        __syncwarp();   // queue pushes and (wide) the other lanes' copies are visible; the buffer of the previous chunk is free
         amb_drain<true>(false, lane, ambQ[warp], &ambN[warp], simg, p.srcRowStride, dimg, p.dstRowStride, p.w, p.h, R, p.kernel);
         if (more) {
 #pragma unroll
             for (int i = 0; i < 2 * R; i++) raw[i] = raw[i + kTile];
 #pragma unroll
-            for (int i = 0; i < kTile; i++) raw[2 * R + i] = nxt[i];
+            for (int i = 0; i < kTile; i++) raw[2 * R + i] = nxtBuf[warp][par][i][lane];
         }
     }
     __syncwarp();

@@ -236,6 +236,9 @@ struct IntRatioParams {
     int dLo, dHi;   // destinations in [dLo, dHi) are interior (identical weights, no clipping)
     float wsum;     // FP32 sum of the weights
     float w[28];    // the T shared weights (T <= 24 used)
+    float wn[28];   // w / sum(w): a fully opaque window is v = sum(R * wn), no premultiply and no division
+    float Eo;       // |FP32 value - reference value| of that sum (detect_int_ratio, api.cu)
+    uint32_t opaqueA;  // alpha byte << 24 such a window produces; 0: shortcut disabled
 };
 
 #ifndef FB_LZ_ROWS
@@ -250,55 +253,88 @@ __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// kOut interior outputs from one window of packed pixels (compile-time tap indices).
-template <int R, int T>
-__device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[T + (kOut - 1) * R], const IntRatioParams &q,
+// max(min(round(v), 255), 0) from t = v + 1.5 * 2^23 (|v| < 2^22): the low 23 bits of t are 2^22 + round(v), so one
+// VIADDMNMX.RELU on the bit pattern subtracts the magic, clamps above and below.
+__device__ __forceinline__ uint32_t clamp255_from_magic(float t) {
+    return (uint32_t)__viaddmin_s32_relu(__float_as_int(t), -0x4B400000, 255);
+}
+
+// kOut interior outputs from one window of packed pixels (compile-time tap indices); the window starts at raw[LEAD].
+template <int R, int T, int LEAD, int NRAW>
+__device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], const IntRatioParams &q,
                                                  uint32_t (&outv)[kOut], bool (&ambv)[kOut]) {
     constexpr int NIN = T + (kOut - 1) * R;
+    static_assert(NRAW >= NIN + LEAD && kOut % 2 == 0, "window does not fit");
     const ResizeParams &p = q.base;
     uint32_t andA = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < NIN; i++) andA &= raw[i];
+    for (int i = 0; i < NIN; i++) andA &= raw[LEAD + i];
     // Channel-paired accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar
     // (w[t] straight from the parameter bank) and B (and alpha) ride in a second accumulator.  [An earlier
     // version paired two OUTPUTS per FFMA2, which needs the weight pairs (w[t], w[t-R]) in registers: ptxas
     // rebuilt every pair with two MOVs per FFMA2 — 3x the instructions, profiles/r1b_*.]
     const float2 kMagic2 = make_float2(-8388608.0f, -8388608.0f);
-    if ((andA >> 24) == 0xFFu) {  // fully opaque window: v = sum(R*w) / sum(w)
-        float2 accRG[kOut];
-        float accB[kOut];
+    if (q.opaqueA != 0u && (andA >> 24) == 0xFFu) {
+        // Fully opaque window: the reference's r/a = sum(R*255*w) / sum(255*w) is sum(R * w/W) up to 1e-13, so the
+        // normalised weights give the value directly: no premultiply, no reciprocal, a constant alpha byte and a
+        // constant error bound Eo (detect_int_ratio).  Round + clamp + pack: magic-number rounding as packed FADD2
+        // on the (R,G) pair and on the B values of two outputs, one VIADDMNMX.RELU per channel (Lanczos overshoots,
+        // so the clamp is real), three PRMTs.  [The general finish_fp32 — reciprocal, per-pixel bound, float clamps —
+        // was 55 of the 168 instructions per output, profiles/r2s2_lanczos.]
+        float2 accRG[kOut], accB[kOut / 2];
 #pragma unroll
-        for (int j = 0; j < kOut; j++) { accRG[j] = make_float2(0.f, 0.f); accB[j] = 0.f; }
+        for (int j = 0; j < kOut; j++) accRG[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < kOut / 2; m++) accB[m] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
-            const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
-                                                     __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
-            const float bl = byte_f(raw[i], 2);
+            const uint32_t px = raw[LEAD + i];
+            const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u)),
+                                                     __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7541u))), kMagic2);
+            const float bl = byte_f(px, 2);
 #pragma unroll
             for (int j = 0; j < kOut; j++) {
                 const int t = i - j * R;  // tap of input i for output j
                 if (t >= 0 && t < T) {
-                    const float w = q.w[t >= 0 && t < T ? t : 0];
+                    const float w = q.wn[t >= 0 && t < T ? t : 0];
                     accRG[j] = __ffma2_rn(rg, make_float2(w, w), accRG[j]);
-                    accB[j] = fmaf(bl, w, accB[j]);
+                    if (j & 1) accB[j / 2].y = fmaf(bl, w, accB[j / 2].y);
+                    else accB[j / 2].x = fmaf(bl, w, accB[j / 2].x);
                 }
             }
         }
-        const float a = 255.f * q.wsum;
+        const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+        const float2 neg1 = make_float2(-1.0f, -1.0f);
+        const float lim = 0.5f - q.Eo;
 #pragma unroll
-        for (int j = 0; j < kOut; j++)
-            outv[j] = finish_fp32(255.f * accRG[j].x, 255.f * accRG[j].y, 255.f * accB[j], a, p.Er, p.Ea, ambv[j]);
-    } else {  // translucent window: premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
+        for (int m = 0; m < kOut / 2; m++) {
+            float2 t[3], d[3];   // (R,G) of output 2m, (R,G) of output 2m+1, B of both
+            const float2 v[3] = {accRG[2 * m], accRG[2 * m + 1], accB[m]};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                t[c] = __fadd2_rn(v[c], magic);
+                const float2 r = __fadd2_rn(t[c], nmagic);
+                d[c] = __ffma2_rn(r, neg1, v[c]);   // v - round(v), exact
+            }
+            ambv[2 * m] = fmaxf(fmaxf(fabsf(d[0].x), fabsf(d[0].y)), fabsf(d[2].x)) >= lim;
+            ambv[2 * m + 1] = fmaxf(fmaxf(fabsf(d[1].x), fabsf(d[1].y)), fabsf(d[2].y)) >= lim;
+            const uint32_t x0 = __byte_perm(clamp255_from_magic(t[0].x), clamp255_from_magic(t[0].y), 0x0040);
+            const uint32_t x1 = __byte_perm(clamp255_from_magic(t[1].x), clamp255_from_magic(t[1].y), 0x0040);
+            outv[2 * m] = __byte_perm(x0, __byte_perm(clamp255_from_magic(t[2].x), q.opaqueA, 0x7000), 0x7610);
+            outv[2 * m + 1] = __byte_perm(x1, __byte_perm(clamp255_from_magic(t[2].y), q.opaqueA, 0x7000), 0x7610);
+        }
+    } else {  // translucent window (or shortcut disabled): premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
         float2 accRG[kOut], accBA[kOut];
 #pragma unroll
         for (int j = 0; j < kOut; j++) accRG[j] = accBA[j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
-            const float fa = byte_f(raw[i], 3);
-            const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
-                                                     __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), kMagic2);
+            const uint32_t px = raw[LEAD + i];
+            const float fa = byte_f(px, 3);
+            const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u)),
+                                                     __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7541u))), kMagic2);
             const float2 prg = __fmul2_rn(rg, make_float2(fa, fa));
-            const float2 pba = make_float2(byte_f(raw[i], 2) * fa, fa);
+            const float2 pba = make_float2(byte_f(px, 2) * fa, fa);
 #pragma unroll
             for (int j = 0; j < kOut; j++) {
                 const int t = i - j * R;
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(128) resize_v_int_ratio_kernel(const IntRatioP
 #pragma unroll
             for (int i = 0; i < NIN; i++)
                 raw[i] = __ldg(reinterpret_cast<const uint32_t *>(s + (long long)(s0 + i) * p.srcRowStride + (long long)x0 * 4));
-            int_ratio_window<R, T>(raw, q, outv, ambv);
+            int_ratio_window<R, T, 0, NIN>(raw, q, outv, ambv);
         } else {
 #pragma unroll
             for (int j = 0; j < kOut; j++) {
@@ -480,7 +516,7 @@ __global__ void __launch_bounds__(128) resize_h_int_ratio_kernel(const IntRatioP
                     if (u + 2 < NIN) raw[u + 2] = t4.z;
                     if (u + 3 < NIN) raw[u + 3] = t4.w;
                 }
-                int_ratio_window<R, T>(raw, q, outv, ambv);
+                int_ratio_window<R, T, 0, NIN>(raw, q, outv, ambv);
             } else {  // edge outputs (clipped / renormalised taps): straight to the exact queue
 #pragma unroll
                 for (int j = 0; j < kOut; j++) { ambv[j] = true; outv[j] = 0u; }
@@ -496,6 +532,157 @@ __global__ void __launch_bounds__(128) resize_h_int_ratio_kernel(const IntRatioP
     }
     __syncthreads();
     drain();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Horizontal pass, warp-autonomous (round 2).  The block-wide kernel above spends 16 % of its stall samples on its one
+// barrier per row and stages half of its blocks (the first and the last of a 1920-output row) through a branchy
+// per-copy path (profiles/r2s2_lanczos).  Here a one-warp block owns 128 adjacent outputs (kOut per lane) and walks
+// kWRows rows; the source span of a row (128*R + window pixels, 16-byte aligned: the window of a lane starts LEAD
+// pixels into its first quad) is prefetched kLzStages-1 rows ahead into the warp's own ring with 16-byte cp.async
+// (quads that cross a row end: zero-filled by hand), one __syncwarp per row, no barrier.  All kOut results of a lane
+// go out as ONE 128-bit store; ambiguous / edge outputs are queued per warp and overwritten by the exact FP64 path
+// 32 at a time.
+// ------------------------------------------------------------------------------------------------
+#ifndef FB_LZ_WROWS
+#define FB_LZ_WROWS 16
+#endif
+#ifndef FB_LZ_STAGES
+#define FB_LZ_STAGES 3
+#endif
+#ifndef FB_LZ_MINB
+#define FB_LZ_MINB 20
+#endif
+constexpr int kWRows = FB_LZ_WROWS;
+constexpr int kLzStages = FB_LZ_STAGES;
+constexpr int kLzQ = 32 * kOut + 32;   // a row adds at most 32*kOut entries to fewer than 32 leftovers
+
+__device__ __forceinline__ void cp_async16_lz(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// Exact path for `take` queued outputs (one per lane).  Not inlined: one copy of the FP64 sequence in the kernel
+// instead of one per call site keeps the hot loop's code small (the first version stalled 0.64 cycles per issue on
+// instruction fetch, profiles/r2s2b_lanczos).
+__device__ __noinline__ void lz_exact_queue(const ResizeParams &p, const uint8_t *s, uint8_t *dimg, const uint32_t *queue, int take) {
+    const int lane = threadIdx.x & 31;
+    if (lane < take) {
+        const uint32_t code = queue[lane];
+        const int ox = (int)(code & 0xFFFFu), oy = (int)(code >> 16);
+        exact_px<false>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
+    }
+}
+
+template <int R, int T, int LEAD>
+__global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel(const __grid_constant__ IntRatioParams q) {
+    constexpr int NIN = T + (kOut - 1) * R;              // window of one lane
+    constexpr int NRAW = (NIN + LEAD + 3) / 4 * 4;        // ... read as whole quads
+    constexpr int STEP = R * kOut;                        // source pixels between the windows of adjacent lanes
+    static_assert(STEP == 16, "staging assumes one 16-px chunk per lane");
+    constexpr int SPAN = STEP * 31 + NRAW;                // staged pixels per row
+    constexpr int QUADS = SPAN / 4;
+    constexpr int NK = (QUADS + 31) / 32;                 // 16-byte copies per lane and row
+    constexpr int CHUNKS = (SPAN + 15) / 16;
+    constexpr int CHB = 80;                               // 16-px chunk + 16 B pad: conflict-free LDS.128 at 1 chunk / lane
+    constexpr int STAGEB = CHUNKS * CHB;
+    const ResizeParams &p = q.base;
+    __shared__ __align__(16) uint8_t stage[kLzStages][STAGEB];
+    __shared__ uint32_t ambQ[kLzQ];
+    const int lane = threadIdx.x;
+    const int img = blockIdx.z;
+    const int xw = blockIdx.x * (32 * kOut);              // first output of the warp
+    const int x0 = xw + lane * kOut;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
+    const int yFirst = blockIdx.y * kWRows;
+    const int yLast = min(yFirst + kWRows, p.outH);       // exclusive
+    const int sBase = R * xw + q.off - LEAD;              // staging pixel u <-> source pixel sBase + u; multiple of 4
+    const bool al16 = ((((uintptr_t)s + (long long)sBase * 4) | (uintptr_t)p.srcRowStride) & 15) == 0;
+    const bool interiorSpan = al16 && sBase >= 0 && sBase + SPAN <= p.srcW;
+    const bool dvec = ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0) && x0 + kOut <= p.outW;
+    const uint32_t myStage = (uint32_t)__cvta_generic_to_shared(&stage[0][0]) + (lane >> 2) * CHB + (lane & 3) * 16;
+    const uint8_t *myRow = s + (long long)sBase * 4 + lane * 16;   // this lane's first quad of row 0
+    auto stage_row = [&](int y, int slot) {
+        if (y < yLast) {
+            const uint8_t *g = myRow + (long long)y * p.srcRowStride;
+            const uint32_t d = myStage + slot * STAGEB;
+            if (interiorSpan) {   // warp-uniform: NK copies at immediate offsets (quad v = lane + 32k: chunk += 8k)
+#pragma unroll
+                for (int k = 0; k < NK; k++)
+                    if (k < QUADS / 32 || lane < QUADS - 32 * k)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * 8 * CHB), "l"(g + k * 512) : "memory");
+            } else {              // first / last warp of a row or an unaligned source: zero outside the row
+#pragma unroll 1
+                for (int k = 0; k < NK; k++) {
+                    const int v = lane + 32 * k;
+                    if (v < QUADS) {
+                        const int sx = sBase + 4 * v;
+                        if (al16 && sx >= 0 && sx + 4 <= p.srcW) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * 8 * CHB), "l"(g + k * 512) : "memory");
+                        } else {
+                            uint32_t t[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                t[i] = (sx + i >= 0 && sx + i < p.srcW) ? __ldg(reinterpret_cast<const uint32_t *>(g + k * 512 + i * 4)) : 0u;
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d + k * 8 * CHB), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_commit_group();
+    };
+    int nq = 0;   // queue length (warp-uniform, in a register: pushes are ballot-compacted, no atomics)
+#pragma unroll
+    for (int k = 0; k < kLzStages - 1; k++) stage_row(yFirst + k, k);
+    int slot = 0;
+#pragma unroll 1
+    for (int y0 = yFirst; y0 < yLast; y0++) {
+        // the slot row y0-1 used is free: every lane passed the __syncwarp at the end of that row
+        stage_row(y0 + kLzStages - 1, slot == 0 ? kLzStages - 1 : slot - 1);
+        cp_async_wait_group<kLzStages - 1>();   // this lane's copies of row y0 have landed
+        __syncwarp();                           // ... and everybody else's
+        uint32_t outv[kOut];
+        bool ambv[kOut];
+        if (x0 >= q.dLo && x0 + kOut <= q.dHi) {
+            uint32_t raw[NRAW];
+            const uint8_t *wbase = &stage[slot][0] + lane * CHB;   // staging pixels 16*lane .. 16*lane + NRAW - 1
+#pragma unroll
+            for (int v4 = 0; v4 < NRAW / 4; v4++) {
+                const int u = v4 * 4;
+                const uint4 t4 = *reinterpret_cast<const uint4 *>(wbase + (u >> 4) * CHB + (u & 15) * 4);
+                raw[u] = t4.x; raw[u + 1] = t4.y; raw[u + 2] = t4.z; raw[u + 3] = t4.w;
+            }
+            int_ratio_window<R, T, LEAD, NRAW>(raw, q, outv, ambv);
+        } else {  // edge outputs (clipped / renormalised taps; or beyond the row): straight to the exact queue
+#pragma unroll
+            for (int j = 0; j < kOut; j++) { ambv[j] = true; outv[j] = 0u; }
+        }
+        uint8_t *drow = dimg + (long long)y0 * p.dstRowStride + (long long)x0 * 4;
+        if (dvec) {
+            *reinterpret_cast<uint4 *>(drow) = make_uint4(outv[0], outv[1], outv[2], outv[3]);   // queued ones are overwritten below
+        } else {
+#pragma unroll
+            for (int j = 0; j < kOut; j++)
+                if (x0 + j < p.outW) *reinterpret_cast<uint32_t *>(drow + j * 4) = outv[j];
+        }
+#pragma unroll
+        for (int j = 0; j < kOut; j++) {
+            const bool push = ambv[j] && x0 + j < p.outW;
+            const uint32_t b = __ballot_sync(0xffffffffu, push);
+            if (b) {   // warp-uniform
+                if (push) ambQ[nq + __popc(b & ((1u << lane) - 1u))] = ((uint32_t)y0 << 16) | (uint32_t)(x0 + j);
+                nq += __popc(b);
+            }
+        }
+        __syncwarp();   // stores, pushes and reads of stage[slot] are done before the drain / the next restage
+        while (nq >= 32) {
+            nq -= 32;
+            lz_exact_queue(p, s, dimg, ambQ + nq, 32);
+        }
+        slot = slot == kLzStages - 1 ? 0 : slot + 1;
+    }
+    if (nq > 0) lz_exact_queue(p, s, dimg, ambQ, nq);
 }
 
 template <bool VERTICAL>
@@ -523,11 +710,18 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
         (VERTICAL || wpadT != nullptr) && getenv("FB_RESIZE_NO_INTRATIO") == nullptr) {
         IntRatioParams q;
         q.base = p; q.off = ir->off; q.dLo = ir->dLo; q.dHi = ir->dHi; q.wsum = ir->wsum;
-        for (int i = 0; i < 28; i++) q.w[i] = i < ir->taps ? ir->w[i] : 0.f;
+        for (int i = 0; i < 28; i++) { q.w[i] = i < ir->taps ? ir->w[i] : 0.f; q.wn[i] = i < ir->taps ? ir->wn[i] : 0.f; }
+        q.Eo = ir->Eo;
+        q.opaqueA = getenv("FB_LZ_NO_OPAQUE") == nullptr ? ir->opaqueA : 0u;
         dim3 g2 = VERTICAL ? dim3((outW + 127) / 128, (outH + kOut - 1) / kOut, n)
                            : dim3(((outW + kOut - 1) / kOut + 127) / 128, (outH + kRowsPerBlock - 1) / kRowsPerBlock, n);
         bool launched = true;
-        if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_h_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
+        static const bool oldH = getenv("FB_LZ_OLD") != nullptr;   // round-1 block-wide kernel, kept for A/B runs
+        static_assert(kOut == 4, "the 128-bit output store assumes four outputs per lane");
+        if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && ((ir->off % 4) + 4) % 4 == 2 && !oldH && outW < 65536 && outH < 65536) {
+            dim3 gw((outW + 32 * kOut - 1) / (32 * kOut), (outH + kWRows - 1) / kWRows, n);
+            resize_h_int_ratio_warp_kernel<4, 24, 2><<<gw, 32, 0, s>>>(q);
+        } else if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_h_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
         else if (VERTICAL && ir->ratio == 4 && ir->taps == 24) resize_v_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
         else if (VERTICAL && ir->ratio == 2 && ir->taps == 12) resize_v_int_ratio_kernel<2, 12><<<g2, 128, 0, s>>>(q);
         else if (VERTICAL && ir->ratio == 3 && ir->taps == 17) resize_v_int_ratio_kernel<3, 17><<<g2, 128, 0, s>>>(q);

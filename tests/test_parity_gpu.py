@@ -453,3 +453,47 @@ def test_blur_sharpen_on_row_padded_batch_keeps_strides(lib, oracle):
         with pytest.raises(ValueError):
             fn(src, arg, out=torch.empty_like(dense))
     assert np.array_equal(batch.gaussian_blur_batch(src, 2.0)[1].cpu().numpy(), oracle.gaussian_blur(dense[1].cpu().numpy(), 2.0))
+
+
+# ---- round 2: warp-autonomous Lanczos H pass with the opaque-window shortcut, cp.async-staged blur V pass ----
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1000, 64, 250, 16), (4 * 131, 40, 131, 10), (2048, 36, 512, 9), (516, 200, 129, 50)])
+def test_lanczos_ratio4_opaque_shortcut_bit_exact(sw, sh, dw, dh, lib, oracle):
+    # fully opaque: every interior window takes sum(R * w/W) with the constant bound; widths that are not a multiple of
+    # the 128 outputs a warp owns (partial last warp, quads crossing the row end)
+    src = S.noise_image(sw, sh, sw + sh, alpha="opaque")
+    assert np.array_equal(api.lanczos_resize(src, dw, dh), oracle.lanczos_resize(src, dw, dh))
+    # overshoot on both sides of [0, 255]: hard 0/255 stripes and checkers make the clamp real
+    hard = np.zeros((sh, sw, 4), np.uint8)
+    hard[..., 3] = 255
+    hard[:, (np.arange(sw) // 3) % 2 == 0, :3] = 255
+    hard[(np.arange(sh) // 5) % 2 == 0, :, 1] ^= 255
+    assert np.array_equal(api.lanczos_resize(hard, dw, dh), oracle.lanczos_resize(hard, dw, dh))
+    # a few translucent pixels: windows that contain one leave the shortcut, their neighbours do not
+    mixed = src.copy()
+    rng = np.random.default_rng(sw)
+    ys, xs = rng.integers(0, sh, 40), rng.integers(0, sw, 40)
+    mixed[ys, xs, 3] = rng.integers(0, 255, 40)
+    assert np.array_equal(api.lanczos_resize(mixed, dw, dh), oracle.lanczos_resize(mixed, dw, dh))
+
+
+def test_lanczos_and_blur_on_unaligned_device_views(lib, oracle):
+    # a view that starts 4 bytes into a row and has a padded pitch: no 16-byte alignment anywhere, so the 16-byte
+    # cp.async staging of both kernels must hand over to the per-pixel paths
+    full = _device_noise(2, 48, 1024 + 9, 81)
+    src = full[:, :, 1:1025, :]
+    dense = src.contiguous()
+    got = batch.lanczos_resize_batch(src, 256, 12)
+    assert torch.equal(got, batch.lanczos_resize_batch(dense, 256, 12))
+    assert np.array_equal(got[1].cpu().numpy(), oracle.lanczos_resize(dense[1].cpu().numpy(), 256, 12))
+    gb = batch.gaussian_blur_batch(src, 2.0)
+    assert np.array_equal(gb[0].cpu().numpy(), oracle.gaussian_blur(dense[0].cpu().numpy(), 2.0))
+
+
+@pytest.mark.parametrize("w,h", [(64, 700), (96, 481), (33, 260), (512, 250)])
+def test_blur_vertical_staging_bit_exact(w, h, lib, oracle):
+    # several 240-row segments per column, whole-warp-inside (16-byte copies) and partial warps (4-byte copies), the
+    # bottom rows clamped inside the staged chunk
+    src = S.noise_image(w, h, w * h, alpha="random")
+    assert np.array_equal(api.GaussianBlur(src, 2.0), oracle.gaussian_blur(src, 2.0))
+    assert np.array_equal(api.GaussianBlur(src, 1.0), oracle.gaussian_blur(src, 1.0))

@@ -18,10 +18,14 @@ ap.add_argument("--pairs", type=int, default=8)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--w", type=int, default=3840)
 ap.add_argument("--h", type=int, default=2160)
+ap.add_argument("--opaque", action="store_true", help="alpha = 255 everywhere (the photo case)")
 args = ap.parse_args()
 g = torch.Generator(device="cuda").manual_seed(1)
 a = torch.randint(0, 256, (args.pairs, args.h, args.w, 4), dtype=torch.uint8, device="cuda", generator=g)
 b = torch.randint(0, 256, (args.pairs, args.h, args.w, 4), dtype=torch.uint8, device="cuda", generator=g)
+if args.opaque:
+    a[..., 3] = 255
+    b[..., 3] = 255
 torch.cuda.synchronize()
 for _ in range(args.iters):
     if args.op == "ssim":
