@@ -189,12 +189,17 @@ static bool build_groups(const int *start, const int *index, const double *weigh
     return true;
 }
 
+// *wabs: the weight of the FP32 error bound (resize.cu launch_pass), max over destinations of 2 S + sum_k P_k with
+// P_k = sum_{s<=k} |w_s| and S = P_last: FMA k rounds a partial sum of magnitude <= X * P_k (X = 255*255 or 255), and the
+// FP32 weight and the product alpha*w add two relative roundings on every term.  [Round 1 used (taps + 3) * S: twice as
+// wide for a Lanczos-3 row, i.e. twice as many outputs sent to the exact path.]
 static void table_stats(const int *start, const double *weight, int n, int *maxTaps, double *wabs) {
     *maxTaps = 0;
     *wabs = 0.0;
     for (int d = 0; d < n; d++) {
-        double sabs = 0.0;
-        for (int t = start[d]; t < start[d + 1]; t++) sabs += fabs(weight[t]);
+        double sabs = 0.0, psum = 0.0;
+        for (int t = start[d]; t < start[d + 1]; t++) { sabs += fabs(weight[t]); psum += sabs; }
+        sabs = 2.0 * sabs + psum;
         if (sabs > *wabs) *wabs = sabs;
         if (start[d + 1] - start[d] > *maxTaps) *maxTaps = start[d + 1] - start[d];
     }
@@ -984,7 +989,7 @@ void fb_free_pinned(void *p) {
     if (p) cudaFreeHost(p);
 }
 
-// Idle contexts held by the pool / live Lanczos tables: what tests/test_resources_gpu.py watches.
+// Idle contexts held by the pool / live Lanczos tables: what tests/test_batch_host_gpu.py watches.
 int fb_debug_pool_size(void) {
     std::lock_guard<std::mutex> lk(g_pool.mu);
     int n = 0;

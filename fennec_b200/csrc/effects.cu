@@ -149,7 +149,7 @@ __device__ __forceinline__ uint32_t blur_round_pack(const float2 (&accRG)[kTile]
 // ---- deferred exact path ---------------------------------------------------------------------------------
 // About 0.16 % of the outputs are ambiguous, but that is ~1 per warp per 16-output chunk: recomputing them on the
 // spot kept one or two lanes busy for ~200 FP64 instructions while the other 30 waited (and the I2F conversions
-// queued on the XU pipe: 23 % busy in profiles/r1c).  Instead each warp queues (x, y) of its ambiguous outputs in
+// queued on the XU pipe: 23 % busy in the round-1c capture, profiles/r1b_ncu_summaries_all_kernels.txt).  Instead each warp queues (x, y) of its ambiguous outputs in
 // shared memory and drains the queue 32 at a time, one output per lane, re-reading the taps through L1/L2.
 constexpr int kAmbQ = 32 * kTile + 32;   // a chunk can add at most 32*kTile entries to fewer than 32 leftovers
 
@@ -214,7 +214,7 @@ __device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *
 // Accumulators: (R, G) of one output share an FFMA2 whose weight is a broadcast scalar; B of outputs (2m, 2m+1)
 // sits in the two halves of accB[m] and takes scalar FFMAs.  [The first version paired two OUTPUTS of one channel
 // per FFMA2, which needs the weight pairs (w[k], w[k-1]) as aligned register pairs: ptxas rebuilt them with one
-// IMAD.MOV per FFMA2 — 28 % of the executed instructions, on the same pipe as the FMAs (profiles/r1d).]
+// IMAD.MOV per FFMA2 — 28 % of the executed instructions, on the same pipe as the FMAs (profiles/r1d_ncu_summaries_blur_lanczos.txt).]
 #ifndef FB_BLUR_BA
 #define FB_BLUR_BA 0   // 1: B rides an FFMA2 together with the (discarded) alpha lane instead of a scalar FFMA
 #endif
@@ -1044,12 +1044,15 @@ int launch_gaussian_blur(cudaStream_t s, const uint8_t *src, uint8_t *dst, long 
     p.w = w; p.h = h; p.radius = radius;
     p.kernel = kernel_dev; p.kernel32 = kernel32_dev;
     for (int k = 0; k < 17; k++) p.w32[k] = (k <= 2 * radius && radius <= 8) ? kernel32_host[k] : 0.f;
-    // FP32 error bound of the tap sum: each of the `taps` FMAs rounds a partial sum <= 255 (<= 255*2^-24 each)
-    // and the FP32 weights differ from the FP64 ones by <= 2^-24 relative (<= 255*2^-24 in total); 25 % margin.
-    // The bound assumes partial sums <= 255 (a convex combination); a caller-supplied kernel that is not normalised or
-    // has negative taps reaches 255 * sum|w| instead, so the bound scales with max(1, sum|w|) (NaN/inf: exact path only).
-    const double scale = (wabs == wabs && wabs < 1e6) ? (wabs > 1.0 ? wabs : 1.0) : 1e6;
-    p.eps = (float)((2 * radius + 2) * 255.0 * 5.9604644775390625e-08 * 1.25 * scale);
+    // FP32 error bound of the tap sum: FMA k rounds a partial sum <= 255 * P_k, P_k = sum_{s<=k} |w_s| in tap order (the
+    // order both fast kernels accumulate in), and the FP32 weights differ from the FP64 ones by <= 2^-24 relative
+    // (255 * 2^-24 * sum|w| in total): eps = 255 * 2^-24 * (sum|w| + sum_k P_k), 10 % margin.  [Round 1 used
+    // (taps + 1) * 255 * 2^-24 * 1.25, twice as wide for a Gaussian: twice as many outputs on the exact path.]
+    // A caller-supplied kernel that is not a convex combination arrives with wabs = 1e9 (api.cu): exact path only.
+    double sabs = 0.0, psum = 0.0;
+    for (int k = 0; k <= 2 * radius; k++) { sabs += fabs((double)kernel32_host[k]); psum += sabs; }
+    const bool sane = (wabs == wabs && wabs < 1e6 && sabs == sabs);
+    p.eps = sane ? (float)(255.0 * 5.9604644775390625e-08 * (sabs + psum) * 1.10) : 1e6f;
     p.exactOnly = (p.eps >= 0.25f) ? 1 : 0;  // absurdly long (or huge-gain) kernels: no useful fast path
     dim3 grid((w + 255) / 256, h, n);
     // horizontal: src → tmp

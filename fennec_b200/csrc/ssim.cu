@@ -6,7 +6,8 @@
 // one-pass filter of four planes per pixel — a', b', q = a'^2 + b'^2, p = a'b' — where a' = luma(a) - c
 // is centred on a per-strip constant c (the luma of the strip's centre pixel) so that
 // E[x^2] - mu^2 does not cancel catastrophically in FP32 (measured <= 2e-6 absolute on adversarial
-// inputs, tests/test_ssim_parity.py; the contract is 1e-5).  The window is
+// inputs, tests/test_parity_gpu.py::test_scores_match_golden and tools/quick_ssim.py: <= 3.3e-7; the contract is
+// 1e-5).  The window is
 // exp(-(x^2+y^2)/4.5) for x,y in [-4,3] (ssim.go:74-77,116-117,223-241): an outer product g(y)g(x).
 //
 // Mapping: one warp owns a strip of 32*CPL input columns and walks down RS(+7) rows.  Each lane owns
@@ -16,7 +17,8 @@
 // are loaded with 128-bit non-allocating loads, one row ahead.  Bytes -> float goes through
 // dp2a (integer dot product with the BT.601 weights x1000) accumulating straight into the bit pattern
 // of 2^23 + L, because I2F runs at 1/8 of the FMA rate on sm_100 (tools/microbench.cu).
-// This kernel is FMA-pipe-bound, not HBM-bound: ~87 FP32 lane-ops per pixel (profiles/).
+// This kernel is FMA-pipe-bound, not HBM-bound: ~92 FP32 lane-ops per pixel, FMA pipe 79 % busy
+// (profiles/r2_k1_ncu_summaries.txt).
 #include "common.cuh"
 
 #include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time through cudart, no libcuda link)
@@ -54,14 +56,21 @@ __device__ __forceinline__ float luma_magic(uint32_t px) {
 }
 
 // ---- per-lane async global→shared copies (LDGSTS) with commit/wait groups -------------------------
-// A TMA bulk-copy + mbarrier ring was measured first (profiles/ssim_strip_r1e): it removed the
+// A 1-D TMA bulk-copy + mbarrier ring was measured first (round 1; the kernel is no longer in the tree — its tiled
+// successor ssim_strip_tma_kernel below is, with its numbers in profiles/r2_k1_variants.txt): it removed the
 // long-scoreboard stall too, but the elected-lane issue path (R2UR/UBLKCP/expect_tx) cost ~60 extra
 // instructions per row per warp — more than it saved for 512-byte rows.  cp.async needs 4.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 template <int BYTES>
-__device__ __forceinline__ void cp_async(uint32_t dst, const void *src) {
+__device__ __forceinline__ void cp_async(uint32_t dst, const uint8_t *src) {
+    static_assert(BYTES == 16 || BYTES == 12 || BYTES == 8 || BYTES == 4, "cp.async copies 4, 8 or 16 bytes");
     if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else if (BYTES == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    else if (BYTES == 12) {   // 4-byte aligned only
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4), "l"(src + 4) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8), "l"(src + 8) : "memory");
+    } else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -97,6 +106,7 @@ struct StripCtx {
     float4 *vb0, *vb1;
     // FAST path only: per-warp ring of kStages row buffers filled by cp.async.
     uint8_t *ring;        // [kStages][2 images][32*CPL*4 bytes]
+    int pxoff[CPL];       // CPL = 3 (4-byte copies): byte offset of each of the lane's pixels, clamped into the row
 };
 
 #ifndef FB_SSIM_F64FORMULA
@@ -107,6 +117,9 @@ struct StripCtx {
 #endif
 #ifndef FB_SSIM_STAGES
 #define FB_SSIM_STAGES 4
+#endif
+#ifndef FB_SSIM_MINB3
+#define FB_SSIM_MINB3 12   // CPL = 3: one-warp blocks per SM the register allocation aims at (12 -> <= 168 registers)
 #endif
 constexpr int kStages = FB_SSIM_STAGES;  // rows in flight per warp (power of two: the stage is the ring slot & (kStages-1))
 
@@ -131,7 +144,7 @@ __device__ __forceinline__ double walk_strip(const StripCtx<CPL> &q) {
     // cp.async, kStages rows ahead, and reads them back after cp.async.wait_group — no cross-lane
     // traffic, so no barrier is needed.  Register prefetch could not give that distance: all LDGs share
     // scoreboard slots, so waiting for row r also waited for the loads of rows r+1, r+2 issued after it
-    // (profiles/ssim_strip_r1d: 23% of samples in long-scoreboard on the first consumer).
+    // (profiles/r1_ssim_strip_ncu_summaries.txt, section r1d: 23% of samples in long-scoreboard on the first consumer).
     // !FAST: two rows in flight in registers, ping-pong by row parity.
     uint32_t pfa[2][CPL], pfb[2][CPL];
     const uint32_t myRing = FAST ? smem_u32(q.ring) + lane * (CPL * 4) : 0u;
@@ -461,7 +474,7 @@ __device__ __forceinline__ double walk_strip_pipe(const StripCtx<4> &q) {
 
 // ------------------------------------------------------------------------------------------------
 // Two rows per iteration (aligned inputs, CPL = 4).  walk_strip pays, per row, a three-level branch tree for the ring
-// slot, a loop branch and one shared-memory round trip with nothing else to issue (profiles/r1: 12 % of the warp
+// slot, a loop branch and one shared-memory round trip with nothing else to issue (profiles/r1_ssim_strip_ncu_summaries.txt: 12 % of the warp
 // samples sit on BRA / ISETP / BSYNC / DEPBAR, and "wait" on fixed latencies is the largest stall).  Here one iteration
 // takes rows r and r+1: four slot cases instead of eight, half the branches per row, both vertical passes back to back
 // (16 independent FFMA2 chains), ONE __syncwarp for two rows, and the second row's neighbour loads are in flight
@@ -474,9 +487,10 @@ struct HConsts {
     float2 qpInit, one_two, neg2;
 };
 
-__device__ __forceinline__ void hpass_formula(const float4 (&own)[4], const float4 *vb, const float2 (&g2)[8],
-                                              const HConsts &k, const bool (&ok)[4], float (&fs)[4]) {
-    constexpr int CPL = 4, kVLanes = 36;
+template <int CPL>
+__device__ __forceinline__ void hpass_formula(const float4 (&own)[CPL], const float4 *vb, const float2 (&g2)[8],
+                                              const HConsts &k, const bool (&ok)[CPL], float (&fs)[CPL]) {
+    constexpr int kVLanes = 36;
     float4 it[CPL + 7];
 #pragma unroll
     for (int i = 0; i < CPL; i++) it[i] = own[i];
@@ -502,8 +516,12 @@ __device__ __forceinline__ void hpass_formula(const float4 (&own)[4], const floa
     }
 }
 
-__device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
-    constexpr int CPL = 4;
+// CPL = 3 (96 columns, 88 outputs per strip) trades 2.3 % more column halo and 4-byte copies (three per image and row,
+// each pixel's address clamped into the row, so any width and any 4-byte-aligned buffer is "fast") for a 96-register
+// ring: ~160 registers, three warps per scheduler instead of two.
+template <int CPL>
+__device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
+    static_assert(CPL == 3 || CPL == 4, "walk_strip2: 3 or 4 columns per lane");
     const uint8_t *pa = q.pa, *pb = q.pb;
     const int nIn = q.nIn, lane = q.lane;
     const float2 s2 = make_float2(kLumaScale, kLumaScale);
@@ -519,24 +537,44 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
     hk.neg2 = make_float2(-1.f, -1.f);
     float2 rab[8][CPL], rqp[8][CPL];
     constexpr uint32_t kRowBuf = 32 * CPL * 4;
-    const uint32_t myRing = smem_u32(q.ring) + lane * 16;
-    const uint8_t *myRingP = q.ring + lane * 16;
+    const uint32_t myRing = smem_u32(q.ring) + lane * (CPL * 4);
+    const uint8_t *myRingP = q.ring + lane * (CPL * 4);
+    auto fetch_row = [&](int stage) {   // this lane's CPL pixels of both images, current row pointers
+        if (CPL == 4) {
+            cp_async<16>(myRing + (2 * stage) * kRowBuf, pa);
+            cp_async<16>(myRing + (2 * stage + 1) * kRowBuf, pb);
+        } else {
 #pragma unroll
-    for (int row = 0; row < kStages; row++) {  // rows 0..3 exist (nIn >= 8)
-        cp_async<16>(myRing + (2 * row) * kRowBuf, pa);
-        cp_async<16>(myRing + (2 * row + 1) * kRowBuf, pb);
-        cp_async_commit();
+            for (int i = 0; i < CPL; i++) {
+                cp_async<4>(myRing + (2 * stage) * kRowBuf + 4 * i, pa + q.pxoff[i]);
+                cp_async<4>(myRing + (2 * stage + 1) * kRowBuf + 4 * i, pb + q.pxoff[i]);
+            }
+        }
         pa += q.rowStrideA;
         pb += q.rowStrideB;
+    };
+#pragma unroll
+    for (int row = 0; row < kStages; row++) {  // rows 0..3 exist (nIn >= 8)
+        fetch_row(row);
+        cp_async_commit();
     }
     // planes of row R (ring stage R & 3) into slot S, then refill the stage with row R + kStages
 #define W2_PLANES(S, R)                                                                         \
     {                                                                                           \
         cp_async_wait<kStages - 1>();                                                           \
         const uint8_t *rb_ = myRingP + (2 * ((S) & (kStages - 1))) * kRowBuf;                   \
-        const uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                                \
-        const uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + kRowBuf);                      \
-        const uint32_t xa_[4] = {va_.x, va_.y, va_.z, va_.w}, xb_[4] = {vb_.x, vb_.y, vb_.z, vb_.w}; \
+        uint32_t xa_[4], xb_[4];                                                                \
+        if (CPL == 4) {                                                                         \
+            const uint4 va_ = *reinterpret_cast<const uint4 *>(rb_);                            \
+            const uint4 vb_ = *reinterpret_cast<const uint4 *>(rb_ + kRowBuf);                  \
+            xa_[0] = va_.x; xa_[1] = va_.y; xa_[2] = va_.z; xa_[3] = va_.w;                     \
+            xb_[0] = vb_.x; xb_[1] = vb_.y; xb_[2] = vb_.z; xb_[3] = vb_.w;                     \
+        } else {                                                                                \
+            _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                   \
+                xa_[i] = *reinterpret_cast<const uint32_t *>(rb_ + 4 * i);                      \
+                xb_[i] = *reinterpret_cast<const uint32_t *>(rb_ + kRowBuf + 4 * i);            \
+            }                                                                                   \
+        }                                                                                       \
         _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
             float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
             float2 t = __ffma2_rn(f, s2, K2);                                                   \
@@ -544,12 +582,7 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
             rab[S][i] = t;                                                                      \
             rqp[S][i] = make_float2(sq.x + sq.y, t.x * t.y);                                    \
         }                                                                                       \
-        if ((R) + kStages < nIn) {                                                              \
-            cp_async<16>(myRing + (2 * ((S) & (kStages - 1))) * kRowBuf, pa);                   \
-            cp_async<16>(myRing + (2 * ((S) & (kStages - 1)) + 1) * kRowBuf, pb);               \
-            pa += q.rowStrideA;                                                                 \
-            pb += q.rowStrideB;                                                                 \
-        }                                                                                       \
+        if ((R) + kStages < nIn) fetch_row((S) & (kStages - 1));                                \
         cp_async_commit();                                                                      \
     }
 #define W2_VTAPS(S, V)                                                                          \
@@ -596,8 +629,8 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<4> &q) {
         const bool second = r + 1 < nIn;
 #pragma unroll
         for (int i = 0; i < CPL; i++) okB[i] = q.valid[i] && second;
-        hpass_formula(vA, vbA, g2, hk, okA, fs);
-        hpass_formula(vB, vbB, g2, hk, okB, fs);
+        hpass_formula<CPL>(vA, vbA, g2, hk, okA, fs);
+        hpass_formula<CPL>(vB, vbB, g2, hk, okB, fs);
     }
 #undef W2_PLANES
 #undef W2_VTAPS
@@ -943,7 +976,7 @@ __global__ void __launch_bounds__(32, 8) ssim_strip_tma_kernel(const __grid_cons
 // 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at ~200 registers without a cap below 8 blocks:
 // 9-10 warps per SM, a third warp on one or two schedulers).
 template <int CPL, int WPB>
-constexpr int ssim_min_blocks() { return CPL != 4 ? 16 / WPB : (WPB == 4 ? FB_SSIM_MINB4 : WPB == 2 ? 4 : 8); }
+constexpr int ssim_min_blocks() { return CPL == 3 ? FB_SSIM_MINB3 / WPB : CPL != 4 ? 16 / WPB : (WPB == 4 ? FB_SSIM_MINB4 : WPB == 2 ? 4 : 8); }
 
 template <int CPL, int MODE = 0, int WPB = 4>
 __global__ void __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>())) ssim_strip_kernel(const SsimParams p) {
@@ -1001,15 +1034,19 @@ __global__ void __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>())) ssim_
 
     // Warp-uniform choice of the load path.  Lanes entirely right of the image (their outputs are all
     // masked) re-read the strip's first columns so that the whole warp can use aligned vector loads.
-    const bool fast = p.vecOK && __all_sync(0xffffffffu, q.nvalid == CPL || q.nvalid == 0);
+    // CPL = 3 copies pixel by pixel (4 bytes, each address clamped into the row): always "fast".
+    const bool fast = (CPL == 3 && MODE == 2) || (p.vecOK && __all_sync(0xffffffffu, q.nvalid == CPL || q.nvalid == 0));
     const int xld = (fast && q.nvalid == 0) ? X0 : xl;
     q.pa = ia + (long long)Y0 * p.rowStrideA + (long long)xld * 4;
     q.pb = ib + (long long)Y0 * p.rowStrideB + (long long)xld * 4;
     if (fast && q.nvalid == 0) q.nvalid = CPL;
+#pragma unroll
+    for (int i = 0; i < CPL; i++) q.pxoff[i] = 4 * min(i, max(q.nvalid, 1) - 1);
 
     double dsum;
     if (PIPE && CPL == 4) dsum = fast ? walk_strip_pipe(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
-    else if (MODE == 2 && CPL == 4) dsum = fast ? walk_strip2(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
+    else if (MODE == 2 && CPL == 4) dsum = fast ? walk_strip2<4>(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
+    else if (MODE == 2 && CPL == 3) dsum = walk_strip2<3>(reinterpret_cast<const StripCtx<3> &>(q));
     else if (MODE == 3 && CPL == 4) dsum = fast ? walk_stripN<4>(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
     else if (MODE == 4 && CPL == 4) dsum = fast ? walk_stripN<2>(reinterpret_cast<const StripCtx<4> &>(q)) : walk_strip<CPL, false>(q);
     else dsum = fast ? walk_strip<CPL, true>(q) : walk_strip<CPL, false>(q);
@@ -1330,12 +1367,15 @@ void gaussian1d(float g[8]) {
     for (int k = 0; k < 8; k++) g[k] = (float)(v[k] / s);
 }
 
+#ifndef FB_SSIM_CPL_DEFAULT
+#define FB_SSIM_CPL_DEFAULT 4
+#endif
 // Segment geometry: strips of OUTC outputs; rs rows per segment chosen so the grid fills the GPU.
 struct Geo { int cpl, outc, nsx, nsy, rs; };
 int ssim_cpl() {
     static int cpl = [] {
-        const char *e = getenv("FB_SSIM_CPL");  // tuning knob: columns per lane (2 or 4)
-        return (e && e[0] == '2') ? 2 : 4;
+        const char *e = getenv("FB_SSIM_CPL");  // tuning knob: columns per lane (2, 3 or 4)
+        return (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : (e && e[0] == '4') ? 4 : FB_SSIM_CPL_DEFAULT;
     }();
     return cpl;
 }
@@ -1498,6 +1538,10 @@ int launch_ssim(DevCtx *c, cudaStream_t s, const uint8_t *a, const uint8_t *b, l
         else if (wpb == 1) FB_LAUNCH_STRIP(0, 1);
         else FB_LAUNCH_STRIP(0, 4);
 #undef FB_LAUNCH_STRIP
+    }
+    else if (g.cpl == 3) {
+        FB_PREPARE((ssim_strip_kernel<3, 2, 1>), 32);
+        ssim_strip_kernel<3, 2, 1><<<(unsigned)segs, 32, 0, s>>>(p);
     }
     else ssim_strip_kernel<2><<<(unsigned)blocks, 128, 0, s>>>(p);
     FB_CUDA(cudaGetLastError());
