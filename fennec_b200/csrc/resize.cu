@@ -564,12 +564,13 @@ __device__ __forceinline__ void cp_async16_lz(void *smem_dst, const void *gsrc) 
 // Exact path for `take` queued outputs (one per lane).  Not inlined: one copy of the FP64 sequence in the kernel
 // instead of one per call site keeps the hot loop's code small (the first version stalled 0.64 cycles per issue on
 // instruction fetch, profiles/r2s2b_lanczos).
+template <bool VERTICAL>
 __device__ __noinline__ void lz_exact_queue(const ResizeParams &p, const uint8_t *s, uint8_t *dimg, const uint32_t *queue, int take) {
     const int lane = threadIdx.x & 31;
     if (lane < take) {
         const uint32_t code = queue[lane];
         const int ox = (int)(code & 0xFFFFu), oy = (int)(code >> 16);
-        exact_px<false>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
+        exact_px<VERTICAL>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
     }
 }
 
@@ -678,11 +679,96 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
         __syncwarp();   // stores, pushes and reads of stage[slot] are done before the drain / the next restage
         while (nq >= 32) {
             nq -= 32;
-            lz_exact_queue(p, s, dimg, ambQ + nq, 32);
+            lz_exact_queue<false>(p, s, dimg, ambQ + nq, 32);
         }
         slot = slot == kLzStages - 1 ? 0 : slot + 1;
     }
-    if (nq > 0) lz_exact_queue(p, s, dimg, ambQ, nq);
+    if (nq > 0) lz_exact_queue<false>(p, s, dimg, ambQ, nq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vertical pass, warp-autonomous (round 2).  resize_v_int_ratio_kernel above issues its 36-row window as 36 global loads
+// with 64-bit address arithmetic each (144 of the 644 instructions of its main block) and synchronises the block twice
+// for the exact queue (20 % of its stall samples at the two barriers, profiles/r2s2b_lanczos).  Here a one-warp block
+// owns 32 adjacent columns and walks kVSteps steps of kOut output rows; the window of the NEXT step is copied into the
+// second of two shared-memory buffers with 16-byte cp.async (8 lanes per row, 9 copies per lane) while the current
+// one is evaluated from LDS at immediate offsets; the exact queue is per warp and ballot-compacted.
+// Needs 16-byte-aligned rows and outW % 32 == 0 (else the kernel above runs).
+// ------------------------------------------------------------------------------------------------
+#ifndef FB_LZ_VSTEPS
+#define FB_LZ_VSTEPS 8
+#endif
+constexpr int kVSteps = FB_LZ_VSTEPS;
+
+template <int R, int T>
+__global__ void __launch_bounds__(32, 20) resize_v_int_ratio_warp_kernel(const __grid_constant__ IntRatioParams q) {
+    constexpr int NIN = T + (kOut - 1) * R;               // source rows of one step's window
+    constexpr int NK = (NIN * 8 + 31) / 32;               // 16-byte copies per lane and step
+    const ResizeParams &p = q.base;
+    __shared__ __align__(16) uint32_t win[2][NIN][32];
+    __shared__ uint32_t ambQ[kLzQ];
+    const int lane = threadIdx.x;
+    const int img = blockIdx.z;
+    const int xw = blockIdx.x * 32, x0 = xw + lane;
+    const uint8_t *s = p.src + (long long)img * p.srcImgStride;
+    uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
+    const int yFirst = blockIdx.y * (kVSteps * kOut);
+    const int yLast = min(yFirst + kVSteps * kOut, p.outH);   // exclusive
+    const int srcH = p.srcW;                                   // launch_pass<true> passes the source HEIGHT as srcSize
+    const uint8_t *colBase = s + (long long)xw * 4 + (lane & 7) * 16;
+    const uint32_t myWin = (uint32_t)__cvta_generic_to_shared(&win[0][0][0]) + (lane >> 3) * 128 + (lane & 7) * 16;
+    auto stage_step = [&](int y0, int buf) {   // window of outputs y0 .. y0+kOut-1: source rows R*y0 + off + i, clamped into the image
+        if (y0 < yLast) {
+            const int s0 = R * y0 + q.off;
+#pragma unroll
+            for (int k = 0; k < NK; k++) {
+                const int r = (lane >> 3) + 4 * k;
+                if (k < NIN / 4 || r < NIN) {
+                    const int sy = min(max(s0 + r, 0), srcH - 1);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(myWin + buf * (NIN * 128) + k * 512),
+                                 "l"(colBase + (long long)sy * p.srcRowStride) : "memory");
+                }
+            }
+        }
+        cp_async_commit_group();
+    };
+    int nq = 0;
+    stage_step(yFirst, 0);
+    int buf = 0;
+#pragma unroll 1
+    for (int y0 = yFirst; y0 < yLast; y0 += kOut, buf ^= 1) {
+        stage_step(y0 + kOut, buf ^ 1);   // its previous reader (step y0 - kOut) is behind the __syncwarp at the end of that step
+        cp_async_wait_group<1>();
+        __syncwarp();
+        uint32_t outv[kOut];
+        bool ambv[kOut];
+        if (y0 >= q.dLo && y0 + kOut <= q.dHi) {
+            uint32_t raw[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) raw[i] = win[buf][i][lane];
+            int_ratio_window<R, T, 0, NIN>(raw, q, outv, ambv);
+        } else {  // edge rows (clipped / renormalised taps): straight to the exact queue
+#pragma unroll
+            for (int j = 0; j < kOut; j++) { ambv[j] = true; outv[j] = 0u; }
+        }
+#pragma unroll
+        for (int j = 0; j < kOut; j++) {
+            const bool live = y0 + j < p.outH;
+            if (live) *reinterpret_cast<uint32_t *>(dimg + (long long)(y0 + j) * p.dstRowStride + (long long)x0 * 4) = outv[j];   // queued ones are overwritten below
+            const bool push = ambv[j] && live;
+            const uint32_t b = __ballot_sync(0xffffffffu, push);
+            if (b) {   // warp-uniform
+                if (push) ambQ[nq + __popc(b & ((1u << lane) - 1u))] = ((uint32_t)(y0 + j) << 16) | (uint32_t)x0;
+                nq += __popc(b);
+            }
+        }
+        __syncwarp();
+        while (nq >= 32) {
+            nq -= 32;
+            lz_exact_queue<true>(p, s, dimg, ambQ + nq, 32);
+        }
+    }
+    if (nq > 0) lz_exact_queue<true>(p, s, dimg, ambQ, nq);
 }
 
 template <bool VERTICAL>
@@ -724,6 +810,10 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
             dim3 gw((outW + 32 * kOut - 1) / (32 * kOut), (outH + kWRows - 1) / kWRows, n);
             resize_h_int_ratio_warp_kernel<4, 24, 2><<<gw, 32, 0, s>>>(q);
         } else if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_h_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
+        else if (VERTICAL && ir->ratio == 4 && ir->taps == 24 && !oldH && outW % 32 == 0 && p.vecOK && outW < 65536 && outH < 65536) {
+            dim3 gw(outW / 32, (outH + kVSteps * kOut - 1) / (kVSteps * kOut), n);
+            resize_v_int_ratio_warp_kernel<4, 24><<<gw, 32, 0, s>>>(q);
+        }
         else if (VERTICAL && ir->ratio == 4 && ir->taps == 24) resize_v_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
         else if (VERTICAL && ir->ratio == 2 && ir->taps == 12) resize_v_int_ratio_kernel<2, 12><<<g2, 128, 0, s>>>(q);
         else if (VERTICAL && ir->ratio == 3 && ir->taps == 17) resize_v_int_ratio_kernel<3, 17><<<g2, 128, 0, s>>>(q);
