@@ -159,19 +159,6 @@ __global__ void __launch_bounds__(256) bench(float *out, int iters, float seed) 
 }
 
 // The SSIM kernel's vertical-pass pattern: 8 accumulator pairs, 8 taps, distinct x pairs, scalar weights.
-// Every FMA is an `asm volatile`, so none can be hoisted out of the iteration loop or folded: the first version of this
-// kernel used plain fmaf() and reported 155-169 scalar lane-FMAs per clock per SM — more than the 128 FP32 lanes an SM
-// has — because only x[i][i].x changed between iterations and ptxas hoisted every FMA chain (prefix) that did not
-// depend on it ("microbenchmark sanity").  The packed form cannot be split, so it was unaffected.
-__device__ __forceinline__ void vfma(float &acc, float x, float g) { asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc) : "f"(x), "f"(g)); }
-__device__ __forceinline__ void vfma2(float2 &acc, float2 x, float g) {
-    unsigned long long a, xx, gg;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc.x), "f"(acc.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x.x), "f"(x.y));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(gg) : "f"(g));
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xx), "l"(gg));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a));
-}
 template <int PACKED>
 __global__ void __launch_bounds__(128) filt(float *out, int iters, float seed) {
     float2 x[8][4];
@@ -190,11 +177,11 @@ __global__ void __launch_bounds__(128) filt(float *out, int iters, float seed) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (PACKED) {
-                    vfma2(acc, x[j][i], g[j]);
-                    vfma2(acc2, x[(j + 3) & 7][i], g[j]);
+                    acc = __ffma2_rn(x[j][i], make_float2(g[j], g[j]), acc);
+                    acc2 = __ffma2_rn(x[(j + 3) & 7][i], make_float2(g[j], g[j]), acc2);
                 } else {
-                    vfma(acc.x, x[j][i].x, g[j]); vfma(acc.y, x[j][i].y, g[j]);
-                    vfma(acc2.x, x[(j + 3) & 7][i].x, g[j]); vfma(acc2.y, x[(j + 3) & 7][i].y, g[j]);
+                    acc.x = fmaf(x[j][i].x, g[j], acc.x); acc.y = fmaf(x[j][i].y, g[j], acc.y);
+                    acc2.x = fmaf(x[(j + 3) & 7][i].x, g[j], acc2.x); acc2.y = fmaf(x[(j + 3) & 7][i].y, g[j], acc2.y);
                 }
             }
             tot.x += acc.x + acc2.x; tot.y += acc.y + acc2.y;
@@ -281,9 +268,9 @@ int main() {
     run_filt<1>("filter pattern FFMA2", out, sms, clk, 2);
     run_filt<1>("filter pattern FFMA2", out, sms, clk, 4);
     // The scalar twin (run_filt<0>) is NOT run: only x[i][i].x changes between iterations, so ptxas hoists every FMA-chain
-    // prefix that does not depend on it out of the loop (44 of the 128 counted FMAs per iteration remain in the SASS, even
-    // with `asm volatile` — PTX carries no volatile), and round 1 printed 155-169 "lane-fma/clk/SM", above the 128 lanes
-    // an SM has.  The packed form cannot be split, so its rows are valid; scalar vs packed pipe rates are the
-    // plain "FFMA x16" / "FFMA2 x8" rows above.
+    // prefix that does not depend on it out of the loop (44 of the 128 counted FMAs per iteration remain in the SASS; an
+    // `asm volatile` version fared no better — PTX carries no volatile), and round 1 printed 155-169 "lane-fma/clk/SM",
+    // above the 128 lanes an SM has.  The packed form cannot be split, so its rows are valid; scalar vs
+    // packed pipe rates are the plain "FFMA x16" / "FFMA2 x8" rows above.
     return 0;
 }
