@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(128) resize_h_int_ratio_kernel(const IntRatioP
 #define FB_LZ_STAGES 3
 #endif
 #ifndef FB_LZ_MINB
-#define FB_LZ_MINB 20
+#define FB_LZ_MINB 24
 #endif
 constexpr int kWRows = FB_LZ_WROWS;
 constexpr int kLzStages = FB_LZ_STAGES;
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
 // Needs 16-byte-aligned rows and outW % 32 == 0 (else the kernel above runs).
 // ------------------------------------------------------------------------------------------------
 #ifndef FB_LZ_VSTEPS
-#define FB_LZ_VSTEPS 8
+#define FB_LZ_VSTEPS 12
 #endif
 constexpr int kVSteps = FB_LZ_VSTEPS;
 
