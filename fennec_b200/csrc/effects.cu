@@ -647,7 +647,65 @@ struct FxTileParams {
     double amount;
     int A, half;   // integer path: A = amount * 2^k, half = 2^(k-1)
     int vecOK;
+    int fastTiles; // Sharpen: interior tiles take sharpen_tile_fast (0: FB_FX_NOFAST=1, the round-1 path everywhere)
 };
+
+// Sharpen with a dyadic amount on a tile that lies strictly inside the image (no clamps, no per-pixel border tests, every
+// row an aligned 128-bit load plus the two neighbour pixels at immediate offsets): the same integer arithmetic as the
+// INTK >= 0 branch of fx_tile_kernel below, ~35 instead of ~62 instructions per pixel.  [fx_tile_kernel<1, 2> executed 70
+// instructions per pixel with the ALU pipe 78 % busy (profiles/r1d_ncu_summaries_msssim_analyze_fx.txt): border tests and
+// their branches, window-rotation moves, shift+mask splits and the shift/or/and packing were half of it.]  Splits use one
+// PRMT per 16-bit-lane word, the output is assembled with two PRMTs, the three-row window is renamed by full unrolling.
+template <int K>
+__device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const uint8_t *s, uint8_t *d, int x0, int yb) {
+    const uint32_t cst = (uint32_t)((1024 << K) + p.half) * 0x00010001u;
+    const uint32_t msk = (uint32_t)(0xFFFF >> K) * 0x00010001u;
+    const uint32_t mulO = (uint32_t)(p.A + (1 << K)), mulB = (uint32_t)p.A;
+    const uint8_t *row = s + (long long)(yb - 1) * p.srcRowStride + (long long)x0 * 4;
+    uint8_t *drow = d + (long long)yb * p.dstRowStride + (long long)x0 * 4;
+    // horizontal 1-2-1 sums of a row on packed 16-bit lanes (R|B and G|A words) + the row's own pixels split the same way
+    auto load_hsum = [&](const uint8_t *r, uint32_t (&hrb)[4], uint32_t (&hga)[4], uint32_t (&orb)[4], uint32_t (&oga)[4], uint32_t (&raw)[4]) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(r);
+        const uint32_t px[6] = {ld_nc_u32(r - 4), q.x, q.y, q.z, q.w, ld_nc_u32(r + 16)};
+        uint32_t rb[6], ga[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { rb[i] = px[i] & 0x00FF00FFu; ga[i] = __byte_perm(px[i], 0u, 0x4341u); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            hrb[i] = rb[i] + 2 * rb[i + 1] + rb[i + 2];
+            hga[i] = ga[i] + 2 * ga[i + 1] + ga[i + 2];
+            orb[i] = rb[i + 1]; oga[i] = ga[i + 1]; raw[i] = px[i + 1];
+        }
+    };
+    uint32_t hP_rb[4], hP_ga[4], hC_rb[4], hC_ga[4], hN_rb[4], hN_ga[4];
+    uint32_t oC_rb[4], oC_ga[4], rawC[4], oN_rb[4], oN_ga[4], rawN[4];
+    load_hsum(row, hP_rb, hP_ga, oN_rb, oN_ga, rawN);               // row yb-1 (its own pixels are not needed)
+    load_hsum(row + p.srcRowStride, hC_rb, hC_ga, oC_rb, oC_ga, rawC);   // row yb
+    row += 2 * (long long)p.srcRowStride;
+#pragma unroll
+    for (int r = 0; r < kFxRows; r++, row += p.srcRowStride, drow += p.dstRowStride) {
+        load_hsum(row, hN_rb, hN_ga, oN_rb, oN_ga, rawN);           // row yb + r + 1
+        uint32_t out[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            // gaussianBlur3x3 (effects.go:124-136): (sum + 8) >> 4 on each 16-bit lane
+            const uint32_t brb = ((hP_rb[i] + 2 * hC_rb[i] + hN_rb[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+            const uint32_t bga = ((hP_ga[i] + 2 * hC_ga[i] + hN_ga[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+            // integer unsharp, see fx_tile_kernel: T = orig*(A + 2^k) - blur*A + half + bias; out = relu(min((T >> k) - 1024, 255))
+            const uint32_t trb = ((oC_rb[i] * mulO + cst - brb * mulB) >> K) & msk;
+            const uint32_t tga = ((oC_ga[i] * mulO + cst - bga * mulB) >> K) & msk;
+            const uint32_t rrb = __viaddmin_s16x2_relu(trb, 0xFC00FC00u, 0x00FF00FFu);   // [R, 0, B, 0]
+            const uint32_t rga = __viaddmin_s16x2_relu(tga, 0xFC00FC00u, 0x00FF00FFu);   // [G, 0, x, 0]
+            out[i] = __byte_perm(__byte_perm(rrb, rga, 0x3240u), rawC[i], 0x7210u);       // [R, G, B, alpha of the source]
+        }
+        *reinterpret_cast<uint4 *>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            hP_rb[i] = hC_rb[i]; hP_ga[i] = hC_ga[i]; hC_rb[i] = hN_rb[i]; hC_ga[i] = hN_ga[i];
+            oC_rb[i] = oN_rb[i]; oC_ga[i] = oN_ga[i]; rawC[i] = rawN[i];
+        }
+    }
+}
 
 template <int MODE /*0 blur3x3, 1 sharpen, 2 adaptive*/, int INTK>
 __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
@@ -657,6 +715,15 @@ __global__ void __launch_bounds__(128) fx_tile_kernel(const FxTileParams p) {
     const uint8_t *s = p.src + (long long)img * p.srcImgStride;
     uint8_t *d = p.dst + (long long)img * p.dstImgStride;
     const bool full = p.vecOK && x0 + 4 <= p.w;
+    if (MODE == 1 && INTK >= 0) {
+        // warp-uniform: every tile of the warp strictly inside the image, source and destination rows 16-byte aligned
+        const bool dal = (((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0;
+        const bool inside = full && dal && x0 >= 4 && x0 + 5 <= p.w && yb >= 1 && yb + kFxRows + 1 <= p.h;
+        if (__all_sync(__activemask(), inside) && p.fastTiles) {
+            sharpen_tile_fast<(INTK >= 0 ? INTK : 0)>(p, s, d, x0, yb);
+            return;
+        }
+    }
     const int xl = max(x0 - 1, 0), xr = min(x0 + 4, p.w - 1);
 
     // px[0] = left neighbour, px[1..4] = own pixels, px[5] = right neighbour (clamped: only borders see the clamp)
@@ -1085,6 +1152,7 @@ static int launch_fx(cudaStream_t s, const uint8_t *src, uint8_t *dst, long long
         t.srcRowStride = rowStride; t.dstRowStride = dstRowStride;
         t.w = w; t.h = h; t.amount = amount; t.A = 0; t.half = 0;
         t.vecOK = (((uintptr_t)src | (uintptr_t)imgStride | (uintptr_t)rowStride) & 15) == 0;
+        t.fastTiles = getenv("FB_FX_NOFAST") == nullptr ? 1 : 0;
         dim3 tgrid((w + 511) / 512, (h + kFxRows - 1) / kFxRows, n);
         int k = -1;
         if (mode == 1) {  // Sharpen: is amount * 2^k an integer for a small k?  (orig<<k) + A*diff must fit in int32
