@@ -656,6 +656,9 @@ struct FxTileParams {
 // instructions per pixel with the ALU pipe 78 % busy (profiles/r1d_ncu_summaries_msssim_analyze_fx.txt): border tests and
 // their branches, window-rotation moves, shift+mask splits and the shift/or/and packing were half of it.]  Splits use one
 // PRMT per 16-bit-lane word, the output is assembled with two PRMTs, the three-row window is renamed by full unrolling.
+#ifndef FB_FX_PF
+#define FB_FX_PF 2
+#endif
 template <int K>
 __device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const uint8_t *s, uint8_t *d, int x0, int yb) {
     const uint32_t cst = (uint32_t)((1024 << K) + p.half) * 0x00010001u;
@@ -665,7 +668,7 @@ __device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const u
     uint8_t *drow = d + (long long)yb * p.dstRowStride + (long long)x0 * 4;
     // horizontal 1-2-1 sums of a row on packed 16-bit lanes (R|B and G|A words) + the row's own pixels split the same way
     auto load_hsum = [&](const uint8_t *r, uint32_t (&hrb)[4], uint32_t (&hga)[4], uint32_t (&orb)[4], uint32_t (&oga)[4], uint32_t (&raw)[4]) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(r);
+        const uint4 q = ld_nc_u128(r);   // non-coherent like the neighbour loads: free to move above the previous rows' stores
         const uint32_t px[6] = {ld_nc_u32(r - 4), q.x, q.y, q.z, q.w, ld_nc_u32(r + 16)};
         uint32_t rb[6], ga[6];
 #pragma unroll
@@ -677,6 +680,11 @@ __device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const u
             orb[i] = rb[i + 1]; oga[i] = ga[i + 1]; raw[i] = px[i + 1];
         }
     };
+#if FB_FX_PF
+    // L2 prefetch of the tile's later rows: 72 registers hold two or three rows of loads in flight, not ten
+#pragma unroll
+    for (int r = FB_FX_PF; r < kFxRows + 2; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (long long)r * p.srcRowStride));
+#endif
     uint32_t hP_rb[4], hP_ga[4], hC_rb[4], hC_ga[4], hN_rb[4], hN_ga[4];
     uint32_t oC_rb[4], oC_ga[4], rawC[4], oN_rb[4], oN_ga[4], rawN[4];
     load_hsum(row, hP_rb, hP_ga, oN_rb, oN_ga, rawN);               // row yb-1 (its own pixels are not needed)

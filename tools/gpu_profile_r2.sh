@@ -9,6 +9,7 @@ for op in "$@"; do
     msssim)  args="--pairs 2 --iters 1 --w 7680 --h 4320"; rx='box|ssim'; cnt=14;;
     ssim)    args="--pairs 32 --iters 2"; rx='ssim_strip'; cnt=1;;
     blur)    args="--pairs 4 --iters 1 --opaque"; rx="blur"; cnt=2;;
+    sharpen) args="--pairs 4 --iters 1 --opaque"; rx="fx_tile"; cnt=1;;
     *)       args="--pairs 4 --iters 1 --opaque"; rx="blur|sharpen|fx_tile|adaptive|box|ycbcr|analyze|orient|palette"; cnt=4;;
   esac
   timeout 300 $NCU -k regex:$rx -c $cnt -f -o gpurun_out/${tag}_$op python tools/profile_driver.py $op $args > gpurun_out/${tag}_$op.log 2>&1
