@@ -399,9 +399,6 @@ __device__ __forceinline__ uint32_t mean2x2_px(uint32_t a0, uint32_t a1, uint32_
     return (((rb + 0x00020002u) >> 2) & 0x00FF00FFu) | ((((ga + 0x00020002u) >> 2) & 0x00FF00FFu) << 8);
 }
 
-#ifndef FB_F2_PIPE
-#define FB_F2_PIPE 0
-#endif
 #ifndef FB_F2_PF
 #define FB_F2_PF 1
 #endif
@@ -455,33 +452,9 @@ __global__ void __launch_bounds__(kF2Threads, MINB) box_fused2_kernel(const BoxF
                 }
                 *reinterpret_cast<uint32_t *>(op) = mean2x2_px(L1[0][0], L1[0][1], L1[1][0], L1[1][1]);
             };
-#if FB_F2_PIPE
-            // Two steps (eight 128-bit loads) are evaluated while the NEXT two are already in flight: the loads of a
-            // pair are issued before the previous pair is consumed, so a thread always has 8-16 loads outstanding
-            // instead of 0-8.  The two buffer sets swap roles (no register moves).
-            auto load4 = [&](uint4 (&t)[4], const uint8_t *qq) {
-#pragma unroll
-                for (int r = 0; r < 4; r++) t[r] = ld_nc_u128(qq + (long long)r * rs);
-            };
-            uint4 ta[4], tb[4], na[4], nb[4];
-            int k = k0;
-            load4(ta, q);                                          // k0 < k1 here
-            if (k + 1 < k1) load4(tb, q + 4 * (long long)rs);
-            // evaluates steps k, k+1 from (ca, cb) after issuing the loads of k+2, k+3 into (fa, fb); false when done
-            auto pair = [&](const uint4 (&ca)[4], const uint4 (&cb)[4], uint4 (&fa)[4], uint4 (&fb)[4]) -> bool {
-                const bool hb = k + 1 < k1, hna = k + 2 < k1, hnb = k + 3 < k1;
-                if (hna) load4(fa, q + 8 * (long long)rs);
-                if (hnb) load4(fb, q + 12 * (long long)rs);
-                step(ca, k, o);
-                if (hb) step(cb, k + 1, o + p.l2RowStride);
-                k += 2; q += 8 * (long long)rs; o += 2 * (long long)p.l2RowStride;
-                return hna;
-            };
-            for (;;) {
-                if (!pair(ta, tb, na, nb)) break;
-                if (!pair(na, nb, ta, tb)) break;
-            }
-#else
+            // [Measured and dropped (profiles/r2_tuning_sweep.txt): register double-buffering of the NEXT pair of steps (needs 2
+            // CTAs per SM: 1.16 ms per 16 8K pairs against 1.13) and a rolling two-step pipeline at the same register
+            // count (ptxas spills at 80 registers: 1.44-1.60 ms; 1.23 at 2 CTAs).  The L2 prefetch below costs nothing.]
             int k = k0;
             for (; k + 2 <= k1; k += 2, q += 8 * (long long)rs, o += 2 * (long long)p.l2RowStride) {
                 uint4 ta[4], tb[4];
@@ -507,7 +480,6 @@ __global__ void __launch_bounds__(kF2Threads, MINB) box_fused2_kernel(const BoxF
                 for (int r = 0; r < 4; r++) ta[r] = ld_nc_u128(q + (long long)r * rs);
                 step(ta, k, o);
             }
-#endif
             a0.flush(colsum0, dy0, pitch0, 4 * st);
             a1.flush(colsum1, dy1, pitch1, 2 * st);
         }
