@@ -960,6 +960,50 @@ __device__ __forceinline__ uint32_t adaptive_exact_at(const uint8_t *img, int rs
     return o[0] | (o[1] << 8) | (o[2] << 16) | (c & 0xFF000000u);
 }
 
+// AdaptiveSharpen on a tile strictly inside the image (the counterpart of sharpen_tile_fast): aligned non-coherent row
+// loads with an L2 prefetch of the later rows, PRMT splits, no border tests, the horizontal 1-2-1 luma sums shared by the
+// Sobel rows above and below.  Same FP32 evaluation, same bound and the same per-warp exact queue as the general body
+// below; returns through the caller's queue drain.
+__device__ __forceinline__ uint32_t adaptive_row_fast(const uint32_t (&hP_rb)[4], const uint32_t (&hP_ga)[4], const uint32_t (&hC_rb)[4],
+                                                      const uint32_t (&hC_ga)[4], const uint32_t (&hN_rb)[4], const uint32_t (&hN_ga)[4],
+                                                      const int (&hlP)[4], const int (&hlN)[4], const int (&colsum)[6],
+                                                      const uint32_t (&rawC)[4], float amountF, uint32_t (&out)[4]) {
+    const float kMagic = 12582912.0f;
+    uint32_t ambMask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t c = rawC[i];
+        const uint32_t brb = ((hP_rb[i] + 2 * hC_rb[i] + hN_rb[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+        const uint32_t bga = ((hP_ga[i] + 2 * hC_ga[i] + hN_ga[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+        const int GX = colsum[i + 2] - colsum[i];
+        const int GY = hlN[i] - hlP[i];
+        const float gxf = __int_as_float(GX + 0x4B400000) - kMagic;
+        const float gyf = __int_as_float(GY + 0x4B400000) - kMagic;
+        const float g2 = fmaxf(fmaf(gxf, gxf, gyf * gyf), 1e-30f);
+        const float la = amountF * fminf(g2 * rsqrtf(g2) * 2.5e-6f, 1.0f);
+        const float lim = 0.5f - fmaf(la, 255.0f * 7.5e-7f, 8e-5f);
+        const float oR = __uint_as_float(__byte_perm(c, 0x4B400000u, 0x7650u)) - kMagic;
+        const float oG = __uint_as_float(__byte_perm(c, 0x4B400000u, 0x7651u)) - kMagic;
+        const float oB = __uint_as_float(__byte_perm(c, 0x4B400000u, 0x7652u)) - kMagic;
+        const float bR = __uint_as_float(__byte_perm(brb, 0x4B400000u, 0x7650u)) - kMagic;
+        const float bG = __uint_as_float(__byte_perm(bga, 0x4B400000u, 0x7650u)) - kMagic;
+        const float bB = __uint_as_float(__byte_perm(brb, 0x4B400000u, 0x7652u)) - kMagic;
+        const float o3[3] = {oR, oG, oB}, b3[3] = {bR, bG, bB};
+        float t3[3];
+        float worst = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            float v = fmaf(la, o3[ch] - b3[ch], o3[ch]);   // orig - blur is an exact small integer
+            v = fminf(fmaxf(v, 0.0f), 255.0f);             // ties at -0.5 / 255.5 cannot change the clamped result
+            t3[ch] = v + kMagic;
+            worst = fmaxf(worst, fabsf(v - (t3[ch] - kMagic)));
+        }
+        if (worst >= lim) ambMask |= 1u << i;
+        out[i] = pack_rgba_low_bytes(t3[0], t3[1], t3[2], c);
+    }
+    return ambMask;
+}
+
 __global__ void __launch_bounds__(128) adaptive_tile_kernel(const FxTileParams p) {
     __shared__ uint32_t ambQ[4][kAdQ];
     __shared__ int ambN[4];
@@ -1005,6 +1049,80 @@ __global__ void __launch_bounds__(128) adaptive_tile_kernel(const FxTileParams p
     };
     const float amountF = (float)p.amount;
     const float kMagic = 12582912.0f;
+
+    // warp-uniform: every tile of the warp strictly inside the image, rows 16-byte aligned
+    if (p.fastTiles && __all_sync(0xffffffffu, active && dvec && xa >= 4 && xa + 5 <= p.w && yb >= 1 && yb + kFxRows + 1 <= p.h)) {
+        const uint8_t *row = s + (long long)(yb - 1) * p.srcRowStride + (long long)xa * 4;
+        uint8_t *drow = d + (long long)yb * p.dstRowStride + (long long)xa * 4;
+#pragma unroll
+        for (int r = 2; r < kFxRows + 2; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (long long)r * p.srcRowStride));
+        // one row: 1-2-1 sums of the colour lanes, integer lumas x1000 of the six pixels and their 1-2-1 sums, raw pixels
+        auto load_row_fast = [&](const uint8_t *r, uint32_t (&hrb)[4], uint32_t (&hga)[4], int (&L)[6], int (&hl)[4], uint32_t (&raw)[4]) {
+            const uint4 q = ld_nc_u128(r);
+            const uint32_t px[6] = {ld_nc_u32(r - 4), q.x, q.y, q.z, q.w, ld_nc_u32(r + 16)};
+            uint32_t rb[6], ga[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                rb[i] = px[i] & 0x00FF00FFu; ga[i] = __byte_perm(px[i], 0u, 0x4341u);
+                L[i] = (int)__dp2a_lo(299u | (587u << 16), px[i], __dp2a_hi(114u, px[i], 0u));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                hrb[i] = rb[i] + 2 * rb[i + 1] + rb[i + 2];
+                hga[i] = ga[i] + 2 * ga[i + 1] + ga[i + 2];
+                hl[i] = L[i] + 2 * L[i + 1] + L[i + 2];
+                raw[i] = px[i + 1];
+            }
+        };
+        uint32_t hP_rb[4], hP_ga[4], hC_rb[4], hC_ga[4], hN_rb[4], hN_ga[4], rawP[4], rawC[4], rawN[4];
+        int lP[6], lC[6], lN[6], hlP[4], hlC[4], hlN[4];
+        load_row_fast(row, hP_rb, hP_ga, lP, hlP, rawP);
+        load_row_fast(row + p.srcRowStride, hC_rb, hC_ga, lC, hlC, rawC);
+        row += 2 * (long long)p.srcRowStride;
+#pragma unroll 1
+        for (int r = 0; r < kFxRows; r++, row += p.srcRowStride, drow += p.dstRowStride) {
+            load_row_fast(row, hN_rb, hN_ga, lN, hlN, rawN);
+            int colsum[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) colsum[i] = lP[i] + 2 * lC[i] + lN[i];
+            uint32_t out[4];
+            const uint32_t ambMask = adaptive_row_fast(hP_rb, hP_ga, hC_rb, hC_ga, hN_rb, hN_ga, hlP, hlN, colsum, rawC, amountF, out);
+            *reinterpret_cast<uint4 *>(drow) = make_uint4(out[0], out[1], out[2], out[3]);
+            amb_push(ambMask, xa, yb + r, 1, 0, ambQ[warp], &ambN[warp]);
+            __syncwarp();
+            {   // drain 32 at a time (warp-uniform decision on lane 0's view, see amb_drain)
+                int n = __shfl_sync(0xffffffffu, ambN[warp], 0);
+                if (n >= 32) {
+                    while (n >= 32) {
+                        n -= 32;
+                        const uint32_t code = ambQ[warp][n + lane];
+                        const int ex = (int)(code & 0xFFFFu), ey = (int)(code >> 16);
+                        *reinterpret_cast<uint32_t *>(d + (long long)ey * p.dstRowStride + (long long)ex * 4) = adaptive_exact_at(s, p.srcRowStride, ex, ey, p.amount);
+                    }
+                    __syncwarp();
+                    if (lane == 0) ambN[warp] = n;
+                    __syncwarp();
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                hP_rb[i] = hC_rb[i]; hP_ga[i] = hC_ga[i]; hC_rb[i] = hN_rb[i]; hC_ga[i] = hN_ga[i];
+                hlP[i] = hlC[i]; hlC[i] = hlN[i]; rawC[i] = rawN[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { lP[i] = lC[i]; lC[i] = lN[i]; }
+        }
+        __syncwarp();
+        {   // leftovers
+            const int n = __shfl_sync(0xffffffffu, ambN[warp], 0);
+            if (lane < n) {
+                const uint32_t code = ambQ[warp][lane];
+                const int ex = (int)(code & 0xFFFFu), ey = (int)(code >> 16);
+                *reinterpret_cast<uint32_t *>(d + (long long)ey * p.dstRowStride + (long long)ex * 4) = adaptive_exact_at(s, p.srcRowStride, ex, ey, p.amount);
+            }
+        }
+        return;
+    }
 
     uint32_t pPrev[6], pCur[6], pNext[6];
     uint32_t hPrevRB[4], hPrevGA[4], hCurRB[4], hCurGA[4], hNextRB[4], hNextGA[4];
