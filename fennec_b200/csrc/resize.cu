@@ -259,12 +259,12 @@ __device__ __forceinline__ uint32_t clamp255_from_magic(float t) {
     return (uint32_t)__viaddmin_s32_relu(__float_as_int(t), -0x4B400000, 255);
 }
 
-// kOut interior outputs from one window of packed pixels (compile-time tap indices); the window starts at raw[LEAD].
-template <int R, int T, int LEAD, int NRAW>
+// KO interior outputs from one window of packed pixels (compile-time tap indices); the window starts at raw[LEAD].
+template <int R, int T, int LEAD, int NRAW, int KO = kOut>
 __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], const IntRatioParams &q,
-                                                 uint32_t (&outv)[kOut], bool (&ambv)[kOut]) {
-    constexpr int NIN = T + (kOut - 1) * R;
-    static_assert(NRAW >= NIN + LEAD && kOut % 2 == 0, "window does not fit");
+                                                 uint32_t (&outv)[KO], bool (&ambv)[KO]) {
+    constexpr int NIN = T + (KO - 1) * R;
+    static_assert(NRAW >= NIN + LEAD && KO % 2 == 0, "window does not fit");
     const ResizeParams &p = q.base;
     uint32_t andA = 0xFFFFFFFFu;
 #pragma unroll
@@ -281,11 +281,11 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
         // on the (R,G) pair and on the B values of two outputs, one VIADDMNMX.RELU per channel (Lanczos overshoots,
         // so the clamp is real), three PRMTs.  [The general finish_fp32 — reciprocal, per-pixel bound, float clamps —
         // was 55 of the 168 instructions per output, profiles/r2s2_lanczos.]
-        float2 accRG[kOut], accB[kOut / 2];
+        float2 accRG[KO], accB[KO / 2];
 #pragma unroll
-        for (int j = 0; j < kOut; j++) accRG[j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < KO; j++) accRG[j] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int m = 0; m < kOut / 2; m++) accB[m] = make_float2(0.f, 0.f);
+        for (int m = 0; m < KO / 2; m++) accB[m] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
             const uint32_t px = raw[LEAD + i];
@@ -293,7 +293,7 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
                                                      __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7541u))), kMagic2);
             const float bl = byte_f(px, 2);
 #pragma unroll
-            for (int j = 0; j < kOut; j++) {
+            for (int j = 0; j < KO; j++) {
                 const int t = i - j * R;  // tap of input i for output j
                 if (t >= 0 && t < T) {
                     const float w = q.wn[t >= 0 && t < T ? t : 0];
@@ -307,7 +307,7 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
         const float2 neg1 = make_float2(-1.0f, -1.0f);
         const float lim = 0.5f - q.Eo;
 #pragma unroll
-        for (int m = 0; m < kOut / 2; m++) {
+        for (int m = 0; m < KO / 2; m++) {
             float2 t[3], d[3];   // (R,G) of output 2m, (R,G) of output 2m+1, B of both
             const float2 v[3] = {accRG[2 * m], accRG[2 * m + 1], accB[m]};
 #pragma unroll
@@ -324,9 +324,9 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
             outv[2 * m + 1] = __byte_perm(x1, __byte_perm(clamp255_from_magic(t[2].y), q.opaqueA, 0x7000), 0x7610);
         }
     } else {  // translucent window (or shortcut disabled): premultiply once per pixel (R*alpha is an exact integer), 4 sums per output
-        float2 accRG[kOut], accBA[kOut];
+        float2 accRG[KO], accBA[KO];
 #pragma unroll
-        for (int j = 0; j < kOut; j++) accRG[j] = accBA[j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < KO; j++) accRG[j] = accBA[j] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
             const uint32_t px = raw[LEAD + i];
@@ -336,7 +336,7 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
             const float2 prg = __fmul2_rn(rg, make_float2(fa, fa));
             const float2 pba = make_float2(byte_f(px, 2) * fa, fa);
 #pragma unroll
-            for (int j = 0; j < kOut; j++) {
+            for (int j = 0; j < KO; j++) {
                 const int t = i - j * R;
                 if (t >= 0 && t < T) {
                     const float w = q.w[t >= 0 && t < T ? t : 0];
@@ -346,7 +346,7 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
             }
         }
 #pragma unroll
-        for (int j = 0; j < kOut; j++)
+        for (int j = 0; j < KO; j++)
             outv[j] = finish_fp32(accRG[j].x, accRG[j].y, accBA[j].x, accBA[j].y, p.Er, p.Ea, ambv[j]);
     }
 }
@@ -553,6 +553,12 @@ __global__ void __launch_bounds__(128) resize_h_int_ratio_kernel(const IntRatioP
 #ifndef FB_LZ_MINB
 #define FB_LZ_MINB 24
 #endif
+#ifndef FB_LZ_KO_DEFAULT
+#define FB_LZ_KO_DEFAULT 4
+#endif
+#ifndef FB_LZ_MINB8
+#define FB_LZ_MINB8 16
+#endif
 constexpr int kWRows = FB_LZ_WROWS;
 constexpr int kLzStages = FB_LZ_STAGES;
 constexpr int kLzQ = 32 * kOut + 32;   // a row adds at most 32*kOut entries to fewer than 32 leftovers
@@ -574,25 +580,26 @@ __device__ __noinline__ void lz_exact_queue(const ResizeParams &p, const uint8_t
     }
 }
 
-template <int R, int T, int LEAD>
-__global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel(const __grid_constant__ IntRatioParams q) {
-    constexpr int NIN = T + (kOut - 1) * R;              // window of one lane
+template <int R, int T, int LEAD, int KO, int STAGES, int MINB>
+__global__ void __launch_bounds__(32, MINB) resize_h_int_ratio_warp_kernel(const __grid_constant__ IntRatioParams q) {
+    constexpr int NIN = T + (KO - 1) * R;                // window of one lane
     constexpr int NRAW = (NIN + LEAD + 3) / 4 * 4;        // ... read as whole quads
-    constexpr int STEP = R * kOut;                        // source pixels between the windows of adjacent lanes
-    static_assert(STEP == 16, "staging assumes one 16-px chunk per lane");
+    constexpr int STEP = R * KO;                          // source pixels between the windows of adjacent lanes = one chunk
+    static_assert(STEP % 4 == 0 && 32 % (STEP / 4) == 0 && KO % 4 == 0, "chunks are whole quads, 32 quads are whole chunks");
+    constexpr int QPC = STEP / 4;                         // 16-byte quads per chunk
     constexpr int SPAN = STEP * 31 + NRAW;                // staged pixels per row
     constexpr int QUADS = SPAN / 4;
     constexpr int NK = (QUADS + 31) / 32;                 // 16-byte copies per lane and row
-    constexpr int CHUNKS = (SPAN + 15) / 16;
-    constexpr int CHB = 80;                               // 16-px chunk + 16 B pad: conflict-free LDS.128 at 1 chunk / lane
+    constexpr int CHUNKS = (SPAN + STEP - 1) / STEP;
+    constexpr int CHB = STEP * 4 + 16;                    // chunk + 16 B pad: conflict-free LDS.128 at 1 chunk / lane
     constexpr int STAGEB = CHUNKS * CHB;
     const ResizeParams &p = q.base;
-    __shared__ __align__(16) uint8_t stage[kLzStages][STAGEB];
-    __shared__ uint32_t ambQ[kLzQ];
+    __shared__ __align__(16) uint8_t stage[STAGES][STAGEB];
+    __shared__ uint32_t ambQ[32 * KO + 32];   // a row adds at most 32*KO entries to fewer than 32 leftovers
     const int lane = threadIdx.x;
     const int img = blockIdx.z;
-    const int xw = blockIdx.x * (32 * kOut);              // first output of the warp
-    const int x0 = xw + lane * kOut;
+    const int xw = blockIdx.x * (32 * KO);              // first output of the warp
+    const int x0 = xw + lane * KO;
     const uint8_t *s = p.src + (long long)img * p.srcImgStride;
     uint8_t *dimg = p.dst + (long long)img * p.dstImgStride;
     const int yFirst = blockIdx.y * kWRows;
@@ -600,8 +607,8 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
     const int sBase = R * xw + q.off - LEAD;              // staging pixel u <-> source pixel sBase + u; multiple of 4
     const bool al16 = ((((uintptr_t)s + (long long)sBase * 4) | (uintptr_t)p.srcRowStride) & 15) == 0;
     const bool interiorSpan = al16 && sBase >= 0 && sBase + SPAN <= p.srcW;
-    const bool dvec = ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0) && x0 + kOut <= p.outW;
-    const uint32_t myStage = (uint32_t)__cvta_generic_to_shared(&stage[0][0]) + (lane >> 2) * CHB + (lane & 3) * 16;
+    const bool dvec = ((((uintptr_t)p.dst | (uintptr_t)p.dstImgStride | (uintptr_t)p.dstRowStride) & 15) == 0) && x0 + KO <= p.outW;
+    const uint32_t myStage = (uint32_t)__cvta_generic_to_shared(&stage[0][0]) + (lane / QPC) * CHB + (lane % QPC) * 16;
     const uint8_t *myRow = s + (long long)sBase * 4 + lane * 16;   // this lane's first quad of row 0
     auto stage_row = [&](int y, int slot) {
         if (y < yLast) {
@@ -611,7 +618,7 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
 #pragma unroll
                 for (int k = 0; k < NK; k++)
                     if (k < QUADS / 32 || lane < QUADS - 32 * k)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * 8 * CHB), "l"(g + k * 512) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * (32 / QPC) * CHB), "l"(g + k * 512) : "memory");
             } else {              // first / last warp of a row or an unaligned source: zero outside the row
 #pragma unroll 1
                 for (int k = 0; k < NK; k++) {
@@ -619,13 +626,13 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
                     if (v < QUADS) {
                         const int sx = sBase + 4 * v;
                         if (al16 && sx >= 0 && sx + 4 <= p.srcW) {
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * 8 * CHB), "l"(g + k * 512) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + k * (32 / QPC) * CHB), "l"(g + k * 512) : "memory");
                         } else {
                             uint32_t t[4];
 #pragma unroll
                             for (int i = 0; i < 4; i++)
                                 t[i] = (sx + i >= 0 && sx + i < p.srcW) ? __ldg(reinterpret_cast<const uint32_t *>(g + k * 512 + i * 4)) : 0u;
-                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d + k * 8 * CHB), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d + k * (32 / QPC) * CHB), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
                         }
                     }
                 }
@@ -635,40 +642,42 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
     };
     int nq = 0;   // queue length (warp-uniform, in a register: pushes are ballot-compacted, no atomics)
 #pragma unroll
-    for (int k = 0; k < kLzStages - 1; k++) stage_row(yFirst + k, k);
+    for (int k = 0; k < STAGES - 1; k++) stage_row(yFirst + k, k);
     int slot = 0;
 #pragma unroll 1
     for (int y0 = yFirst; y0 < yLast; y0++) {
         // the slot row y0-1 used is free: every lane passed the __syncwarp at the end of that row
-        stage_row(y0 + kLzStages - 1, slot == 0 ? kLzStages - 1 : slot - 1);
-        cp_async_wait_group<kLzStages - 1>();   // this lane's copies of row y0 have landed
+        stage_row(y0 + STAGES - 1, slot == 0 ? STAGES - 1 : slot - 1);
+        cp_async_wait_group<STAGES - 1>();   // this lane's copies of row y0 have landed
         __syncwarp();                           // ... and everybody else's
-        uint32_t outv[kOut];
-        bool ambv[kOut];
-        if (x0 >= q.dLo && x0 + kOut <= q.dHi) {
+        uint32_t outv[KO];
+        bool ambv[KO];
+        if (x0 >= q.dLo && x0 + KO <= q.dHi) {
             uint32_t raw[NRAW];
-            const uint8_t *wbase = &stage[slot][0] + lane * CHB;   // staging pixels 16*lane .. 16*lane + NRAW - 1
+            const uint8_t *wbase = &stage[slot][0] + lane * CHB;   // staging pixels STEP*lane .. STEP*lane + NRAW - 1
 #pragma unroll
             for (int v4 = 0; v4 < NRAW / 4; v4++) {
                 const int u = v4 * 4;
-                const uint4 t4 = *reinterpret_cast<const uint4 *>(wbase + (u >> 4) * CHB + (u & 15) * 4);
+                const uint4 t4 = *reinterpret_cast<const uint4 *>(wbase + (u / STEP) * CHB + (u % STEP) * 4);
                 raw[u] = t4.x; raw[u + 1] = t4.y; raw[u + 2] = t4.z; raw[u + 3] = t4.w;
             }
-            int_ratio_window<R, T, LEAD, NRAW>(raw, q, outv, ambv);
+            int_ratio_window<R, T, LEAD, NRAW, KO>(raw, q, outv, ambv);
         } else {  // edge outputs (clipped / renormalised taps; or beyond the row): straight to the exact queue
 #pragma unroll
-            for (int j = 0; j < kOut; j++) { ambv[j] = true; outv[j] = 0u; }
+            for (int j = 0; j < KO; j++) { ambv[j] = true; outv[j] = 0u; }
         }
         uint8_t *drow = dimg + (long long)y0 * p.dstRowStride + (long long)x0 * 4;
-        if (dvec) {
-            *reinterpret_cast<uint4 *>(drow) = make_uint4(outv[0], outv[1], outv[2], outv[3]);   // queued ones are overwritten below
+        if (dvec) {   // queued ones are overwritten below
+#pragma unroll
+            for (int v = 0; v < KO / 4; v++)
+                *reinterpret_cast<uint4 *>(drow + 16 * v) = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
         } else {
 #pragma unroll
-            for (int j = 0; j < kOut; j++)
+            for (int j = 0; j < KO; j++)
                 if (x0 + j < p.outW) *reinterpret_cast<uint32_t *>(drow + j * 4) = outv[j];
         }
 #pragma unroll
-        for (int j = 0; j < kOut; j++) {
+        for (int j = 0; j < KO; j++) {
             const bool push = ambv[j] && x0 + j < p.outW;
             const uint32_t b = __ballot_sync(0xffffffffu, push);
             if (b) {   // warp-uniform
@@ -681,7 +690,7 @@ __global__ void __launch_bounds__(32, FB_LZ_MINB) resize_h_int_ratio_warp_kernel
             nq -= 32;
             lz_exact_queue<false>(p, s, dimg, ambQ + nq, 32);
         }
-        slot = slot == kLzStages - 1 ? 0 : slot + 1;
+        slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
     if (nq > 0) lz_exact_queue<false>(p, s, dimg, ambQ, nq);
 }
@@ -805,10 +814,15 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
                            : dim3(((outW + kOut - 1) / kOut + 127) / 128, (outH + kRowsPerBlock - 1) / kRowsPerBlock, n);
         bool launched = true;
         static const bool oldH = getenv("FB_LZ_OLD") != nullptr;   // round-1 block-wide kernel, kept for A/B runs
-        static_assert(kOut == 4, "the 128-bit output store assumes four outputs per lane");
+        static const int hko = [] { const char *e = getenv("FB_LZ_KO"); return (e && e[0] == '4') ? 4 : (e && e[0] == '8') ? 8 : FB_LZ_KO_DEFAULT; }();
         if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && ((ir->off % 4) + 4) % 4 == 2 && !oldH && outW < 65536 && outH < 65536) {
-            dim3 gw((outW + 32 * kOut - 1) / (32 * kOut), (outH + kWRows - 1) / kWRows, n);
-            resize_h_int_ratio_warp_kernel<4, 24, 2><<<gw, 32, 0, s>>>(q);
+            if (hko == 8) {   // eight outputs per lane: 256 outputs per warp and row
+                dim3 gw((outW + 32 * 8 - 1) / (32 * 8), (outH + kWRows - 1) / kWRows, n);
+                resize_h_int_ratio_warp_kernel<4, 24, 2, 8, 2, FB_LZ_MINB8><<<gw, 32, 0, s>>>(q);
+            } else {
+                dim3 gw((outW + 32 * 4 - 1) / (32 * 4), (outH + kWRows - 1) / kWRows, n);
+                resize_h_int_ratio_warp_kernel<4, 24, 2, 4, kLzStages, FB_LZ_MINB><<<gw, 32, 0, s>>>(q);
+            }
         } else if (!VERTICAL && ir->ratio == 4 && ir->taps == 24 && (ir->off & 1) == 0) resize_h_int_ratio_kernel<4, 24><<<g2, 128, 0, s>>>(q);
         else if (VERTICAL && ir->ratio == 4 && ir->taps == 24 && !oldH && outW % 32 == 0 && p.vecOK && outW < 65536 && outH < 65536) {
             dim3 gw(outW / 32, (outH + kVSteps * kOut - 1) / (kVSteps * kOut), n);

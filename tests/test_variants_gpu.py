@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("env", [
     {"FB_SSIM_WS": "1"}, {"FB_SSIM_CPL": "2"}, {"FB_SSIM_CPL": "3"},
-    {"FB_LZ_OLD": "1"}, {"FB_LZ_NO_OPAQUE": "1"},
+    {"FB_LZ_OLD": "1"}, {"FB_LZ_NO_OPAQUE": "1"}, {"FB_LZ_KO": "8"}, {"FB_FX_NOFAST": "1"},
     {"FB_SSIM_MODE": "0", "FB_SSIM_WPB": "4"}, {"FB_SSIM_MODE": "0", "FB_SSIM_WPB": "1"},
     {"FB_SSIM_MODE": "2", "FB_SSIM_WPB": "4"}, {"FB_SSIM_MODE": "1"}, {"FB_SSIM_MODE": "3"}, {"FB_SSIM_MODE": "4"}, {"FB_SSIM_MODE": "5"}, {"FB_SSIM_MODE": "6"},
     {"FB_BLUR_WPB": "4", "FB_BOX_NOFUSE2": "1", "FB_NO_STAGING": "1"},
