@@ -118,6 +118,9 @@ struct StripCtx {
 #ifndef FB_SSIM_STAGES
 #define FB_SSIM_STAGES 4
 #endif
+#ifndef FB_SSIM_MINB1
+#define FB_SSIM_MINB1 8    // one-warp blocks, CPL = 4: resident blocks the register allocation aims at (10 -> <= 200 registers)
+#endif
 #ifndef FB_SSIM_MINB3
 #define FB_SSIM_MINB3 12   // CPL = 3: one-warp blocks per SM the register allocation aims at (12 -> <= 168 registers)
 #endif
@@ -482,6 +485,9 @@ __device__ __forceinline__ double walk_strip_pipe(const StripCtx<4> &q) {
 // protocol of walk_strip valid.  An odd row count runs the second half of the last iteration on stale ring
 // data (finite: real pixel rows) with its outputs masked.
 // ------------------------------------------------------------------------------------------------
+#ifndef FB_SSIM_PXMASK
+#define FB_SSIM_PXMASK 1   // 1: 200 registers (10 one-warp blocks per SM), 1.677 ms per 64 4K pairs; 0: one FSEL per pixel less but 204 registers (9 blocks), 1.736 ms
+#endif
 struct HConsts {
     float c, kTh;
     float2 qpInit, one_two, neg2;
@@ -489,7 +495,7 @@ struct HConsts {
 
 template <int CPL>
 __device__ __forceinline__ void hpass_formula(const float4 (&own)[CPL], const float4 *vb, const float2 (&g2)[8],
-                                              const HConsts &k, const bool (&ok)[CPL], float (&fs)[CPL]) {
+                                              const HConsts &k, float (&fs)[CPL], const bool (&valid)[CPL], bool rowOK) {
     constexpr int kVLanes = 36;
     float4 it[CPL + 7];
 #pragma unroll
@@ -511,8 +517,15 @@ __device__ __forceinline__ void hpass_formula(const float4 (&own)[CPL], const fl
         const float2 AB1 = __ffma2_rn(make_float2(th, th), k.one_two, mn);
         const float2 AB2 = __ffma2_rn(mn, k.neg2, make_float2(mqp.y, mqp.x));
         const float2 nd = __fmul2_rn(AB1, AB2);
-        const float ssim4 = __fdividef(nd.x, nd.y);
-        fs[i] += ok[i] ? ssim4 : 0.f;
+        // fs += num * (1/den) as ONE FMA; columns without a valid output (the strip's last two lanes, lanes right of the
+        // image) accumulate finite values that the caller drops at the end, rows past the segment are skipped by the caller
+        float rden;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(nd.y));   // den in [C1*C2/4, ~1e10]: no range fix-up needed (__fdividef adds an FSETP and two predicated FMULs)
+#if FB_SSIM_PXMASK
+        fs[i] = fmaf((valid[i] && rowOK) ? nd.x : 0.f, rden, fs[i]);   // per-pixel mask (FSEL), as round 1
+#else
+        fs[i] = fmaf(nd.x, rden, fs[i]);
+#endif
     }
 }
 
@@ -602,9 +615,6 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
 #pragma unroll
     for (int i = 0; i < CPL; i++) fs[i] = 0.f;
     constexpr int kVLanes = 36, kVBuf = CPL * kVLanes;
-    bool okA[CPL], okB[CPL];
-#pragma unroll
-    for (int i = 0; i < CPL; i++) okA[i] = q.valid[i];
 
 #pragma unroll 1
     for (int r = 7; r < nIn; r += 2) {
@@ -626,17 +636,14 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
 #pragma unroll
         for (int i = 0; i < CPL; i++) { vbA[i * kVLanes] = vA[i]; vbB[i * kVLanes] = vB[i]; }
         __syncwarp();
-        const bool second = r + 1 < nIn;
-#pragma unroll
-        for (int i = 0; i < CPL; i++) okB[i] = q.valid[i] && second;
-        hpass_formula<CPL>(vA, vbA, g2, hk, okA, fs);
-        hpass_formula<CPL>(vB, vbB, g2, hk, okB, fs);
+        hpass_formula<CPL>(vA, vbA, g2, hk, fs, q.valid, true);
+        if (FB_SSIM_PXMASK || r + 1 < nIn) hpass_formula<CPL>(vB, vbB, g2, hk, fs, q.valid, r + 1 < nIn);   // warp-uniform: an odd row count ends on a half iteration
     }
 #undef W2_PLANES
 #undef W2_VTAPS
     double dsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    for (int i = 0; i < CPL; i++) dsum += q.valid[i] ? (double)fs[i] : 0.0;
     return dsum;
 }
 
@@ -734,19 +741,19 @@ __device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < NR; j++) {
-            const bool rowOK = r + j < nIn;
-            bool ok[CPL];
-            float4 own[CPL];
+            if (r + j < nIn) {   // warp-uniform
+                float4 own[CPL];
 #pragma unroll
-            for (int i = 0; i < CPL; i++) { ok[i] = q.valid[i] && rowOK; own[i] = vb0[j * kVBuf + i * kVLanes]; }
-            hpass_formula(own, vb0 + j * kVBuf, g2, hk, ok, fs);
+                for (int i = 0; i < CPL; i++) own[i] = vb0[j * kVBuf + i * kVLanes];
+                hpass_formula(own, vb0 + j * kVBuf, g2, hk, fs, q.valid, true);
+            }
         }
     }
 #undef WN_PLANES
 #undef WN_VTAPS_STS
     double dsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    for (int i = 0; i < CPL; i++) dsum += q.valid[i] ? (double)fs[i] : 0.0;
     return dsum;
 }
 
@@ -859,9 +866,6 @@ __device__ __forceinline__ double walk_strip_tma(const StripCtx<4> &q, const Tma
 #pragma unroll
     for (int i = 0; i < CPL; i++) fs[i] = 0.f;
     constexpr int kVLanes = 36, kVBuf = CPL * kVLanes;
-    bool okA[CPL], okB[CPL];
-#pragma unroll
-    for (int i = 0; i < CPL; i++) okA[i] = q.valid[i];
 
 #pragma unroll 1
     for (int r = 7; r < nIn; r += 2) {
@@ -886,16 +890,14 @@ __device__ __forceinline__ double walk_strip_tma(const StripCtx<4> &q, const Tma
 #pragma unroll
         for (int i = 0; i < CPL; i++) { vbA[i * kVLanes] = vA[i]; vbB[i * kVLanes] = vB[i]; }
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < CPL; i++) okB[i] = q.valid[i] && second;
-        hpass_formula(vA, vbA, g2, hk, okA, fs);
-        hpass_formula(vB, vbB, g2, hk, okB, fs);
+        hpass_formula(vA, vbA, g2, hk, fs, q.valid, true);
+        if (second) hpass_formula(vB, vbB, g2, hk, fs, q.valid, true);   // warp-uniform
     }
 #undef WT_PLANES
 #undef WT_VTAPS
     double dsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < CPL; i++) dsum += (double)fs[i];
+    for (int i = 0; i < CPL; i++) dsum += q.valid[i] ? (double)fs[i] : 0.0;
     return dsum;
 }
 
@@ -976,10 +978,15 @@ __global__ void __launch_bounds__(32, 8) ssim_strip_tma_kernel(const __grid_cons
 // 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at ~200 registers without a cap below 8 blocks:
 // 9-10 warps per SM, a third warp on one or two schedulers).
 template <int CPL, int WPB>
-constexpr int ssim_min_blocks() { return CPL == 3 ? FB_SSIM_MINB3 / WPB : CPL != 4 ? 16 / WPB : (WPB == 4 ? FB_SSIM_MINB4 : WPB == 2 ? 4 : 8); }
+constexpr int ssim_min_blocks() { return CPL == 3 ? FB_SSIM_MINB3 / WPB : CPL != 4 ? 16 / WPB : (WPB == 4 ? FB_SSIM_MINB4 : WPB == 2 ? 4 : FB_SSIM_MINB1); }
 
+#ifdef FB_SSIM_MAXNREG   // experiment: an explicit register cap instead of the resident-blocks hint
+#define FB_SSIM_BOUNDS(CPL, WPB) __maxnreg__(FB_SSIM_MAXNREG)
+#else
+#define FB_SSIM_BOUNDS(CPL, WPB) __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>()))
+#endif
 template <int CPL, int MODE = 0, int WPB = 4>
-__global__ void __launch_bounds__(32 * WPB, (ssim_min_blocks<CPL, WPB>())) ssim_strip_kernel(const SsimParams p) {
+__global__ void FB_SSIM_BOUNDS(CPL, WPB) ssim_strip_kernel(const SsimParams p) {
     constexpr int WARPS = WPB;
     constexpr bool PIPE = MODE == 1;
     constexpr int NVB = (MODE == 2 || MODE == 3) ? 4 : 2;   // MODE 4 (two rows, single-buffered) needs 2
