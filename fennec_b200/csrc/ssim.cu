@@ -486,13 +486,27 @@ __device__ __forceinline__ double walk_strip_pipe(const StripCtx<4> &q) {
 // data (finite: real pixel rows) with its outputs masked.
 // ------------------------------------------------------------------------------------------------
 #ifndef FB_SSIM_PXMASK
-#define FB_SSIM_PXMASK 1   // 1: 200 registers (10 one-warp blocks per SM), 1.677 ms per 64 4K pairs; 0: one FSEL per pixel less but 204 registers (9 blocks), 1.736 ms
+#define FB_SSIM_PXMASK 1   // 1: mask every pixel's term (one FSEL); 0: mask columns at the end and skip rows by a uniform branch — one instruction per pixel less, yet 1.686 against 1.656 ms per 64 4K pairs (ptxas schedules the two differently)
 #endif
 struct HConsts {
-    float c, kTh;
-    float2 qpInit, one_two, neg2;
+    float2 cc;       // (c, c): the centring constant of the strip
+    float2 c1;       // (C1/2, C1)
+    float2 pqInit;   // (C2/2, C2): folded into the filter accumulators of the (p, q) planes
 };
+__device__ __forceinline__ HConsts make_hconsts(float c) {
+    HConsts k;
+    k.cc = make_float2(c, c);
+    k.c1 = make_float2(0.5f * kC1f, kC1f);
+    k.pqInit = make_float2(0.5f * kC2f, kC2f);
+    return k;
+}
 
+// Horizontal 8-tap pass over the V rows + the SSIM formula.  With A, B the filtered centred lumas (mu - c) and
+// P' = E[a'b'] + C2/2, Q' = E[a'^2 + b'^2] + C2 from the (p, q) planes:
+//   (2 mua mub + C1)/2 = (A+c)(B+c) + C1/2         mua^2 + mub^2 + C1 = (A+c)^2 + (B+c)^2 + C1     (no cancellation: plain means)
+//   (2 sab + C2)/2     = P' - A B                  saa + sbb + C2     = Q' - A^2 - B^2             (centred: E[x^2] - mu^2 stays small)
+// as FADD2, FFMA2, FFMA, FFMA2, FFMA, two FMULs, MUFU.RCP, one FMA into the lane's sum: 11 FMA-pipe lane-ops per pixel
+// (round 1: 14 — separate squares, m, nn, th and a fix-up inside __fdividef).
 template <int CPL>
 __device__ __forceinline__ void hpass_formula(const float4 (&own)[CPL], const float4 *vb, const float2 (&g2)[8],
                                               const HConsts &k, float (&fs)[CPL], const bool (&valid)[CPL], bool rowOK) {
@@ -505,26 +519,24 @@ __device__ __forceinline__ void hpass_formula(const float4 (&own)[CPL], const fl
 #pragma unroll
     for (int i = 0; i < CPL; i++) {
         float2 mab = __fmul2_rn(make_float2(it[i].x, it[i].y), g2[0]);
-        float2 mqp = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], k.qpInit);
+        float2 mpq = __ffma2_rn(make_float2(it[i].z, it[i].w), g2[0], k.pqInit);
 #pragma unroll
         for (int t = 1; t < 8; t++) {
             mab = __ffma2_rn(make_float2(it[i + t].x, it[i + t].y), g2[t], mab);
-            mqp = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mqp);
+            mpq = __ffma2_rn(make_float2(it[i + t].z, it[i + t].w), g2[t], mpq);
         }
-        const float2 sq = __fmul2_rn(mab, mab);
-        const float2 mn = make_float2(mab.x * mab.y, sq.x + sq.y);
-        const float th = fmaf(k.c, mab.x + mab.y, k.kTh);
-        const float2 AB1 = __ffma2_rn(make_float2(th, th), k.one_two, mn);
-        const float2 AB2 = __ffma2_rn(mn, k.neg2, make_float2(mqp.y, mqp.x));
-        const float2 nd = __fmul2_rn(AB1, AB2);
-        // fs += num * (1/den) as ONE FMA; columns without a valid output (the strip's last two lanes, lanes right of the
-        // image) accumulate finite values that the caller drops at the end, rows past the segment are skipped by the caller
+        const float2 abc = __fadd2_rn(mab, k.cc);                                            // (mua, mub)
+        const float2 n1 = __ffma2_rn(abc, make_float2(abc.y, abc.y), k.c1);                  // (mua mub + C1/2, mub^2 + C1)
+        const float den1 = fmaf(abc.x, abc.x, n1.y);
+        const float2 n2 = __ffma2_rn(make_float2(-mab.x, -mab.y), make_float2(mab.y, mab.y), mpq);   // (P' - AB, Q' - B^2)
+        const float den2 = fmaf(-mab.x, mab.x, n2.y);
+        const float num = n1.x * n2.x, den = den1 * den2;                                    // ssim / 4 = num / den
         float rden;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(nd.y));   // den in [C1*C2/4, ~1e10]: no range fix-up needed (__fdividef adds an FSETP and two predicated FMULs)
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(den));   // den in [C1*C2, ~1e10]: no range fix-up needed (__fdividef adds an FSETP and two predicated FMULs)
 #if FB_SSIM_PXMASK
-        fs[i] = fmaf((valid[i] && rowOK) ? nd.x : 0.f, rden, fs[i]);   // per-pixel mask (FSEL), as round 1
+        fs[i] = fmaf((valid[i] && rowOK) ? num : 0.f, rden, fs[i]);   // per-pixel mask (FSEL), as round 1
 #else
-        fs[i] = fmaf(nd.x, rden, fs[i]);
+        fs[i] = fmaf(num, rden, fs[i]);   // columns without a valid output accumulate finite values the caller drops at the end
 #endif
     }
 }
@@ -543,11 +555,7 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
 #pragma unroll
     for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
     HConsts hk;
-    hk.c = q.c;
-    hk.kTh = fmaf(q.c, q.c, 0.5f * kC1f);
-    hk.qpInit = make_float2(kC2f, 0.5f * kC2f);
-    hk.one_two = make_float2(1.f, 2.f);
-    hk.neg2 = make_float2(-1.f, -1.f);
+    hk = make_hconsts(q.c);
     float2 rab[8][CPL], rqp[8][CPL];
     constexpr uint32_t kRowBuf = 32 * CPL * 4;
     const uint32_t myRing = smem_u32(q.ring) + lane * (CPL * 4);
@@ -591,9 +599,8 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
         _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
             float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
             float2 t = __ffma2_rn(f, s2, K2);                                                   \
-            float2 sq = __fmul2_rn(t, t);                                                       \
             rab[S][i] = t;                                                                      \
-            rqp[S][i] = make_float2(sq.x + sq.y, t.x * t.y);                                    \
+            rqp[S][i] = make_float2(t.x * t.y, fmaf(t.x, t.x, t.y * t.y));   /* (p, q) */       \
         }                                                                                       \
         if ((R) + kStages < nIn) fetch_row((S) & (kStages - 1));                                \
         cp_async_commit();                                                                      \
@@ -643,7 +650,7 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
 #undef W2_VTAPS
     double dsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < CPL; i++) dsum += q.valid[i] ? (double)fs[i] : 0.0;
+    for (int i = 0; i < CPL; i++) dsum += (FB_SSIM_PXMASK || q.valid[i]) ? (double)fs[i] : 0.0;
     return dsum;
 }
 
@@ -663,11 +670,7 @@ __device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
 #pragma unroll
     for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
     HConsts hk;
-    hk.c = q.c;
-    hk.kTh = fmaf(q.c, q.c, 0.5f * kC1f);
-    hk.qpInit = make_float2(kC2f, 0.5f * kC2f);
-    hk.one_two = make_float2(1.f, 2.f);
-    hk.neg2 = make_float2(-1.f, -1.f);
+    hk = make_hconsts(q.c);
     float2 rab[8][CPL], rqp[8][CPL];
     constexpr uint32_t kRowBuf = 32 * CPL * 4;
     const uint32_t myRing = smem_u32(q.ring) + lane * 16;
@@ -690,9 +693,8 @@ __device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
         _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
             float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
             float2 t = __ffma2_rn(f, s2, K2);                                                   \
-            float2 sq = __fmul2_rn(t, t);                                                       \
             rab[(S) & 7][i] = t;                                                                \
-            rqp[(S) & 7][i] = make_float2(sq.x + sq.y, t.x * t.y);                              \
+            rqp[(S) & 7][i] = make_float2(t.x * t.y, fmaf(t.x, t.x, t.y * t.y));   /* (p, q) */ \
         }                                                                                       \
         if ((R) + kStages < nIn) {                                                              \
             cp_async<16>(myRing + (2 * ((S) & (kStages - 1))) * kRowBuf, pa);                   \
@@ -753,7 +755,7 @@ __device__ __forceinline__ double walk_stripN(const StripCtx<4> &q) {
 #undef WN_VTAPS_STS
     double dsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < CPL; i++) dsum += q.valid[i] ? (double)fs[i] : 0.0;
+    for (int i = 0; i < CPL; i++) dsum += (FB_SSIM_PXMASK || q.valid[i]) ? (double)fs[i] : 0.0;
     return dsum;
 }
 
@@ -807,11 +809,7 @@ __device__ __forceinline__ double walk_strip_tma(const StripCtx<4> &q, const Tma
 #pragma unroll
     for (int j = 0; j < 8; j++) g2[j] = make_float2(q.g[j], q.g[j]);
     HConsts hk;
-    hk.c = q.c;
-    hk.kTh = fmaf(q.c, q.c, 0.5f * kC1f);
-    hk.qpInit = make_float2(kC2f, 0.5f * kC2f);
-    hk.one_two = make_float2(1.f, 2.f);
-    hk.neg2 = make_float2(-1.f, -1.f);
+    hk = make_hconsts(q.c);
     float2 rab[8][CPL], rqp[8][CPL];
     // stage st <- rows [row0, row0 + kTmaRows) of both images (rows below the image arrive as zeros)
     auto issue = [&](int st, int row0) {
@@ -839,9 +837,8 @@ __device__ __forceinline__ double walk_strip_tma(const StripCtx<4> &q, const Tma
         _Pragma("unroll") for (int i = 0; i < CPL; i++) {                                       \
             float2 f = make_float2(luma_magic(xa_[i]), luma_magic(xb_[i]));                     \
             float2 tt = __ffma2_rn(f, s2, K2);                                                  \
-            float2 sq = __fmul2_rn(tt, tt);                                                     \
             rab[S][i] = tt;                                                                     \
-            rqp[S][i] = make_float2(sq.x + sq.y, tt.x * tt.y);                                  \
+            rqp[S][i] = make_float2(tt.x * tt.y, fmaf(tt.x, tt.x, tt.y * tt.y));   /* (p, q) */ \
         }                                                                                       \
         if (((S) & (kTmaRows - 1)) == kTmaRows - 1) {   /* last row of the stage: every lane has read it; refill it */ \
             __syncwarp();                                                                       \
@@ -897,7 +894,7 @@ __device__ __forceinline__ double walk_strip_tma(const StripCtx<4> &q, const Tma
 #undef WT_VTAPS
     double dsum = 0.0;
 #pragma unroll
-    for (int i = 0; i < CPL; i++) dsum += q.valid[i] ? (double)fs[i] : 0.0;
+    for (int i = 0; i < CPL; i++) dsum += (FB_SSIM_PXMASK || q.valid[i]) ? (double)fs[i] : 0.0;
     return dsum;
 }
 
