@@ -58,3 +58,74 @@ def test_adaptive_fast_path_bound_is_sound(kind, strength, oracle):
         wrong = (got != want).any(-1)
         assert not (wrong & ~amb).any(), "a pixel outside the error bound disagrees with the reference arithmetic"
         assert amb.mean() < 0.01
+
+
+# ---- round 2: the constant bounds of the Lanczos opaque-window shortcut and of the blur fast path ----------------------
+
+def _fma32_chain(x: np.ndarray, w32: np.ndarray) -> np.ndarray:
+    """acc = fmaf(x_k, w_k, acc) over the last axis in float32 (products of a byte and a float32 are exact in float64;
+    the float64 sum is rounded once to float32: the double rounding is far below the margins tested here)."""
+    acc = np.zeros(x.shape[:-1], f32)
+    for k in range(x.shape[-1]):
+        acc = (x[..., k].astype(np.float64) * np.float64(w32[k]) + acc.astype(np.float64)).astype(f32)
+    return acc
+
+
+def _windows(taps: int, w: np.ndarray, n: int, seed: int) -> np.ndarray:
+    """Random byte windows plus the adversaries: extreme overshoot both ways, all-255, alternating, single spikes."""
+    rng = np.random.default_rng(seed)
+    adv = [np.where(w > 0, 255, 0), np.where(w > 0, 0, 255), np.full(taps, 255), np.full(taps, 1), np.arange(taps) % 2 * 255]
+    adv += [np.eye(taps, dtype=np.int64)[k] * 255 for k in range(taps)]
+    return np.concatenate([rng.integers(0, 256, (n, taps)), np.stack(adv)]).astype(np.int64)
+
+
+def test_lanczos_opaque_shortcut_bound_is_sound(oracle):
+    """csrc/api.cu detect_int_ratio: E = 255 * 2^-24 * (sum|wn| + sum_k P_k) * 1.05 + 1e-6 must bound the distance between the
+    FP32 FMA chain over the normalised weights (csrc/resize.cu int_ratio_window, opaque branch) and the reference's
+    binary64 sequence r += R * (255 w); a += 255 w; v = r * (1 / a)  (resize.go:99-110) — for the ratio-4 Lanczos-3 row."""
+    start, index, weight = oracle.lanczos_weights(1920, 7680)
+    mid = 960
+    w = np.asarray(weight[start[mid]:start[mid + 1]], np.float64)
+    assert len(w) == 24
+    W = w.sum()
+    wn = (w / W).astype(f32)
+    P = np.cumsum(np.abs(wn.astype(np.float64)))
+    Eo = 255.0 * 2.0 ** -24 * (P[-1] + P.sum()) * 1.05 + 1e-6
+    assert 2.5e-4 < Eo < 3.5e-4                                   # what the kernel comment quotes (3.0e-4)
+    x = _windows(24, w, 200_000, 7)
+    r = np.zeros(len(x)); a = np.zeros(len(x))
+    for k in range(24):                                           # the reference's order and operations, alpha = 255
+        aw = 255.0 * w[k]
+        r = r + x[:, k].astype(np.float64) * aw
+        a = a + aw
+    ref = r * (1.0 / a)
+    got = _fma32_chain(x, wn).astype(np.float64)
+    assert np.abs(got - ref).max() <= Eo
+    assert np.abs(got - ref).max() > Eo / 50                      # ... and the bound is not vacuous
+    # outputs the shortcut does NOT flag round like the reference
+    amb = np.abs(got - np.rint(got)) >= 0.5 - Eo
+    clamp = lambda v: np.clip(np.floor(v + 0.5), 0, 255)         # noqa: E731  (clampF: half away from zero, v > -0.5 here or clamped)
+    assert (clamp(got)[~amb] == clamp(ref)[~amb]).all()
+    assert amb.mean() < 0.003
+
+
+@pytest.mark.parametrize("sigma", [0.8, 2.0, 2.66])
+def test_blur_fast_path_bound_is_sound(sigma, oracle):
+    """csrc/effects.cu launch_gaussian_blur: eps = 255 * 2^-24 * (sum|w32| + sum_k P_k) * 1.10 bounds the FP32 FMA chain against
+    the reference's binary64 multiply-then-add sequence (effects.go:172-188)."""
+    k64, radius = oracle.blur_kernel(sigma)
+    k64 = np.asarray(k64, np.float64)
+    w32 = k64.astype(f32)
+    P = np.cumsum(np.abs(w32.astype(np.float64)))
+    eps = 255.0 * 2.0 ** -24 * (P[-1] + P.sum()) * 1.10
+    taps = 2 * radius + 1
+    x = _windows(taps, k64 - k64.mean(), 200_000, int(sigma * 100))
+    ref = np.zeros(len(x))
+    for k in range(taps):
+        ref = ref + x[:, k].astype(np.float64) * k64[k]
+    got = _fma32_chain(x, w32).astype(np.float64)
+    assert np.abs(got - ref).max() <= eps
+    amb = np.abs(got - np.rint(got)) >= 0.5 - eps
+    clamp = lambda v: np.clip(np.floor(v + 0.5), 0, 255)         # noqa: E731
+    assert (clamp(got)[~amb] == clamp(ref)[~amb]).all()
+    assert amb.mean() < 0.002
