@@ -72,4 +72,15 @@ for (w, h) in [(97, 61), (4, 1), (130, 17)]:
     img = S.noise_image(w, h, w, alpha="random")
     gi, go = api.apply_palette(img, pal); oi, oo = O.apply_palette(img, pal)
     assert np.array_equal(gi, oi) and np.array_equal(go, oo)
+# round-2 kernels: lean interior tiles of Sharpen / AdaptiveSharpen (need whole warps inside the image), warp-autonomous
+# Lanczos H / V passes with the opaque shortcut and ragged widths, cp.async-staged blur V pass over several segments
+wide = S.noise_image(700, 300, 11, alpha="random")
+assert np.array_equal(api.Sharpen(wide, 0.5), O.sharpen(wide, 0.5))
+assert np.array_equal(api.AdaptiveSharpen(wide, 0.6), O.adaptive_sharpen(wide, 0.6))
+assert np.array_equal(api.GaussianBlur(wide, 2.0), O.gaussian_blur(wide, 2.0))
+for (w, h, al) in [(1000, 64, "opaque"), (4 * 131, 40, "opaque"), (1536, 72, "random")]:
+    src = S.noise_image(w, h, w + 2, alpha=al)
+    assert np.array_equal(api.lanczos_resize(src, w // 4, h // 4), O.lanczos_resize(src, w // 4, h // 4))
+a8 = S.gradient_noise_image(1920, 1080, 13); b8 = S.perturb(a8, 4, 7)
+assert abs(api.MSSSIM(a8, b8) - O.msssim(a8, b8)) <= 1e-5
 print("sanitize subset ok")
