@@ -623,6 +623,10 @@ __device__ __forceinline__ double walk_strip2(const StripCtx<CPL> &q) {
     for (int i = 0; i < CPL; i++) fs[i] = 0.f;
     constexpr int kVLanes = 36, kVBuf = CPL * kVLanes;
 
+    // [Software-pipelined lumas — readback, dp2a and centring of rows r+2, r+3 issued in the basic block of the horizontal pass
+    // of rows r, r+1 (slot-independent, so outside the switch), planes + vertical taps first thing in the next iteration —
+    // were measured at 1.733 against 1.651 ms per 64 4K pairs (218 registers); as with MODE 1 in round 1, ptxas' own
+    // interleaving of the serial version is better.  profiles/r2_tuning_sweep.txt]
 #pragma unroll 1
     for (int r = 7; r < nIn; r += 2) {
         float4 vA[CPL], vB[CPL];
