@@ -132,6 +132,13 @@ static void detect_int_ratio(const int *start, const int *index, const double *w
     while (hi < dstSize && same(hi)) hi++;
     if (hi - lo < 8) return;
     ir->ratio = R; ir->taps = T; ir->off = off; ir->dLo = lo; ir->dHi = hi;
+    // binary64 rows of the interior destinations: bit-identical for an integer ratio (the tap offsets from the centre are the
+    // same exact numbers for every d) — verified here, not assumed; then the exact path needs no CSR loads for them
+    ir->wdExact = 1;
+    for (int d = lo; d < hi && ir->wdExact; d++)
+        for (int k = 0; k < T; k++)
+            if (weight[start[d] + k] != weight[start[mid] + k]) { ir->wdExact = 0; break; }
+    for (int k = 0; k < 24; k++) ir->wd[k] = k < T ? weight[start[mid] + k] : 0.0;
     float ws = 0.f;
     for (int k = 0; k < T; k++) { ir->w[k] = (float)weight[start[mid] + k]; ws += ir->w[k]; }
     ir->wsum = ws;

@@ -176,6 +176,8 @@ struct IntRatioInfo {
     float wn[28];
     float Eo = 0.f;
     unsigned int opaqueA = 0;   // alpha byte << 24; 0 disables the shortcut
+    int wdExact = 0;            // the interior destinations' binary64 weight rows are bit-identical (wd[] below)
+    double wd[24];
 };
 int launch_resize_h(cudaStream_t s, const uint8_t *src, long long srcImgStride, int srcRowStride, int srcW,
                     int srcH, uint8_t *dst, long long dstImgStride, int dstRowStride, int dstW, int n,

@@ -239,6 +239,8 @@ struct IntRatioParams {
     float wn[28];   // w / sum(w): a fully opaque window is v = sum(R * wn), no premultiply and no division
     float Eo;       // |FP32 value - reference value| of that sum (detect_int_ratio, api.cu)
     uint32_t opaqueA;  // alpha byte << 24 such a window produces; 0: shortcut disabled
+    int wdExact;       // every interior destination has bit-identical binary64 weights: the exact path can use wd[] below
+    double wd[24];     // ... instead of the CSR index and weight rows (no dependent index -> pixel loads)
 };
 
 #ifndef FB_LZ_ROWS
@@ -257,6 +259,33 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // VIADDMNMX.RELU on the bit pattern subtracts the magic, clamps above and below.
 __device__ __forceinline__ uint32_t clamp255_from_magic(float t) {
     return (uint32_t)__viaddmin_s32_relu(__float_as_int(t), -0x4B400000, 255);
+}
+
+// finish_fp32 for the integer-ratio window kernels, same decisions with ~30 instead of 50 instructions: the reciprocal is the
+// MUFU approximation (1 ulp, covered by the 6.0e-7 = 2^-21 + 2^-23 term of the bound), the magic-number rounding runs as
+// packed FADD2 on the (R,G) and (B,A) pairs, the clamp is one VIADDMNMX.RELU per channel on the bit pattern and the pack
+// three PRMTs.  Values outside [0, 255] are flagged at the same rate as inside (harmless: the exact path clamps too).
+__device__ __forceinline__ uint32_t finish_fp32_lean(float2 rg, float2 ba, float Er, float Ea, bool &amb) {
+    const float a = ba.y;
+    amb = fabsf(a - 0.5f) <= Ea;  // the a > 0.5 gate itself (resize.go:107)
+    uint32_t out = 0u;
+    if (!amb && a > 0.5f) {
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(a));
+        const float2 vrg = __fmul2_rn(rg, make_float2(inv, inv));
+        const float2 vba = make_float2(ba.x * inv, a);
+        const float vmax = fmaxf(fmaxf(fabsf(vrg.x), fabsf(vrg.y)), fabsf(vba.x));
+        const float eps = fmaf(fmaf(vmax, Ea, Er), inv, vmax * 6.0e-7f);
+        const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+        const float2 neg1 = make_float2(-1.0f, -1.0f);
+        const float2 t1 = __fadd2_rn(vrg, magic), t2 = __fadd2_rn(vba, magic);
+        const float2 d1 = __ffma2_rn(__fadd2_rn(t1, nmagic), neg1, vrg), d2 = __ffma2_rn(__fadd2_rn(t2, nmagic), neg1, vba);
+        amb = !(eps < 0.25f) || fmaxf(fmaxf(fabsf(d1.x), fabsf(d1.y)), fabsf(d2.x)) >= 0.5f - eps || fabsf(d2.y) >= 0.5f - Ea;
+        const uint32_t x = __byte_perm(clamp255_from_magic(t1.x), clamp255_from_magic(t1.y), 0x0040);
+        const uint32_t z = __byte_perm(clamp255_from_magic(t2.x), clamp255_from_magic(t2.y), 0x0040);
+        out = __byte_perm(x, z, 0x5410);
+    }
+    return out;
 }
 
 // KO interior outputs from one window of packed pixels (compile-time tap indices); the window starts at raw[LEAD].
@@ -346,8 +375,7 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
             }
         }
 #pragma unroll
-        for (int j = 0; j < KO; j++)
-            outv[j] = finish_fp32(accRG[j].x, accRG[j].y, accBA[j].x, accBA[j].y, p.Er, p.Ea, ambv[j]);
+        for (int j = 0; j < KO; j++) outv[j] = finish_fp32_lean(accRG[j], accBA[j], p.Er, p.Ea, ambv[j]);
     }
 }
 
@@ -570,13 +598,50 @@ __device__ __forceinline__ void cp_async16_lz(void *smem_dst, const void *gsrc) 
 // Exact path for `take` queued outputs (one per lane).  Not inlined: one copy of the FP64 sequence in the kernel
 // instead of one per call site keeps the hot loop's code small (the first version stalled 0.64 cycles per issue on
 // instruction fetch, profiles/r2s2b_lanczos).
-template <bool VERTICAL>
-__device__ __noinline__ void lz_exact_queue(const ResizeParams &p, const uint8_t *s, uint8_t *dimg, const uint32_t *queue, int take) {
+// Interior destination of an integer ratio: taps R*d + off + k, k < T, with the shared binary64 weights q.wd[] — the same
+// operations in the same order as exact_px, without the CSR index / weight loads.
+template <bool VERTICAL, int R, int T>
+__device__ __forceinline__ void exact_px_interior(const IntRatioParams &q, const uint8_t *s, int x, int y, uint8_t *dpx) {
+    const ResizeParams &p = q.base;
+    const int s0 = R * (VERTICAL ? y : x) + q.off;
+    const uint8_t *base = VERTICAL ? s + (long long)s0 * p.srcRowStride + (long long)x * 4 : s + (long long)y * p.srcRowStride + (long long)s0 * 4;
+    const long long step = VERTICAL ? (long long)p.srcRowStride : 4;
+    double r2 = 0.0, g2 = 0.0, b2 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int tb = 0; tb < T; tb += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (tb + k < T) v[k] = __ldg(reinterpret_cast<const uint32_t *>(base + (tb + k) * step));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (tb + k < T) {
+                const double aw = __dmul_rn(byte_to_double(v[k] >> 24), q.wd[tb + k]);
+                r2 = __dadd_rn(r2, __dmul_rn(byte_to_double(v[k] & 0xFF), aw));
+                g2 = __dadd_rn(g2, __dmul_rn(byte_to_double((v[k] >> 8) & 0xFF), aw));
+                b2 = __dadd_rn(b2, __dmul_rn(byte_to_double((v[k] >> 16) & 0xFF), aw));
+                a2 = __dadd_rn(a2, aw);
+            }
+        }
+    }
+    finish_px(r2, g2, b2, a2, dpx);
+}
+
+// Exact path for `take` queued outputs (one per lane).  Not inlined: one copy of the FP64 sequence in the kernel
+// instead of one per call site keeps the hot loop's code small (the first version stalled 0.64 cycles per issue on
+// instruction fetch, profiles/r2s2b_lanczos).  Interior destinations (the ambiguous ones) take the table-free form,
+// edge destinations (clipped, renormalised taps) the CSR rows.
+template <bool VERTICAL, int R, int T>
+__device__ __noinline__ void lz_exact_queue(const IntRatioParams &q, const uint8_t *s, uint8_t *dimg, const uint32_t *queue, int take) {
+    const ResizeParams &p = q.base;
     const int lane = threadIdx.x & 31;
     if (lane < take) {
         const uint32_t code = queue[lane];
         const int ox = (int)(code & 0xFFFFu), oy = (int)(code >> 16);
-        exact_px<VERTICAL>(p, s, ox, oy, dimg + (long long)oy * p.dstRowStride + (long long)ox * 4);
+        const int d = VERTICAL ? oy : ox;
+        uint8_t *dpx = dimg + (long long)oy * p.dstRowStride + (long long)ox * 4;
+        if (q.wdExact && d >= q.dLo && d < q.dHi) exact_px_interior<VERTICAL, R, T>(q, s, ox, oy, dpx);
+        else exact_px<VERTICAL>(p, s, ox, oy, dpx);
     }
 }
 
@@ -688,11 +753,11 @@ __global__ void __launch_bounds__(32, MINB) resize_h_int_ratio_warp_kernel(const
         __syncwarp();   // stores, pushes and reads of stage[slot] are done before the drain / the next restage
         while (nq >= 32) {
             nq -= 32;
-            lz_exact_queue<false>(p, s, dimg, ambQ + nq, 32);
+            lz_exact_queue<false, R, T>(q, s, dimg, ambQ + nq, 32);
         }
         slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
-    if (nq > 0) lz_exact_queue<false>(p, s, dimg, ambQ, nq);
+    if (nq > 0) lz_exact_queue<false, R, T>(q, s, dimg, ambQ, nq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -774,10 +839,10 @@ __global__ void __launch_bounds__(32, 20) resize_v_int_ratio_warp_kernel(const _
         __syncwarp();
         while (nq >= 32) {
             nq -= 32;
-            lz_exact_queue<true>(p, s, dimg, ambQ + nq, 32);
+            lz_exact_queue<true, R, T>(q, s, dimg, ambQ + nq, 32);
         }
     }
-    if (nq > 0) lz_exact_queue<true>(p, s, dimg, ambQ, nq);
+    if (nq > 0) lz_exact_queue<true, R, T>(q, s, dimg, ambQ, nq);
 }
 
 template <bool VERTICAL>
@@ -809,6 +874,8 @@ int launch_pass(cudaStream_t s, const uint8_t *src, long long srcImgStride, int 
         q.base = p; q.off = ir->off; q.dLo = ir->dLo; q.dHi = ir->dHi; q.wsum = ir->wsum;
         for (int i = 0; i < 28; i++) { q.w[i] = i < ir->taps ? ir->w[i] : 0.f; q.wn[i] = i < ir->taps ? ir->wn[i] : 0.f; }
         q.Eo = ir->Eo;
+        q.wdExact = (ir->wdExact && getenv("FB_LZ_NO_WD") == nullptr) ? 1 : 0;
+        for (int i = 0; i < 24; i++) q.wd[i] = i < ir->taps ? ir->wd[i] : 0.0;
         q.opaqueA = getenv("FB_LZ_NO_OPAQUE") == nullptr ? ir->opaqueA : 0u;
         dim3 g2 = VERTICAL ? dim3((outW + 127) / 128, (outH + kOut - 1) / kOut, n)
                            : dim3(((outW + kOut - 1) / kOut + 127) / 128, (outH + kRowsPerBlock - 1) / kRowsPerBlock, n);
