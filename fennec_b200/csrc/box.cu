@@ -401,6 +401,12 @@ __device__ __forceinline__ uint32_t mean2x2_px(uint32_t a0, uint32_t a1, uint32_
     return (((rb + 0x00020002u) >> 2) & 0x00FF00FFu) | ((((ga + 0x00020002u) >> 2) & 0x00FF00FFu) << 8);
 }
 
+#ifndef FB_F2_SINGLE
+#define FB_F2_SINGLE 1
+#endif
+#ifndef FB_F2_SPF
+#define FB_F2_SPF 2   // single-step loop: L2 prefetch distance in steps
+#endif
 #ifndef FB_F2_PF
 #define FB_F2_PF 1
 #endif
@@ -458,6 +464,20 @@ __global__ void __launch_bounds__(kF2Threads, MINB) box_fused2_kernel(const BoxF
             // CTAs per SM: 1.16 ms per 16 8K pairs against 1.13) and a rolling two-step pipeline at the same register
             // count (ptxas spills at 80 registers: 1.44-1.60 ms; 1.23 at 2 CTAs).  The L2 prefetch below costs nothing.]
             int k = k0;
+#if FB_F2_SINGLE   // one step (four loads) per iteration with an L2 prefetch FB_F2_SPF steps ahead: 64 registers, so a 4th CTA fits the SM
+                   // (16 8K pairs: 0.960 ms against 1.064 ms with two steps in flight at 3 CTAs; prefetch 1 / 3 / 4 / 6 steps ahead:
+                   // 0.995 / 0.973 / 0.971 / 1.001; 3 or 5 CTAs: 1.021 / 1.217 — profiles/r2_tuning_sweep.txt)
+            for (; k < k1; k++, q += 4 * (long long)rs, o += (long long)p.l2RowStride) {
+                uint4 ta[4];
+                if (k + FB_F2_SPF + 1 <= k1) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (long long)(4 * FB_F2_SPF + r) * rs));
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) ta[r] = ld_nc_u128(q + (long long)r * rs);
+                step(ta, k, o);
+            }
+#endif
             for (; k + 2 <= k1; k += 2, q += 8 * (long long)rs, o += 2 * (long long)p.l2RowStride) {
                 uint4 ta[4], tb[4];
 #if FB_F2_PF > 0
@@ -735,7 +755,7 @@ int launch_box_fused2(cudaStream_t s, const uint8_t *srcA, long long srcImgStrid
         attrSet = true;
     }
     dim3 grid((srcW + p.chunkCols - 1) / p.chunkCols, (srcH + p.bandRows - 1) / p.bandRows, 2 * n);
-    static const int minb = [] { const char *e = getenv("FB_F2_MINB"); return (e && e[0] >= '2' && e[0] <= '5') ? e[0] - '0' : 3; }();
+    static const int minb = [] { const char *e = getenv("FB_F2_MINB"); return (e && e[0] >= '2' && e[0] <= '5') ? e[0] - '0' : (FB_F2_SINGLE ? 4 : 3); }();
     if (minb == 2) box_fused2_kernel<2><<<grid, kF2Threads, smem, s>>>(p);
     else if (minb == 4) box_fused2_kernel<4><<<grid, kF2Threads, smem, s>>>(p);
     else if (minb == 5) box_fused2_kernel<5><<<grid, kF2Threads, smem, s>>>(p);
