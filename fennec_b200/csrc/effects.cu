@@ -120,14 +120,14 @@ __device__ __forceinline__ uint32_t pack_rgba_low_bytes(float tr, float tg, floa
     return __byte_perm(x, z, 0x7610);
 }
 
-template <typename AlphaFn>
-__device__ __forceinline__ uint32_t blur_round_pack(const float2 (&accRG)[kTile], const float2 (&accB)[kTile / 2], float lim,
-                                                    uint32_t (&out)[kTile], AlphaFn alphaWord) {
+template <int TILE, typename AlphaFn>
+__device__ __forceinline__ uint32_t blur_round_pack(const float2 (&accRG)[TILE], const float2 (&accB)[TILE / 2], float lim,
+                                                    uint32_t (&out)[TILE], AlphaFn alphaWord) {
     const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
     const float2 neg1 = make_float2(-1.0f, -1.0f);
     uint32_t ambMask = 0;
 #pragma unroll
-    for (int m = 0; m < kTile / 2; m++) {
+    for (int m = 0; m < TILE / 2; m++) {
         float2 t[3], d[3];   // (R,G) of output 2m, (R,G) of output 2m+1, (B, B) of both
         const float2 v[3] = {accRG[2 * m], accRG[2 * m + 1], accB[m]};
 #pragma unroll
@@ -218,24 +218,24 @@ __device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *
 #ifndef FB_BLUR_BA
 #define FB_BLUR_BA 0   // 1: B rides an FFMA2 together with the (discarded) alpha lane instead of a scalar FFMA
 #endif
-template <int R, int NIN, int OFF>
+template <int R, int NIN, int OFF, int TILE>
 __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const float (&w32)[17],
-                                               float2 (&accRG)[kTile], float2 (&accB)[kTile / 2]) {
+                                               float2 (&accRG)[TILE], float2 (&accB)[TILE / 2]) {
     float wt[2 * R + 1];
 #pragma unroll
     for (int k = 0; k <= 2 * R; k++) wt[k] = w32[k];   // kernel parameters: uniform / constant-bank operands
 #pragma unroll
-    for (int j = 0; j < kTile; j++) accRG[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < TILE; j++) accRG[j] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int m = 0; m < kTile / 2; m++) accB[m] = make_float2(0.f, 0.f);
+    for (int m = 0; m < TILE / 2; m++) accB[m] = make_float2(0.f, 0.f);
     const float2 nmagic = make_float2(-8388608.0f, -8388608.0f);
 #if FB_BLUR_BA
-    float2 accBA[kTile];
+    float2 accBA[TILE];
 #pragma unroll
-    for (int j = 0; j < kTile; j++) accBA[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < TILE; j++) accBA[j] = make_float2(0.f, 0.f);
 #endif
 #pragma unroll
-    for (int i = OFF - R; i < OFF + kTile + R; i++) {
+    for (int i = OFF - R; i < OFF + TILE + R; i++) {
         // [byte k, 0, 0, 0x4B] = bits of 2^23 + byte; one FADD2 converts R and G, one FADD converts B
         const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
                                                  __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), nmagic);
@@ -246,7 +246,7 @@ __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const
         const float bl = byte_to_float(raw[i], 2);
 #endif
 #pragma unroll
-        for (int j = 0; j < kTile; j++) {
+        for (int j = 0; j < TILE; j++) {
             const int k = i - OFF - j + R;  // tap of input i for output j
             if (k >= 0 && k <= 2 * R) {
                 accRG[j] = __ffma2_rn(rg, make_float2(wt[k], wt[k]), accRG[j]);
@@ -261,7 +261,7 @@ __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const
     }
 #if FB_BLUR_BA
 #pragma unroll
-    for (int m = 0; m < kTile / 2; m++) accB[m] = make_float2(accBA[2 * m].x, accBA[2 * m + 1].x);
+    for (int m = 0; m < TILE / 2; m++) accB[m] = make_float2(accBA[2 * m].x, accBA[2 * m + 1].x);
 #endif
 }
 
@@ -361,9 +361,9 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_h_fast_kernel(const B
                 raw[v * 4 + 0] = q.x; raw[v * 4 + 1] = q.y; raw[v * 4 + 2] = q.z; raw[v * 4 + 3] = q.w;
             }
             float2 accRG[kTile], accB[kTile / 2];
-            blur_taps_fp32<R, 32, 8>(raw, p.w32, accRG, accB);
+            blur_taps_fp32<R, 32, 8, kTile>(raw, p.w32, accRG, accB);
             uint32_t out[kTile];
-            uint32_t ambMask = blur_round_pack(accRG, accB, lim, out, [&](int j) { return raw[8 + j]; });  // alpha from the source (effects.go:189)
+            uint32_t ambMask = blur_round_pack<kTile>(accRG, accB, lim, out, [&](int j) { return raw[8 + j]; });  // alpha from the source (effects.go:189)
             uint8_t *drow = p.dst + (long long)img * p.dstImgStride + (long long)y * p.dstRowStride + (long long)x0 * 4;
             if (dvec && x0 + kTile <= p.w) {
 #pragma unroll
@@ -407,12 +407,19 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
 // profiles/r2s2_blur).  cp.async has no destination registers; its completion is an explicit wait_group at the end of
 // the chunk.  Whole-warp-inside-the-row segments copy 16 bytes per lane (8 lanes per row, 4 rows per instruction);
 // otherwise every lane copies its own (clamped) column 4 bytes at a time.
+#ifndef FB_BLUR_VTILE
+#define FB_BLUR_VTILE 16
+#endif
+#ifndef FB_BLUR_VMINB
+#define FB_BLUR_VMINB 16
+#endif
+constexpr int kTileV = FB_BLUR_VTILE;   // outputs per thread and chunk in the vertical pass
 template <int R, int WPB>
-__global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const BlurParams p) {
-    constexpr int NIN = kTile + 2 * R;
+__global__ void __launch_bounds__(32 * WPB, FB_BLUR_VMINB / WPB) blur_v_fast_kernel(const BlurParams p) {
+    constexpr int NIN = kTileV + 2 * R;
     __shared__ uint32_t ambQ[WPB][kAmbQ];
     __shared__ int ambN[WPB];
-    __shared__ __align__(16) uint32_t nxtBuf[WPB][2][kTile][32];
+    __shared__ __align__(16) uint32_t nxtBuf[WPB][2][kTileV][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) ambN[warp] = 0;
     __syncwarp();
@@ -432,18 +439,18 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const B
         const int sy = min(max(y, 0), p.h - 1);  // clamp to edge (effects.go:199-204)
         return __ldg(reinterpret_cast<const uint32_t *>(scol + (long long)sy * p.srcRowStride));
     };
-    // rows yn .. yn + kTile - 1 (clamped to the last row) of this warp's 32 columns into buf[kTile][32]
+    // rows yn .. yn + kTileV - 1 (clamped to the last row) of this warp's 32 columns into buf[kTileV][32]
     auto stage_rows = [&](int yn, uint32_t (*buf)[32]) {
         if (wide) {
             const uint8_t *g0 = simg + (long long)xw * 4 + (lane & 7) * 16;
 #pragma unroll
-            for (int k = 0; k < kTile / 4; k++) {
+            for (int k = 0; k < kTileV / 4; k++) {
                 const int r = (lane >> 3) + 4 * k;
                 cp_async16(&buf[r][(lane & 7) * 4], g0 + (long long)min(yn + r, p.h - 1) * p.srcRowStride);
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < kTile; r++) cp_async4(&buf[r][lane], scol + (long long)min(yn + r, p.h - 1) * p.srcRowStride);
+            for (int r = 0; r < kTileV; r++) cp_async4(&buf[r][lane], scol + (long long)min(yn + r, p.h - 1) * p.srcRowStride);
         }
         cp_async_commit_group();
     };
@@ -452,23 +459,23 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const B
     for (int i = 0; i < NIN; i++) raw[i] = ld_row(ys - R + i);
     int par = 0;
 #pragma unroll 1
-    for (int y0 = ys; y0 < yEnd; y0 += kTile, par ^= 1) {
-        const bool more = y0 + kTile < yEnd;
-        if (more) stage_rows(y0 + kTile + R, nxtBuf[warp][par]);   // first new row of the next chunk
-        float2 accRG[kTile], accB[kTile / 2];
-        blur_taps_fp32<R, NIN, R>(raw, p.w32, accRG, accB);
-        uint32_t out[kTile];
-        uint32_t ambMask = blur_round_pack(accRG, accB, lim, out, [&](int j) { return raw[R + j]; });  // alpha rides in tmp (effects.go:189,215)
+    for (int y0 = ys; y0 < yEnd; y0 += kTileV, par ^= 1) {
+        const bool more = y0 + kTileV < yEnd;
+        if (more) stage_rows(y0 + kTileV + R, nxtBuf[warp][par]);   // first new row of the next chunk
+        float2 accRG[kTileV], accB[kTileV / 2];
+        blur_taps_fp32<R, NIN, R, kTileV>(raw, p.w32, accRG, accB);
+        uint32_t out[kTileV];
+        uint32_t ambMask = blur_round_pack<kTileV>(accRG, accB, lim, out, [&](int j) { return raw[R + j]; });  // alpha rides in tmp (effects.go:189,215)
         {
             uint8_t *dp = dcol + (long long)y0 * p.dstRowStride;
             if (!active) {
                 ambMask = 0;
-            } else if (y0 + kTile <= yEnd) {
+            } else if (y0 + kTileV <= yEnd) {
 #pragma unroll
-                for (int j = 0; j < kTile; j++, dp += p.dstRowStride) *reinterpret_cast<uint32_t *>(dp) = out[j];
+                for (int j = 0; j < kTileV; j++, dp += p.dstRowStride) *reinterpret_cast<uint32_t *>(dp) = out[j];
             } else {
 #pragma unroll
-                for (int j = 0; j < kTile; j++, dp += p.dstRowStride)
+                for (int j = 0; j < kTileV; j++, dp += p.dstRowStride)
                     if (y0 + j < yEnd) *reinterpret_cast<uint32_t *>(dp) = out[j];
                 ambMask &= (1u << (yEnd - y0)) - 1u;
             }
@@ -479,9 +486,9 @@ __global__ void __launch_bounds__(32 * WPB, 16 / WPB) blur_v_fast_kernel(const B
         amb_drain<true>(false, lane, ambQ[warp], &ambN[warp], simg, p.srcRowStride, dimg, p.dstRowStride, p.w, p.h, R, p.kernel);
         if (more) {
 #pragma unroll
-            for (int i = 0; i < 2 * R; i++) raw[i] = raw[i + kTile];
+            for (int i = 0; i < 2 * R; i++) raw[i] = raw[i + kTileV];
 #pragma unroll
-            for (int i = 0; i < kTile; i++) raw[2 * R + i] = nxtBuf[warp][par][i][lane];
+            for (int i = 0; i < kTileV; i++) raw[2 * R + i] = nxtBuf[warp][par][i][lane];
         }
     }
     __syncwarp();
