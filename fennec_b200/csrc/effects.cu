@@ -971,6 +971,10 @@ __device__ __forceinline__ uint32_t adaptive_exact_at(const uint8_t *img, int rs
 // loads with an L2 prefetch of the later rows, PRMT splits, no border tests, the horizontal 1-2-1 luma sums shared by the
 // Sobel rows above and below.  Same FP32 evaluation, same bound and the same per-warp exact queue as the general body
 // below; returns through the caller's queue drain.
+#ifndef FB_AD_UNROLL
+#define FB_AD_UNROLL 1   // rows of the lean AdaptiveSharpen loop unrolled (the three-row window is renamed instead of moved)
+#endif
+constexpr int kAdUnroll = FB_AD_UNROLL;
 __device__ __forceinline__ uint32_t adaptive_row_fast(const uint32_t (&hP_rb)[4], const uint32_t (&hP_ga)[4], const uint32_t (&hC_rb)[4],
                                                       const uint32_t (&hC_ga)[4], const uint32_t (&hN_rb)[4], const uint32_t (&hN_ga)[4],
                                                       const int (&hlP)[4], const int (&hlN)[4], const int (&colsum)[6],
@@ -1086,7 +1090,7 @@ __global__ void __launch_bounds__(128) adaptive_tile_kernel(const FxTileParams p
         load_row_fast(row, hP_rb, hP_ga, lP, hlP, rawP);
         load_row_fast(row + p.srcRowStride, hC_rb, hC_ga, lC, hlC, rawC);
         row += 2 * (long long)p.srcRowStride;
-#pragma unroll 1
+#pragma unroll (kAdUnroll)
         for (int r = 0; r < kFxRows; r++, row += p.srcRowStride, drow += p.dstRowStride) {
             load_row_fast(row, hN_rb, hN_ga, lN, hlN, rawN);
             int colsum[6];
