@@ -497,3 +497,20 @@ def test_blur_vertical_staging_bit_exact(w, h, lib, oracle):
     src = S.noise_image(w, h, w * h, alpha="random")
     assert np.array_equal(api.GaussianBlur(src, 2.0), oracle.gaussian_blur(src, 2.0))
     assert np.array_equal(api.GaussianBlur(src, 1.0), oracle.gaussian_blur(src, 1.0))
+
+
+def test_round2_kernels_random_shapes_bit_exact(lib, oracle):
+    # seeded random geometry for the warp-autonomous Lanczos passes (ratio 4: ragged last warps, row counts that do not
+    # fill a warp's 16 rows / 12 steps, every alpha kind) and for the lean Sharpen / AdaptiveSharpen / blur tiles
+    rng = np.random.default_rng(20261017)
+    for k in range(10):
+        dw, dh = int(rng.integers(9, 420)), int(rng.integers(3, 90))
+        alpha = ("opaque", "random", "ramp")[k % 3]
+        src = S.noise_image(4 * dw, 4 * dh, 1000 + k, alpha=alpha)
+        assert np.array_equal(api.lanczos_resize(src, dw, dh), oracle.lanczos_resize(src, dw, dh)), (dw, dh, alpha)
+    for k in range(6):
+        w, h = int(rng.integers(140, 900)), int(rng.integers(12, 200))
+        src = S.noise_image(w, h, 2000 + k, alpha="random")
+        assert np.array_equal(api.Sharpen(src, 0.5), oracle.sharpen(src, 0.5)), (w, h)
+        assert np.array_equal(api.AdaptiveSharpen(src, 0.5), oracle.adaptive_sharpen(src, 0.5)), (w, h)
+        assert np.array_equal(api.GaussianBlur(src, 2.0), oracle.gaussian_blur(src, 2.0)), (w, h)
