@@ -976,8 +976,9 @@ __global__ void __launch_bounds__(32, 8) ssim_strip_tma_kernel(const __grid_cons
 
 // MODE 0: walk_strip, 1: walk_strip_pipe, 2: walk_strip2, 3: walk_stripN<4>, 4: walk_stripN<2> (5: ssim_strip_tma_kernel).  WPB = warps (independent strips) per block: warps never
 // synchronise with each other, so the block size only sets the granularity at which the SM's registers are handed out:
-// 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at ~200 registers without a cap below 8 blocks:
-// 9-10 warps per SM, a third warp on one or two schedulers).
+// 2 blocks of 4 warps at <= 255 registers, or one-warp blocks (ptxas settles at 200-208 registers with the 8-block hint; the
+// register file is per scheduler, 16 K registers each, so anything from 171 to 255 registers means two warps per scheduler =
+// 8 per SM — asking for 9 or 10 blocks makes ptxas cap at 168 registers, with spills).
 template <int CPL, int WPB>
 constexpr int ssim_min_blocks() { return CPL == 3 ? FB_SSIM_MINB3 / WPB : CPL != 4 ? 16 / WPB : (WPB == 4 ? FB_SSIM_MINB4 : WPB == 2 ? 4 : FB_SSIM_MINB1); }
 
