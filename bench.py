@@ -231,6 +231,10 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 4:
+        # config 4 gathered on rank 0: above four ranks the NVLink ingest of the gathering GPU binds the vertical pass, so the
+        # library pipelines sub-batches (V with its peer stores on a side stream under the next H) — csrc/api.cu resize_on_device
+        os.environ.setdefault("FB_LZ_PIPE", "peer")
     torch.cuda.set_device(local)
     build.build()
     api.set_device(local)

@@ -229,6 +229,9 @@ static void destroy_ctx(DevCtx *c) {   // the device of *c is current
     if (c->ev) cudaEventDestroy(c->ev);
     if (c->useEv) cudaEventDestroy(c->useEv);
     for (int i = 0; i < 2; i++) if (c->stageEv[i]) cudaEventDestroy(c->stageEv[i]);
+    for (int i = 0; i < 4; i++) if (c->pipeEv[i]) cudaEventDestroy(c->pipeEv[i]);
+    if (c->joinEv) cudaEventDestroy(c->joinEv);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1227,6 +1230,13 @@ static int check_weights(const char *fn, const fb_weights *w, int dstSize, int s
     return FB_OK;
 }
 
+// Is `p` memory of another device than `dev` (a peer-mapped destination: batch.PeerGather, a symmetric-memory view)?
+static bool on_other_device(const void *p, int dev) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice && at.device != dev;
+}
+
 static int resize_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, long long srcImgStride, int srcRowStride,
                             int srcW, int srcH, uint8_t *ddst, long long dstImgStride, int dstRowStride, int dstW,
                             int dstH, int n, const LanczosTable &tx, const LanczosTable &ty) {
@@ -1234,6 +1244,44 @@ static int resize_on_device(DevCtx *c, cudaStream_t s, const uint8_t *dsrc, long
     long long timg = (long long)tpitch * srcH;
     uint8_t *tmp = (uint8_t *)c->ws.take((size_t)timg * n);
     if (!tmp) { set_error("internal: workspace under-reserved (resize tmp)"); return FB_E_INVALID; }
+    // Peer destination (the gather fused into the vertical pass's stores, batch.PeerGather): with many ranks storing into ONE GPU
+    // the V pass is bound by the NVLink ingest of that GPU, not by this one — 8 ranks: 465 MB at ~900 GB/s = 0.52 ms behind
+    // 0.57 ms of compute.  The batch then runs as up to four sub-batches, V of sub-batch k on a high-priority side stream while
+    // H of sub-batch k+1 (compute-bound, local) runs on the caller's stream; the side stream is joined before returning.
+    // Measured (8 images per rank, opaque 8K -> 1080p): 8 GPUs 1.146 -> 0.927 ms, 4 GPUs 0.758 -> 0.773 (the ingest is not
+    // the bound yet), local destinations 0.569 -> 0.68-0.72 (four small launches, tails) — so it is opt-in:
+    // FB_LZ_PIPE=peer pipelines batches whose destination lives on another device (bench.py sets it above four ranks),
+    // FB_LZ_PIPE=1 every batch (tests), unset / 0: never.
+    static const int pipeEnv = [] { const char *e = getenv("FB_LZ_PIPE"); return !e ? 0 : (e[0] == '1' ? 1 : (e[0] == 'p' ? 2 : 0)); }();
+    const bool pipelined = n >= 2 && (pipeEnv == 1 || (pipeEnv == 2 && on_other_device(ddst, c->dev)));
+    if (pipelined) {
+        if (!c->side) {
+            // highest priority: V blocks (few, stalled on remote stores) must be dispatched ahead of the next sub-batch's H blocks,
+            // which would otherwise fill every SM first and serialise the two
+            int prLo = 0, prHi = 0;
+            cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+            bool ok = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prHi) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&c->joinEv, cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; ok && i < 4; i++) ok = cudaEventCreateWithFlags(&c->pipeEv[i], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); set_error("resize: cannot create the side stream"); return FB_E_CUDA; }
+        }
+        const int chunks = n < 4 ? n : 4, per = (n + chunks - 1) / chunks;
+        FB_CUDA(cudaEventRecord(c->joinEv, s));               // the side stream starts behind whatever precedes this call on s
+        FB_CUDA(cudaStreamWaitEvent(c->side, c->joinEv, 0));
+        for (int k = 0, i0 = 0; i0 < n; k++, i0 += per) {
+            const int m = n - i0 < per ? n - i0 : per;
+            FB_TRY(launch_resize_h(s, dsrc + (size_t)i0 * srcImgStride, srcImgStride, srcRowStride, srcW, srcH, tmp + (size_t)i0 * timg, timg,
+                                   tpitch, dstW, m, tx.start, tx.index, tx.weight, tx.weight32, tx.maxTaps, tx.wabs, tx.first, tx.wpadT,
+                                   tx.groups, &tx.ir));
+            FB_CUDA(cudaEventRecord(c->pipeEv[k & 3], s));
+            FB_CUDA(cudaStreamWaitEvent(c->side, c->pipeEv[k & 3], 0));
+            FB_TRY(launch_resize_v(c->side, tmp + (size_t)i0 * timg, timg, tpitch, dstW, srcH, ddst + (size_t)i0 * dstImgStride, dstImgStride,
+                                   dstRowStride, dstH, m, ty.start, ty.index, ty.weight, ty.weight32, ty.maxTaps, ty.wabs, &ty.ir));
+        }
+        FB_CUDA(cudaEventRecord(c->joinEv, c->side));
+        FB_CUDA(cudaStreamWaitEvent(s, c->joinEv, 0));
+        return FB_OK;
+    }
     FB_TRY(launch_resize_h(s, dsrc, srcImgStride, srcRowStride, srcW, srcH, tmp, timg, tpitch, dstW, n, tx.start,
                            tx.index, tx.weight, tx.weight32, tx.maxTaps, tx.wabs, tx.first, tx.wpadT, tx.groups, &tx.ir));
     return launch_resize_v(s, tmp, timg, tpitch, dstW, srcH, ddst, dstImgStride, dstRowStride, dstH, n, ty.start,

@@ -64,6 +64,11 @@ struct DevCtx {
     cudaEvent_t stageEv[2] = {nullptr, nullptr};
     bool stageBusy[2] = {false, false};
     unsigned stageNext = 0;
+    // Side stream of the pipelined Lanczos batch (api.cu: resize_on_device): the vertical pass of one sub-batch runs on it
+    // while the horizontal pass of the next runs on the caller's stream; created on first use.
+    cudaStream_t side = nullptr;
+    cudaEvent_t pipeEv[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t joinEv = nullptr;
 };
 
 int ensure_init();

@@ -59,3 +59,23 @@ def test_cpp_host_mirror(lib):
         subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_lanczos_pipelined_sub_batches_match(lib):
+    """FB_LZ_PIPE=1: the batch runs as sub-batches with the vertical pass on a side stream (csrc/api.cu resize_on_device, the
+    path peer-gathered destinations take above four ranks) — same bytes as the per-image host entry point."""
+    code = (
+        "import numpy as np, torch\n"
+        "from fennec_b200 import api, batch, synth as S\n"
+        "for n, (w, h), (dw, dh) in [(5, (512, 128), (128, 32)), (2, (300, 90), (75, 40)), (9, (256, 64), (64, 16))]:\n"
+        "    imgs = [S.noise_image(w, h, 7 * n + i, alpha=('opaque', 'random')[i % 2]) for i in range(n)]\n"
+        "    d = torch.from_numpy(np.stack(imgs)).cuda()\n"
+        "    for rep in range(3):\n"
+        "        got = batch.lanczos_resize_batch(d, dw, dh).cpu().numpy()\n"
+        "        assert all(np.array_equal(got[i], api.lanczos_resize(imgs[i], dw, dh)) for i in range(n)), (n, rep)\n"
+        "print('pipelined ok')\n")
+    e = dict(os.environ)
+    e["FB_LZ_PIPE"] = "1"
+    e["PYTHONPATH"] = ROOT + os.pathsep + e.get("PYTHONPATH", "")
+    r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "pipelined ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
