@@ -666,11 +666,17 @@ struct FxTileParams {
 #ifndef FB_FX_PF
 #define FB_FX_PF 2
 #endif
+#ifndef FB_FX_IMAD
+#define FB_FX_IMAD 1
+#endif
 template <int K>
 __device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const uint8_t *s, uint8_t *d, int x0, int yb) {
     const uint32_t cst = (uint32_t)((1024 << K) + p.half) * 0x00010001u;
     const uint32_t msk = (uint32_t)(0xFFFF >> K) * 0x00010001u;
     const uint32_t mulO = (uint32_t)(p.A + (1 << K)), mulB = (uint32_t)p.A;
+    const uint32_t two = (uint32_t)p.fastTiles + 1u;   // == 2 on this path, from the parameter bank
+    const uint32_t sh4 = two << 27;   // 2^28: __umulhi(x, 2^28) == x >> 4 on the FMA pipe
+    (void)two; (void)sh4;
     const uint8_t *row = s + (long long)(yb - 1) * p.srcRowStride + (long long)x0 * 4;
     uint8_t *drow = d + (long long)yb * p.dstRowStride + (long long)x0 * 4;
     // horizontal 1-2-1 sums of a row on packed 16-bit lanes (R|B and G|A words) + the row's own pixels split the same way
@@ -682,8 +688,13 @@ __device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const u
         for (int i = 0; i < 6; i++) { rb[i] = px[i] & 0x00FF00FFu; ga[i] = __byte_perm(px[i], 0u, 0x4341u); }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
+#if FB_FX_IMAD   // x + 2y as an IMAD with the 2 from the parameter bank (ptxas cannot turn it back into an ALU-pipe LEA)
+            hrb[i] = rb[i + 1] * two + rb[i] + rb[i + 2];
+            hga[i] = ga[i + 1] * two + ga[i] + ga[i + 2];
+#else
             hrb[i] = rb[i] + 2 * rb[i + 1] + rb[i + 2];
             hga[i] = ga[i] + 2 * ga[i + 1] + ga[i + 2];
+#endif
             orb[i] = rb[i + 1]; oga[i] = ga[i + 1]; raw[i] = px[i + 1];
         }
     };
@@ -704,8 +715,16 @@ __device__ __forceinline__ void sharpen_tile_fast(const FxTileParams &p, const u
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             // gaussianBlur3x3 (effects.go:124-136): (sum + 8) >> 4 on each 16-bit lane
+#if FB_FX_IMAD >= 2   // ... and the >> 4 as IMAD.HI by 2^28
+            const uint32_t brb = __umulhi(hC_rb[i] * two + hP_rb[i] + hN_rb[i] + 0x00080008u, sh4) & 0x00FF00FFu;
+            const uint32_t bga = __umulhi(hC_ga[i] * two + hP_ga[i] + hN_ga[i] + 0x00080008u, sh4) & 0x00FF00FFu;
+#elif FB_FX_IMAD
+            const uint32_t brb = ((hC_rb[i] * two + hP_rb[i] + hN_rb[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+            const uint32_t bga = ((hC_ga[i] * two + hP_ga[i] + hN_ga[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+#else
             const uint32_t brb = ((hP_rb[i] + 2 * hC_rb[i] + hN_rb[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
             const uint32_t bga = ((hP_ga[i] + 2 * hC_ga[i] + hN_ga[i] + 0x00080008u) >> 4) & 0x00FF00FFu;
+#endif
             // integer unsharp, see fx_tile_kernel: T = orig*(A + 2^k) - blur*A + half + bias; out = relu(min((T >> k) - 1024, 255))
             const uint32_t trb = ((oC_rb[i] * mulO + cst - brb * mulB) >> K) & msk;
             const uint32_t tga = ((oC_ga[i] * mulO + cst - bga * mulB) >> K) & msk;
