@@ -215,6 +215,9 @@ __device__ __forceinline__ void amb_drain(bool all, int lane, uint32_t *q, int *
 // sits in the two halves of accB[m] and takes scalar FFMAs.  [The first version paired two OUTPUTS of one channel
 // per FFMA2, which needs the weight pairs (w[k], w[k-1]) as aligned register pairs: ptxas rebuilt them with one
 // IMAD.MOV per FFMA2 — 28 % of the executed instructions, on the same pipe as the FMAs (profiles/r1d_ncu_summaries_blur_lanczos.txt).]
+#ifndef FB_BLUR_I2F
+#define FB_BLUR_I2F 2   // 2: every channel through I2F.U8 (XU pipe, otherwise idle): 0.636 ms per 16 4K images against 0.658 with PRMT + FADD; 1: B only, 0.649
+#endif
 #ifndef FB_BLUR_BA
 #define FB_BLUR_BA 0   // 1: B rides an FFMA2 together with the (discarded) alpha lane instead of a scalar FFMA
 #endif
@@ -237,11 +240,17 @@ __device__ __forceinline__ void blur_taps_fp32(const uint32_t (&raw)[NIN], const
 #pragma unroll
     for (int i = OFF - R; i < OFF + TILE + R; i++) {
         // [byte k, 0, 0, 0x4B] = bits of 2^23 + byte; one FADD2 converts R and G, one FADD converts B
+#if FB_BLUR_I2F >= 2   // experiment: every channel through I2F.U8 on the XU pipe (16 lanes/clk/SM) instead of PRMT + FADD
+        const float2 rg = make_float2((float)(raw[i] & 0xFFu), (float)((raw[i] >> 8) & 0xFFu));
+#else
         const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7540u)),
                                                  __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7541u))), nmagic);
+#endif
 #if FB_BLUR_BA
         const float2 ba = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7542u)),
                                                  __uint_as_float(__byte_perm(raw[i], 0x4B000000u, 0x7543u))), nmagic);
+#elif FB_BLUR_I2F >= 1   // experiment: B through I2F.U8 (XU pipe), leaving the FMA pipe one FADD per input less
+        const float bl = (float)((raw[i] >> 16) & 0xFFu);
 #else
         const float bl = byte_to_float(raw[i], 2);
 #endif

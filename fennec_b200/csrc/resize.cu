@@ -288,6 +288,10 @@ __device__ __forceinline__ uint32_t finish_fp32_lean(float2 rg, float2 ba, float
     return out;
 }
 
+#ifndef FB_LZ_I2F
+#define FB_LZ_I2F 1   // 1: the B (and alpha) bytes become floats through I2F.U8 on the otherwise idle XU pipe (16 lanes/clk/SM) instead of
+                     // PRMT + FADD: 0.550 against 0.568 ms per 8 opaque 8K images; 2: R and G too — the XU pipe saturates, 0.651 ms
+#endif
 // KO interior outputs from one window of packed pixels (compile-time tap indices); the window starts at raw[LEAD].
 template <int R, int T, int LEAD, int NRAW, int KO = kOut>
 __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], const IntRatioParams &q,
@@ -318,9 +322,17 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
             const uint32_t px = raw[LEAD + i];
+#if FB_LZ_I2F >= 2
+            const float2 rg = make_float2((float)(px & 0xFFu), (float)((px >> 8) & 0xFFu));
+#else
             const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u)),
                                                      __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7541u))), kMagic2);
+#endif
+#if FB_LZ_I2F
+            const float bl = (float)((px >> 16) & 0xFFu);   // I2F.U8 on the XU pipe instead of PRMT + FADD
+#else
             const float bl = byte_f(px, 2);
+#endif
 #pragma unroll
             for (int j = 0; j < KO; j++) {
                 const int t = i - j * R;  // tap of input i for output j
@@ -359,11 +371,11 @@ __device__ __forceinline__ void int_ratio_window(const uint32_t (&raw)[NRAW], co
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
             const uint32_t px = raw[LEAD + i];
-            const float fa = byte_f(px, 3);
+            const float fa = byte_f(px, 3), fb = byte_f(px, 2);   // (I2F for these two was measured slower here: 0.819 against 0.803 ms)
             const float2 rg = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7540u)),
                                                      __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7541u))), kMagic2);
             const float2 prg = __fmul2_rn(rg, make_float2(fa, fa));
-            const float2 pba = make_float2(byte_f(px, 2) * fa, fa);
+            const float2 pba = make_float2(fb * fa, fa);
 #pragma unroll
             for (int j = 0; j < KO; j++) {
                 const int t = i - j * R;
